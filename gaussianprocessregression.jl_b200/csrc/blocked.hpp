@@ -1,0 +1,137 @@
+// Backend-agnostic blocked (recursive) dense algorithms on an upper-triangular
+// column-major factor.  Everything is expressed through three primitives of a
+// backend BE:
+//
+//   be.gemm(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, flags)
+//   be.potrf_leaf(A, lda, Dinv_blk, global_row_offset)   128x128 diagonal block:
+//        A(upper) <- chol(A) (U^T U = A) and Dinv_blk <- inv(U) (full 128x128, zeros below the diagonal)
+//   be.copy_upper_128(dst, ldd, src128)                  dst(upper part of a 128 block) <- src (ld 128)
+//
+// The product (libgpr_sm100a.so) instantiates this with the CUDA backend
+// (DMMA GEMM + leaf kernels, gpr_api.cu).  tests/hostlogic instantiates it
+// with a plain-loop CPU backend so that the index arithmetic of the
+// recursions is checked in CI without a GPU; that CPU backend is test
+// infrastructure and is never linked into the product library.
+//
+// Replaces the LAPACK calls of the reference path:
+//   dpotrf('U')  /root/reference/src/cost.jl:77,87,104   /root/reference/src/predict.jl:31
+//   dpotrs       /root/reference/src/cost.jl:79,89,106,107-109   /root/reference/src/predict.jl:32
+//   dtrsm(R,U,N) /root/reference/src/predict.jl:84,90
+// and computes K^-1 as trtri + lauum (2N^3/3) instead of potrs on the identity (2N^3).
+//
+// All sizes are multiples of 128 (the library pads to 128 with an identity
+// diagonal).  A triangular factor is addressed as (T, ldt, n, b0): pointer to
+// its top-left element, leading dimension, order, and the index of its first
+// 128-block inside the global factor (selects the Dinv blocks).
+#pragma once
+#include <stdint.h>
+
+namespace gpr {
+
+constexpr int LEAF = 128;
+constexpr int BLK_UPPER_ONLY = 1;   // == GEMM_UPPER_ONLY
+
+template <class BE>
+struct Blocked {
+  BE& be;
+  double* dinv;   // nblocks x (128*128), block b at dinv + b*128*128, ld 128
+
+  Blocked(BE& b, double* d) : be(b), dinv(d) {}
+
+  double* dinv_blk(int64_t b) const { return dinv + b * (int64_t)(LEAF * LEAF); }
+  static int64_t split(int64_t n) { return ((n / LEAF) / 2) * LEAF; }
+
+  // A(upper) <- U with U^T U = A.  A: n x n at the diagonal, global block b0.
+  void potrf(double* A, int64_t ld, int64_t n, int64_t b0) {
+    if (n == LEAF) { be.potrf_leaf(A, ld, dinv_blk(b0), b0 * LEAF); return; }
+    const int64_t n1 = split(n), n2 = n - n1;
+    double* A12 = A + n1 * ld;
+    double* A22 = A + n1 + n1 * ld;
+    potrf(A, ld, n1, b0);
+    trsm_LUT(A, ld, n1, b0, A12, ld, n2, 1.0);
+    be.gemm('T', 'N', n2, n2, n1, -1.0, A12, ld, A12, ld, 1.0, A22, ld, BLK_UPPER_ONLY);
+    potrf(A22, ld, n2, b0 + n1 / LEAF);
+  }
+
+  // B (n x m) <- s * T^-T B,   T upper n x n, s = +-1
+  void trsm_LUT(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m, double s) {
+    if (n == LEAF) { be.gemm('T', 'N', LEAF, m, LEAF, s, dinv_blk(b0), LEAF, B, ldb, 0.0, B, ldb, 0); return; }
+    const int64_t n1 = split(n), n2 = n - n1;
+    const double* Tb = T + n1 * ldt;
+    const double* Tc = T + n1 + n1 * ldt;
+    trsm_LUT(T, ldt, n1, b0, B, ldb, m, s);
+    be.gemm('T', 'N', n2, m, n1, -s, Tb, ldt, B, ldb, 1.0, B + n1, ldb, 0);
+    trsm_LUT(Tc, ldt, n2, b0 + n1 / LEAF, B + n1, ldb, m, s);
+  }
+
+  // B (n x m) <- s * T^-1 B
+  void trsm_LUN(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m, double s) {
+    if (n == LEAF) { be.gemm('N', 'N', LEAF, m, LEAF, s, dinv_blk(b0), LEAF, B, ldb, 0.0, B, ldb, 0); return; }
+    const int64_t n1 = split(n), n2 = n - n1;
+    const double* Tb = T + n1 * ldt;
+    const double* Tc = T + n1 + n1 * ldt;
+    trsm_LUN(Tc, ldt, n2, b0 + n1 / LEAF, B + n1, ldb, m, s);
+    be.gemm('N', 'N', n1, m, n2, -s, Tb, ldt, B + n1, ldb, 1.0, B, ldb, 0);
+    trsm_LUN(T, ldt, n1, b0, B, ldb, m, s);
+  }
+
+  // B (m x n) <- s * B T^-1
+  void trsm_RUN(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m, double s) {
+    if (n == LEAF) { be.gemm('N', 'N', m, LEAF, LEAF, s, B, ldb, dinv_blk(b0), LEAF, 0.0, B, ldb, 0); return; }
+    const int64_t n1 = split(n), n2 = n - n1;
+    const double* Tb = T + n1 * ldt;
+    const double* Tc = T + n1 + n1 * ldt;
+    double* B2 = B + n1 * ldb;
+    trsm_RUN(T, ldt, n1, b0, B, ldb, m, s);
+    be.gemm('N', 'N', m, n2, n1, -s, B, ldb, Tb, ldt, 1.0, B2, ldb, 0);
+    trsm_RUN(Tc, ldt, n2, b0 + n1 / LEAF, B2, ldb, m, s);
+  }
+
+  // B (m x n) <- B T^T,  T upper n x n whose diagonal 128-blocks are the Dinv blocks
+  // (i.e. T is the already inverted factor W = U^-1).
+  void trmm_RUT(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m) {
+    if (n == LEAF) { be.gemm('N', 'T', m, LEAF, LEAF, 1.0, B, ldb, dinv_blk(b0), LEAF, 0.0, B, ldb, 0); return; }
+    const int64_t n1 = split(n), n2 = n - n1;
+    const double* Tb = T + n1 * ldt;
+    const double* Tc = T + n1 + n1 * ldt;
+    double* B2 = B + n1 * ldb;
+    trmm_RUT(T, ldt, n1, b0, B, ldb, m);
+    be.gemm('N', 'T', m, n1, n2, 1.0, B2, ldb, Tb, ldt, 1.0, B, ldb, 0);
+    trmm_RUT(Tc, ldt, n2, b0 + n1 / LEAF, B2, ldb, m);
+  }
+
+  // W(upper) <- inv(U), in place.  Needs the Dinv blocks produced by potrf.
+  void trtri(double* W, int64_t ld, int64_t n, int64_t b0) {
+    if (n == LEAF) { be.copy_upper_128(W, ld, dinv_blk(b0)); return; }
+    const int64_t n1 = split(n), n2 = n - n1;
+    double* W12 = W + n1 * ld;
+    double* W22 = W + n1 + n1 * ld;
+    trsm_LUN(W, ld, n1, b0, W12, ld, n2, 1.0);                     // U11^-1 U12
+    trsm_RUN(W22, ld, n2, b0 + n1 / LEAF, W12, ld, n1, -1.0);      // -(.) U22^-1
+    trtri(W, ld, n1, b0);
+    trtri(W22, ld, n2, b0 + n1 / LEAF);
+  }
+
+  // W(upper) <- W W^T (upper part), in place, W = inv(U) as left by trtri.
+  void lauum(double* W, int64_t ld, int64_t n, int64_t b0) {
+    if (n == LEAF) {
+      be.gemm('N', 'T', LEAF, LEAF, LEAF, 1.0, dinv_blk(b0), LEAF, dinv_blk(b0), LEAF, 0.0, W, ld, BLK_UPPER_ONLY);
+      return;
+    }
+    const int64_t n1 = split(n), n2 = n - n1;
+    double* W12 = W + n1 * ld;
+    double* W22 = W + n1 + n1 * ld;
+    lauum(W, ld, n1, b0);
+    be.gemm('N', 'T', n1, n1, n2, 1.0, W12, ld, W12, ld, 1.0, W, ld, BLK_UPPER_ONLY);
+    trmm_RUT(W22, ld, n2, b0 + n1 / LEAF, W12, ld, n1);
+    lauum(W22, ld, n2, b0 + n1 / LEAF);
+  }
+
+  // B (n x m) <- (U^T U)^-1 B
+  void potrs(const double* U, int64_t ld, int64_t n, double* B, int64_t ldb, int64_t m) {
+    trsm_LUT(U, ld, n, 0, B, ldb, m, 1.0);
+    trsm_LUN(U, ld, n, 0, B, ldb, m, 1.0);
+  }
+};
+
+}  // namespace gpr

@@ -1,0 +1,268 @@
+// FP64 tile GEMM for sm_100a on the DMMA pipe (mma.sync m8n8k4.f64 -> SASS DMMA.8x8x4).
+//
+// This is the work-horse of the factor / solve / inverse path that replaces the
+// reference's LAPACK calls (dpotrf / dpotrs / dtrsm / dsyrk / dgemm; see
+// SURVEY.md 2.3 B1-B3, B8, B9, B11 -> /root/reference/src/cost.jl:77-111,
+// /root/reference/src/predict.jl:29-95, /root/reference/src/split_predict.jl:10-19).
+//
+//   C(MxN) = alpha * op(A)(MxK) * op(B)(KxN) + beta * C          (column major)
+//
+// All dimensions are multiples of the tile (M,N % 128 == 0, K % 16 == 0): the
+// library pads every matrix to 128 (identity on the padded diagonal), so the
+// kernel has no edge handling at all.
+//
+// Operand storage forms (what "contiguous" means in global memory):
+//   A_KC = true  : op(A)[m,k] = A[k + m*lda]   (transA = 'T', k contiguous)
+//   A_KC = false : op(A)[m,k] = A[m + k*lda]   (transA = 'N', m contiguous)
+//   B_KC = true  : op(B)[k,n] = B[k + n*ldb]   (transB = 'N', k contiguous)
+//   B_KC = false : op(B)[k,n] = B[n + k*ldb]   (transB = 'T', n contiguous)
+//
+// CTA tile 128x128x16, 256 threads = 8 warps laid out 2 (m) x 4 (n), warp tile
+// 64x32 = 8x4 DMMA 8x8 accumulator tiles (64 doubles / thread).  Operands are
+// staged global->shared with cp.async (16 B, LDGSTS) through a 4-deep ring and
+// read back as conflict-free LDS.128 fragments:
+//   k-contiguous tile : smem[row][24]  (row stride 24 doubles)
+//   m-contiguous tile : smem[k][130]   (row stride 130 doubles)
+// Inside a k-block of 8 the lane with threadID_in_group t owns k = 2t (first
+// DMMA) and k = 2t+1 (second DMMA) so one LDS.128 feeds two DMMAs; A and B use
+// the same assignment so the contraction is consistent.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpr {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 128;
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_LDK = 24;    // k-contiguous smem row stride (doubles)
+constexpr int GEMM_LDM = 130;   // m-contiguous smem row stride (doubles)
+
+enum GemmFlags : int {
+  GEMM_UPPER_ONLY = 1,   // C is a diagonal-anchored symmetric block: only tiles/elements with row <= col are computed/stored
+};
+
+struct GemmParams {
+  int M, N, K;
+  double alpha, beta;
+  const double* A; long long lda;
+  const double* B; long long ldb;
+  double* C; long long ldc;
+  int flags;
+};
+
+template <bool KC> struct GemmTile {
+  static constexpr int ELEMS = KC ? (128 * GEMM_LDK) : (GEMM_BK * GEMM_LDM);
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// Stage one 128 x 16 operand tile (kt-th k-tile) into shared memory.
+//   KC : element (r,k) at P[k + r*ld]   -> smem[r*LDK + k]
+//   !KC: element (r,k) at P[r + k*ld]   -> smem[k*LDM + r]
+template <bool KC>
+__device__ __forceinline__ void gemm_load_tile(double* smem, const double* __restrict__ P, long long ld,
+                                               int kt, int tid) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int c = tid + GEMM_THREADS * q;
+    if (KC) {
+      int r = c >> 3, kc = c & 7;
+      cp_async16(smem + r * GEMM_LDK + 2 * kc, P + (long long)kt * GEMM_BK + 2 * kc + (long long)r * ld);
+    } else {
+      int k = c >> 6, rc = c & 63;
+      cp_async16(smem + k * GEMM_LDM + 2 * rc, P + 2 * rc + ((long long)kt * GEMM_BK + k) * ld);
+    }
+  }
+}
+
+// Tile-local row of accumulator sub-tile i (0..7) for lane group g (A operand),
+// and tile-local column of accumulator sub-tile j (0..3) for in-tile column q
+// (B operand).  The maps differ per storage form so that fragment loads are
+// LDS.128 and bank-conflict free.
+template <bool KC> __device__ __forceinline__ int gemm_row_of(int wm, int i, int g) {
+  return KC ? (64 * wm + 8 * i + g) : (64 * wm + 16 * (i >> 1) + 2 * g + (i & 1));
+}
+template <bool KC> __device__ __forceinline__ int gemm_col_of(int wn, int j, int q) {
+  return KC ? (32 * wn + 8 * j + q) : (32 * wn + 16 * (j >> 1) + 2 * q + (j & 1));
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmParams p) {
+  extern __shared__ __align__(16) double gemm_smem[];
+  constexpr int SA = GemmTile<A_KC>::ELEMS;
+  constexpr int SB = GemmTile<B_KC>::ELEMS;
+
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  if ((p.flags & GEMM_UPPER_ONLY) && tile_m > tile_n) return;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
+
+  const long long m0 = (long long)tile_m * GEMM_BM, n0 = (long long)tile_n * GEMM_BN;
+  const double* Ap = A_KC ? (p.A + m0 * p.lda) : (p.A + m0);
+  const double* Bp = B_KC ? (p.B + n0 * p.ldb) : (p.B + n0);
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int KT = p.K / GEMM_BK;
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+    if (s < KT) {
+      gemm_load_tile<A_KC>(gemm_smem + s * (SA + SB), Ap, p.lda, s, tid);
+      gemm_load_tile<B_KC>(gemm_smem + s * (SA + SB) + SA, Bp, p.ldb, s, tid);
+    }
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<GEMM_STAGES - 2>();
+    __syncthreads();
+    {
+      int nk = kt + GEMM_STAGES - 1;
+      if (nk < KT) {
+        int s = nk % GEMM_STAGES;
+        gemm_load_tile<A_KC>(gemm_smem + s * (SA + SB), Ap, p.lda, nk, tid);
+        gemm_load_tile<B_KC>(gemm_smem + s * (SA + SB) + SA, Bp, p.ldb, nk, tid);
+      }
+      cp_async_commit();
+    }
+    const double* As = gemm_smem + (kt % GEMM_STAGES) * (SA + SB);
+    const double* Bs = As + SA;
+
+#pragma unroll
+    for (int sp = 0; sp < 2; ++sp) {   // two k-blocks of 8 per 16-wide tile
+      double a[8][2], b[4][2];
+      if (A_KC) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const double2 v = *reinterpret_cast<const double2*>(As + (64 * wm + 8 * i + g) * GEMM_LDK + 8 * sp + 2 * t);
+          a[i][0] = v.x; a[i][1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int pi = 0; pi < 4; ++pi) {
+            const double2 v = *reinterpret_cast<const double2*>(As + (8 * sp + 2 * t + h) * GEMM_LDM + 64 * wm + 16 * pi + 2 * g);
+            a[2 * pi][h] = v.x; a[2 * pi + 1][h] = v.y;
+          }
+      }
+      if (B_KC) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 v = *reinterpret_cast<const double2*>(Bs + (32 * wn + 8 * j + g) * GEMM_LDK + 8 * sp + 2 * t);
+          b[j][0] = v.x; b[j][1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int pj = 0; pj < 2; ++pj) {
+            const double2 v = *reinterpret_cast<const double2*>(Bs + (8 * sp + 2 * t + h) * GEMM_LDM + 32 * wn + 16 * pj + 2 * g);
+            b[2 * pj][h] = v.x; b[2 * pj + 1][h] = v.y;
+          }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i][h], b[j][h]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: C = alpha*acc + beta*C (element (row, col) of the tile lives in
+  // acc[i][j][v] with row = row_of(i,g), col = col_of(j, 2t+v)).
+  const bool diag_tile = (p.flags & GEMM_UPPER_ONLY) && (tile_m == tile_n);
+  const double alpha = p.alpha, beta = p.beta;
+  double* Cp = p.C + m0 + n0 * p.ldc;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int col = gemm_col_of<B_KC>(wn, j, 2 * t + v);
+      double* Ccol = Cp + (long long)col * p.ldc;
+      if (A_KC) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = gemm_row_of<true>(wm, i, g);
+          if (diag_tile && row > col) continue;
+          double r = alpha * acc[i][j][v];
+          if (beta != 0.0) r += beta * Ccol[row];
+          Ccol[row] = r;
+        }
+      } else {
+#pragma unroll
+        for (int pi = 0; pi < 4; ++pi) {
+          const int row = gemm_row_of<false>(wm, 2 * pi, g);   // even row; row+1 is sub-tile 2*pi+1
+          double r0 = alpha * acc[2 * pi][j][v], r1 = alpha * acc[2 * pi + 1][j][v];
+          if (!diag_tile) {
+            double2* ptr = reinterpret_cast<double2*>(Ccol + row);
+            if (beta != 0.0) { const double2 o = *ptr; r0 += beta * o.x; r1 += beta * o.y; }
+            *ptr = make_double2(r0, r1);
+          } else {
+            if (row <= col) { if (beta != 0.0) r0 += beta * Ccol[row]; Ccol[row] = r0; }
+            if (row + 1 <= col) { if (beta != 0.0) r1 += beta * Ccol[row + 1]; Ccol[row + 1] = r1; }
+          }
+        }
+      }
+    }
+}
+
+template <bool A_KC, bool B_KC> constexpr size_t gemm_smem_bytes() {
+  return (size_t)GEMM_STAGES * (GemmTile<A_KC>::ELEMS + GemmTile<B_KC>::ELEMS) * sizeof(double);
+}
+
+// transA/transB: 'N' or 'T' (BLAS meaning, column major).  Supported: TN, NN, NT.
+inline cudaError_t launch_dgemm128(cudaStream_t st, char transA, char transB, int M, int N, int K, double alpha,
+                                   const double* A, long long lda, const double* B, long long ldb, double beta,
+                                   double* C, long long ldc, int flags) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if ((M % GEMM_BM) || (N % GEMM_BN) || (K % GEMM_BK) || K <= 0) return cudaErrorInvalidValue;
+  GemmParams p{M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, flags};
+  dim3 grid(M / GEMM_BM, N / GEMM_BN), block(GEMM_THREADS);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(dgemm128_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<true, true>());
+    cudaFuncSetAttribute(dgemm128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<false, true>());
+    cudaFuncSetAttribute(dgemm128_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<false, false>());
+    attr_done = true;
+  }
+  const bool aT = (transA == 'T' || transA == 't'), bT = (transB == 'T' || transB == 't');
+  if (aT && !bT)
+    dgemm128_kernel<true, true><<<grid, block, gemm_smem_bytes<true, true>(), st>>>(p);
+  else if (!aT && !bT)
+    dgemm128_kernel<false, true><<<grid, block, gemm_smem_bytes<false, true>(), st>>>(p);
+  else if (!aT && bT)
+    dgemm128_kernel<false, false><<<grid, block, gemm_smem_bytes<false, false>(), st>>>(p);
+  else
+    return cudaErrorNotSupported;
+  return cudaGetLastError();
+}
+
+}  // namespace gpr

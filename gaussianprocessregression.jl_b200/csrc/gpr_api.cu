@@ -1,0 +1,1054 @@
+// libgpr_sm100a.so: C ABI (include/gpr_sm100a.h) over the sm_100a kernels.
+// Host orchestration only; all arithmetic is in the kernels of this directory.
+// There is deliberately no CPU path: without a usable CUDA device every entry
+// point fails with GPR_ERR_CUDA.
+#include "../../include/gpr_sm100a.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "blocked.hpp"
+#include "cov_kernels.cuh"
+#include "dgemm_sm100.cuh"
+#include "leaf_kernels.cuh"
+
+using namespace gpr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+struct Timer {
+  cudaEvent_t beg[GPR_T_COUNT], end[GPR_T_COUNT];
+  bool used[GPR_T_COUNT];
+  double acc_ms[GPR_T_COUNT];
+};
+
+}  // namespace
+
+struct gpr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 0;
+  int64_t predict_tile = 8192;
+  long long launches = 0;
+  long long* d_info = nullptr;
+  cudaError_t pending = cudaSuccess;   // first launch error seen by the backend
+};
+
+namespace {
+
+int fail(gpr_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return code;
+}
+int fail_cuda(gpr_ctx* ctx, cudaError_t e, const char* what, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s [gpr_api.cu:%d]", (int)e, cudaGetErrorString(e), what, line);
+  return fail(ctx, e == cudaErrorMemoryAllocation ? GPR_ERR_MEMORY : GPR_ERR_CUDA, buf);
+}
+#define CK(call)                                                              \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call, __LINE__);        \
+  } while (0)
+
+// CUDA backend of csrc/blocked.hpp
+struct CudaBE {
+  gpr_ctx* ctx;
+  void note(cudaError_t e) { if (e != cudaSuccess && ctx->pending == cudaSuccess) ctx->pending = e; }
+  void gemm(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+            const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags) {
+    note(launch_dgemm128(ctx->stream, tA, tB, (int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, flags));
+    ctx->launches++;
+  }
+  void potrf_leaf(double* A, int64_t lda, double* dinv, int64_t goff) {
+    potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, ctx->stream>>>(A, lda, dinv, ctx->d_info, goff);
+    note(cudaGetLastError());
+    ctx->launches++;
+  }
+  void copy_upper_128(double* dst, int64_t ldd, const double* src) {
+    copy_upper_128_kernel<<<1, 256, 0, ctx->stream>>>(dst, ldd, src);
+    note(cudaGetLastError());
+    ctx->launches++;
+  }
+};
+
+int setup_kernel_attributes(gpr_ctx* ctx) {
+  CK(cudaFuncSetAttribute(dgemm128_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<true, true>()));
+  CK(cudaFuncSetAttribute(dgemm128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<false, true>()));
+  CK(cudaFuncSetAttribute(dgemm128_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<false, false>()));
+  CK(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(kbuild_kernel<DM_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(kbuild_kernel<DM_SPLIT_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(kbuild_kernel<DM_SPLIT_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(grad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  return GPR_OK;
+}
+
+int make_spec(gpr_ctx* ctx, const int* types, int ncomp, int D, KSpec* spec, int* P_out, int* nk_out) {
+  if (!types || ncomp < 1 || ncomp > KSPEC_MAXC) return fail(ctx, GPR_ERR_ARG, "ncomp must be in 1..8");
+  if (D < 1) return fail(ctx, GPR_ERR_ARG, "D must be >= 1");
+  int off = 0, nk = 0;
+  spec->ncomp = ncomp;
+  for (int c = 0; c < KSPEC_MAXC; ++c) { spec->type[c] = 0; spec->hp_off[c] = 0; }
+  for (int c = 0; c < ncomp; ++c) {
+    spec->type[c] = types[c];
+    spec->hp_off[c] = off;
+    if (types[c] == GPR_KERN_SE || types[c] == GPR_KERN_MATERN52) { off += D + 1; nk++; }
+    else if (types[c] == GPR_KERN_NOISE) off += 1;
+    else return fail(ctx, GPR_ERR_ARG, "unknown kernel component type");
+  }
+  if (nk == 0) return fail(ctx, GPR_ERR_ARG, "covariance needs at least one non-noise component");
+  if (P_out) *P_out = off;
+  if (nk_out) *nk_out = nk;
+  return GPR_OK;
+}
+
+// covariance build launcher
+int launch_kbuild(gpr_ctx* ctx, int mode, const KBuildArgs& a) {
+  int nk = 0;
+  for (int c = 0; c < a.spec.ncomp; ++c) if (a.spec.type[c] != KT_NOISE) nk++;
+  const size_t smem = (size_t)2 * nk * a.D * KB_TILE * sizeof(double);
+  if (smem > 200 * 1024) return fail(ctx, GPR_ERR_UNSUPPORTED, "covariance build: (#components x D) too large for shared memory");
+  dim3 grid((unsigned)((a.Rp + KB_TILE - 1) / KB_TILE), (unsigned)((a.Cp + KB_TILE - 1) / KB_TILE));
+  if (grid.y > 65535) return fail(ctx, GPR_ERR_UNSUPPORTED, "covariance build: too many column tiles");
+  if (mode == DM_EUCLID) kbuild_kernel<DM_EUCLID><<<grid, KB_THREADS, smem, ctx->stream>>>(a);
+  else if (mode == DM_SPLIT_A) kbuild_kernel<DM_SPLIT_A><<<grid, KB_THREADS, smem, ctx->stream>>>(a);
+  else kbuild_kernel<DM_SPLIT_C><<<grid, KB_THREADS, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return GPR_OK;
+}
+
+struct DevBuf {
+  double* p = nullptr;
+  size_t n = 0;   // elements
+};
+
+}  // namespace
+
+struct gpr_model {
+  gpr_ctx* ctx = nullptr;
+  KSpec spec;
+  std::vector<int> types;
+  int ncomp = 0, D = 0, P = 0, nk = 0, ny = 1, train_axis = 1;
+  int64_t N = 0, Np = 0, nyp = 128;
+  double* d_x = nullptr;      // D x N
+  double* d_y = nullptr;      // N x ny
+  double* d_hp = nullptr;     // P
+  double* d_U = nullptr;      // Np x Np: upper = U, strict lower = K
+  double* d_Kinv = nullptr;   // Np x Np upper = K^-1 (may alias d_U when memory is short)
+  double* d_dinv = nullptr;   // Np/128 blocks of 128x128
+  double* d_wt = nullptr;     // Np x nyp : K^-1 y (all columns), zero padded
+  double* d_scal = nullptr;   // [logdet, y.alpha]
+  double* d_G = nullptr;      // P
+  double* d_gpart = nullptr;  // grad partials
+  int gr_blocks = 0;
+  bool kinv_alias = false;
+  // state
+  bool have_factor = false, have_inverse = false, factor_destroyed = false, kinv_symmetric = false;
+  std::vector<double> hp_host;
+  double eps_host = 0.0;
+  int64_t info_host = 0;
+  // predict workspaces (lazy)
+  DevBuf w_kxp, w_xp, w_part, w_mean, w_var;
+  Timer tm;
+};
+
+namespace {
+
+void timer_init(Timer& t) {
+  for (int i = 0; i < GPR_T_COUNT; ++i) {
+    cudaEventCreate(&t.beg[i]); cudaEventCreate(&t.end[i]);
+    t.used[i] = false; t.acc_ms[i] = 0.0;
+  }
+}
+void timer_free(Timer& t) {
+  for (int i = 0; i < GPR_T_COUNT; ++i) { cudaEventDestroy(t.beg[i]); cudaEventDestroy(t.end[i]); }
+}
+void timer_reset(Timer& t) { for (int i = 0; i < GPR_T_COUNT; ++i) { t.used[i] = false; t.acc_ms[i] = 0.0; } }
+// accumulate a previously recorded slot (needs the events to have completed)
+void timer_collect(Timer& t, int slot) {
+  if (!t.used[slot]) return;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, t.beg[slot], t.end[slot]) == cudaSuccess) t.acc_ms[slot] += ms;
+  t.used[slot] = false;
+}
+struct Scope {
+  Timer& t; int slot; cudaStream_t st;
+  Scope(Timer& t_, int s, cudaStream_t st_) : t(t_), slot(s), st(st_) {
+    if (t.used[slot]) { cudaEventSynchronize(t.end[slot]); timer_collect(t, slot); }
+    cudaEventRecord(t.beg[slot], st);
+  }
+  ~Scope() { cudaEventRecord(t.end[slot], st); t.used[slot] = true; }
+};
+
+int ensure(gpr_ctx* ctx, DevBuf& b, size_t elems) {
+  if (b.n >= elems && b.p) return GPR_OK;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.n = 0; }
+  CK(cudaMalloc(&b.p, elems * sizeof(double)));
+  b.n = elems;
+  return GPR_OK;
+}
+
+int check_pending(gpr_ctx* ctx, const char* where) {
+  if (ctx->pending != cudaSuccess) {
+    cudaError_t e = ctx->pending; ctx->pending = cudaSuccess;
+    return fail_cuda(ctx, e, where, __LINE__);
+  }
+  return GPR_OK;
+}
+
+// K (+ noise, + jitter, identity padding) into m->d_U, then blocked potrf; solves for all y columns.
+int factor_and_solve(gpr_model* m, const double* hp, double eps, int64_t* info) {
+  gpr_ctx* ctx = m->ctx;
+  const int64_t N = m->N, Np = m->Np;
+  CK(cudaMemcpyAsync(m->d_hp, hp, sizeof(double) * m->P, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_info, 0, sizeof(long long), ctx->stream));
+  {
+    Scope s(m->tm, GPR_T_KBUILD, ctx->stream);
+    KBuildArgs a{};
+    a.out = m->d_U; a.ldo = Np; a.R = N; a.C = N; a.Rp = Np; a.Cp = Np;
+    a.x1 = m->d_x; a.x2 = m->d_x; a.D = m->D; a.hp = m->d_hp; a.spec = m->spec;
+    a.eps = eps; a.same = 1; a.add_noise = 1; a.pad_identity = 1; a.sigma_one = 0; a.row_scale = nullptr; a.diag_shift = 0;
+    int rc = launch_kbuild(ctx, DM_EUCLID, a);
+    if (rc) return rc;
+  }
+  CudaBE be{ctx};
+  Blocked<CudaBE> blk(be, m->d_dinv);
+  {
+    Scope s(m->tm, GPR_T_POTRF, ctx->stream);
+    blk.potrf(m->d_U, Np, Np, 0);
+  }
+  {
+    Scope s(m->tm, GPR_T_POTRS, ctx->stream);
+    const int threads = 256;
+    const int64_t total = Np * m->nyp;
+    int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 65535);
+    pad_copy_kernel<<<blocks, threads, 0, ctx->stream>>>(m->d_wt, Np, Np, m->nyp, m->d_y, N, N, m->ny);
+    ctx->launches++;
+    blk.potrs(m->d_U, Np, Np, m->d_wt, Np, m->nyp);
+    const double* alpha = m->d_wt + (int64_t)(m->train_axis - 1) * Np;
+    const double* ycol = m->d_y + (int64_t)(m->train_axis - 1) * N;
+    logdet_dot_kernel<<<1, 1024, 0, ctx->stream>>>(m->d_U, Np, N, ycol, alpha, m->d_scal);
+    ctx->launches++;
+  }
+  long long h_info = 0;
+  CK(cudaMemcpyAsync(&h_info, ctx->d_info, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int rc = check_pending(ctx, "factor_and_solve");
+  if (rc) return rc;
+  m->info_host = h_info;
+  if (info) *info = h_info;
+  m->have_factor = (h_info == 0);
+  m->have_inverse = false;
+  m->factor_destroyed = false;
+  m->kinv_symmetric = false;
+  if (h_info != 0) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "matrix is not positive definite; Cholesky failed at pivot %lld", h_info);
+    return fail(ctx, GPR_ERR_NOT_POSDEF, buf);
+  }
+  return GPR_OK;
+}
+
+int form_inverse(gpr_model* m) {
+  gpr_ctx* ctx = m->ctx;
+  const int64_t Np = m->Np;
+  if (!m->d_Kinv) {
+    cudaError_t e = cudaMalloc(&m->d_Kinv, sizeof(double) * Np * Np);
+    if (e != cudaSuccess) {   // not enough memory for a second N x N: invert in place (destroys U)
+      cudaGetLastError();
+      m->d_Kinv = m->d_U;
+      m->kinv_alias = true;
+    }
+  }
+  CudaBE be{ctx};
+  Blocked<CudaBE> blk(be, m->d_dinv);
+  {
+    Scope s(m->tm, GPR_T_TRTRI, ctx->stream);
+    if (!m->kinv_alias) CK(cudaMemcpyAsync(m->d_Kinv, m->d_U, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, ctx->stream));
+    else m->factor_destroyed = true;
+    blk.trtri(m->d_Kinv, Np, Np, 0);
+  }
+  {
+    Scope s(m->tm, GPR_T_LAUUM, ctx->stream);
+    blk.lauum(m->d_Kinv, Np, Np, 0);
+  }
+  m->have_inverse = true;
+  m->kinv_symmetric = false;
+  return check_pending(ctx, "form_inverse");
+}
+
+int compute_grad(gpr_model* m, int log_scale, double* G_host) {
+  gpr_ctx* ctx = m->ctx;
+  if (!m->have_inverse) return fail(ctx, GPR_ERR_STATE, "grad: cache holds no K^-1 (call gpr_update_cache with want_inverse = 1)");
+  {
+    Scope s(m->tm, GPR_T_GRAD, ctx->stream);
+    GradArgs a{};
+    a.Kinv = m->d_Kinv; a.ld = m->Np; a.alpha = m->d_wt + (int64_t)(m->train_axis - 1) * m->Np;
+    a.x = m->d_x; a.D = m->D; a.N = m->N; a.hp = m->d_hp; a.spec = m->spec; a.P = m->P; a.eps = m->eps_host;
+    a.partial = m->d_gpart;
+    const size_t smem = ((size_t)(m->P + 1) * GR_THREADS + 2 * (size_t)m->D * GR_TILE + 2 * GR_TILE) * sizeof(double);
+    grad_reduce_kernel<<<m->gr_blocks, GR_THREADS, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    grad_finalize_kernel<<<1, 256, 0, ctx->stream>>>(m->d_gpart, m->gr_blocks, m->P, m->d_hp, m->spec, m->D, log_scale, m->d_G);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(G_host, m->d_G, sizeof(double) * m->P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GPR_OK;
+}
+
+int compute_loss(gpr_model* m, double* F) {
+  gpr_ctx* ctx = m->ctx;
+  if (!m->have_factor) return fail(ctx, GPR_ERR_STATE, "loss: no valid factorization in the cache");
+  double sc[2];
+  CK(cudaMemcpyAsync(sc, m->d_scal, sizeof sc, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // 0.5 * (dot(y, K^-1 y) + logdet(K) + N log(2 pi))   (src/loss_grad.jl:40)
+  *F = 0.5 * (sc[1] + sc[0] + (double)m->N * std::log(2.0 * M_PI));
+  return GPR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpr_version(void) { return 100; }
+
+int gpr_ctx_create(int device, gpr_ctx** out) {
+  gpr_ctx* ctx = nullptr;
+  if (!out) return fail(nullptr, GPR_ERR_ARG, "ctx out pointer is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, GPR_ERR_CUDA, std::string("no CUDA device available (libgpr_sm100a has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, GPR_ERR_ARG, "device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, GPR_ERR_CUDA, "libgpr_sm100a.so is built for sm_100a only; device compute capability is " +
+                                           std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  ctx = new gpr_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete ctx; return fail_cuda(nullptr, e, "cudaStreamCreate", __LINE__); }
+  e = cudaMalloc(&ctx->d_info, sizeof(long long));
+  if (e != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return fail_cuda(nullptr, e, "cudaMalloc", __LINE__); }
+  int rc = setup_kernel_attributes(ctx);
+  if (rc) { g_create_error = ctx->err; cudaFree(ctx->d_info); cudaStreamDestroy(ctx->stream); delete ctx; return rc; }
+  *out = ctx;
+  return GPR_OK;
+}
+
+int gpr_ctx_destroy(gpr_ctx* ctx) {
+  if (!ctx) return GPR_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_info);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GPR_OK;
+}
+
+const char* gpr_last_error(gpr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return GPR_ERR_ARG;
+  if (!strcmp(name, "predict_tile")) {
+    if (value < 128) return fail(ctx, GPR_ERR_ARG, "predict_tile must be >= 128");
+    ctx->predict_tile = round_up(value, 128);
+    return GPR_OK;
+  }
+  return fail(ctx, GPR_ERR_ARG, std::string("unknown option ") + name);
+}
+
+int64_t gpr_ctx_launch_count(gpr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gpr_dim_hp(const int* comp_types, int ncomp, int D) {
+  int P = 0;
+  for (int c = 0; c < ncomp; ++c) {
+    if (comp_types[c] == GPR_KERN_SE || comp_types[c] == GPR_KERN_MATERN52) P += D + 1;
+    else if (comp_types[c] == GPR_KERN_NOISE) P += 1;
+    else return GPR_ERR_ARG;
+  }
+  return P;
+}
+
+int gpr_model_create(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, int64_t N, const double* x, const double* y,
+                     int ny, int train_axis, gpr_model** out) {
+  if (!ctx) return GPR_ERR_ARG;
+  if (!out || !x || !y) return fail(ctx, GPR_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (N < 1) return fail(ctx, GPR_ERR_ARG, "x and y size mismatch.");
+  if (ny < 1 || train_axis < 1 || train_axis > ny) return fail(ctx, GPR_ERR_ARG, "train_axis out of range");
+  CK(cudaSetDevice(ctx->device));
+  gpr_model* m = new gpr_model();
+  m->ctx = ctx;
+  int rc = make_spec(ctx, comp_types, ncomp, D, &m->spec, &m->P, &m->nk);
+  if (rc) { delete m; return rc; }
+  if (m->P > 90) { delete m; return fail(ctx, GPR_ERR_UNSUPPORTED, "more than 90 hyper-parameters are not supported"); }
+  timer_init(m->tm);
+  m->types.assign(comp_types, comp_types + ncomp);
+  m->ncomp = ncomp; m->D = D; m->N = N; m->Np = round_up(N, 128); m->ny = ny; m->train_axis = train_axis;
+  m->nyp = round_up(ny, 128);
+  const int64_t Np = m->Np;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](double** p, size_t elems) { if (e == cudaSuccess) e = cudaMalloc(p, elems * sizeof(double)); };
+  A(&m->d_x, (size_t)D * N);
+  A(&m->d_y, (size_t)N * ny);
+  A(&m->d_hp, (size_t)m->P);
+  A(&m->d_U, (size_t)Np * Np);
+  A(&m->d_dinv, (size_t)Np * 128);
+  A(&m->d_wt, (size_t)Np * m->nyp);
+  A(&m->d_scal, 2);
+  A(&m->d_G, (size_t)m->P);
+  const int64_t T = (N + GR_TILE - 1) / GR_TILE;
+  m->gr_blocks = (int)std::min<int64_t>(T * (T + 1) / 2, (int64_t)ctx->sm_count * 4);
+  A(&m->d_gpart, (size_t)m->gr_blocks * (m->P + 1));
+  if (e != cudaSuccess) { gpr_model_destroy(m); return fail_cuda(ctx, e, "cudaMalloc(model)", __LINE__); }
+  e = cudaMemcpyAsync(m->d_x, x, sizeof(double) * D * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_y, y, sizeof(double) * N * ny, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { gpr_model_destroy(m); return fail_cuda(ctx, e, "upload x,y", __LINE__); }
+  *out = m;
+  return GPR_OK;
+}
+
+int gpr_model_destroy(gpr_model* m) {
+  if (!m) return GPR_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->d_x); cudaFree(m->d_y); cudaFree(m->d_hp); cudaFree(m->d_U);
+  if (m->d_Kinv && !m->kinv_alias) cudaFree(m->d_Kinv);
+  cudaFree(m->d_dinv); cudaFree(m->d_wt); cudaFree(m->d_scal); cudaFree(m->d_G); cudaFree(m->d_gpart);
+  cudaFree(m->w_kxp.p); cudaFree(m->w_xp.p); cudaFree(m->w_part.p); cudaFree(m->w_mean.p); cudaFree(m->w_var.p);
+  timer_free(m->tm);
+  delete m;
+  return GPR_OK;
+}
+
+int gpr_model_set_y(gpr_model* m, const double* y) {
+  if (!m || !y) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(m->d_y, y, sizeof(double) * m->N * m->ny, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  m->have_factor = m->have_inverse = false;
+  m->hp_host.clear();
+  return GPR_OK;
+}
+
+int gpr_model_set_x(gpr_model* m, const double* x) {
+  if (!m || !x) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(m->d_x, x, sizeof(double) * m->N * m->D, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  m->have_factor = m->have_inverse = false;
+  m->hp_host.clear();
+  return GPR_OK;
+}
+
+int gpr_kernel(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, const double* hp, const double* x, int64_t N,
+               const double* xp, int64_t M, int same_x, double eps, int add_noise, double* out) {
+  if (!ctx) return GPR_ERR_ARG;
+  if (!hp || !x || !xp || !out || N < 1 || M < 1) return fail(ctx, GPR_ERR_ARG, "NULL or empty argument");
+  if (same_x && N != M) return fail(ctx, GPR_ERR_ARG, "same_x requires N == M");
+  CK(cudaSetDevice(ctx->device));
+  KSpec spec; int P = 0, nk = 0;
+  int rc = make_spec(ctx, comp_types, ncomp, D, &spec, &P, &nk);
+  if (rc) return rc;
+  double *d_x = nullptr, *d_xp = nullptr, *d_hp = nullptr, *d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_x, sizeof(double) * D * N);
+  if (e == cudaSuccess && !same_x) e = cudaMalloc(&d_xp, sizeof(double) * D * M);
+  if (e == cudaSuccess) e = cudaMalloc(&d_hp, sizeof(double) * P);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * N * M);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, x, sizeof(double) * D * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && !same_x) e = cudaMemcpyAsync(d_xp, xp, sizeof(double) * D * M, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_hp, hp, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream);
+  rc = GPR_OK;
+  if (e == cudaSuccess) {
+    KBuildArgs a{};
+    a.out = d_out; a.ldo = N; a.R = N; a.C = M; a.Rp = N; a.Cp = M;
+    a.x1 = d_x; a.x2 = same_x ? d_x : d_xp; a.D = D; a.hp = d_hp; a.spec = spec;
+    a.eps = eps; a.same = same_x; a.add_noise = add_noise; a.pad_identity = 0; a.sigma_one = 0; a.row_scale = nullptr; a.diag_shift = 0;
+    rc = launch_kbuild(ctx, DM_EUCLID, a);
+    if (!rc) e = cudaMemcpyAsync(out, d_out, sizeof(double) * N * M, cudaMemcpyDeviceToHost, ctx->stream);
+    if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(d_x); cudaFree(d_xp); cudaFree(d_hp); cudaFree(d_out);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "gpr_kernel", __LINE__);
+  return GPR_OK;
+}
+
+int gpr_kernel_grad(gpr_ctx* ctx, int comp_type, int D, const double* hp_comp, const double* x, int64_t N, int li,
+                    double eps, double* out) {
+  if (!ctx) return GPR_ERR_ARG;
+  if (!hp_comp || !x || !out || N < 1) return fail(ctx, GPR_ERR_ARG, "NULL or empty argument");
+  if (comp_type != GPR_KERN_SE && comp_type != GPR_KERN_MATERN52) return fail(ctx, GPR_ERR_ARG, "gpr_kernel_grad: dense derivative exists for SE / Matern52 only");
+  if (li < 0 || li > D) return fail(ctx, GPR_ERR_ARG, "hyper-parameter index out of range");
+  CK(cudaSetDevice(ctx->device));
+  double *d_x = nullptr, *d_hp = nullptr, *d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_x, sizeof(double) * D * N);
+  if (e == cudaSuccess) e = cudaMalloc(&d_hp, sizeof(double) * (D + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * N * N);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, x, sizeof(double) * D * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_hp, hp_comp, sizeof(double) * (D + 1), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    KGradArgs a{d_out, N, N, d_x, D, d_hp, comp_type, li, eps};
+    const int64_t total = N * N;
+    int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+    kgrad_dense_kernel<<<blocks, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * N * N, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(d_x); cudaFree(d_hp); cudaFree(d_out);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "gpr_kernel_grad", __LINE__);
+  return GPR_OK;
+}
+
+int gpr_update_cache(gpr_model* m, const double* hp, int P, double eps, int want_inverse, int64_t* info) {
+  if (!m) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  if (!hp) return fail(ctx, GPR_ERR_ARG, "hp is NULL");
+  if (P != m->P) return fail(ctx, GPR_ERR_ARG, "Parameter size mismatch.");
+  CK(cudaSetDevice(ctx->device));
+  if (info) *info = 0;
+  // same hp as the cached evaluation: reuse (SecondOrder optimisers call loss and grad! separately, src/train.jl:58-87)
+  const bool same_hp = m->have_factor && !m->factor_destroyed && m->hp_host.size() == (size_t)P && m->eps_host == eps &&
+                       std::equal(hp, hp + P, m->hp_host.begin());
+  if (!same_hp) {
+    timer_reset(m->tm);
+    Scope total(m->tm, GPR_T_TOTAL, ctx->stream);
+    m->hp_host.assign(hp, hp + P);
+    m->eps_host = eps;
+    int rc = factor_and_solve(m, hp, eps, info);
+    if (rc) { m->hp_host.clear(); return rc; }
+    if (want_inverse) { rc = form_inverse(m); if (rc) { m->hp_host.clear(); return rc; } }
+  } else if (want_inverse && !m->have_inverse) {
+    int rc = form_inverse(m);
+    if (rc) return rc;
+  }
+  return GPR_OK;
+}
+
+int gpr_loss(gpr_model* m, double* F) {
+  if (!m || !F) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  CK(cudaSetDevice(ctx->device));
+  return compute_loss(m, F);
+}
+
+int gpr_grad(gpr_model* m, int log_scale, double* G) {
+  if (!m || !G) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  CK(cudaSetDevice(ctx->device));
+  return compute_grad(m, log_scale, G);
+}
+
+int gpr_nlml_grad(gpr_model* m, const double* hp_in, int P, int log_scale, double eps, double* F, double* G,
+                  int64_t* info) {
+  if (!m) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  if (!hp_in) return fail(ctx, GPR_ERR_ARG, "hp is NULL");
+  if (P != m->P) return fail(ctx, GPR_ERR_ARG, "Parameter size mismatch.");
+  std::vector<double> hp(hp_in, hp_in + P);
+  if (log_scale) for (auto& v : hp) v = std::exp(v);   // hp = exp.(log_hp)  (src/cost.jl:61)
+  int rc = gpr_update_cache(m, hp.data(), P, eps, G != nullptr, info);
+  if (rc) return rc;
+  if (G) { rc = compute_grad(m, log_scale, G); if (rc) return rc; }
+  if (F) { rc = compute_loss(m, F); if (rc) return rc; }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GPR_OK;
+}
+
+int gpr_fetch(gpr_model* m, int which, double* out) {
+  if (!m || !out) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  CK(cudaSetDevice(ctx->device));
+  const int64_t N = m->N, Np = m->Np;
+  if (which == GPR_FETCH_U) {
+    if (!m->have_factor || m->factor_destroyed) return fail(ctx, GPR_ERR_STATE, "fetch U: no factorization in the cache");
+    CK(cudaMemcpy2DAsync(out, sizeof(double) * N, m->d_U, sizeof(double) * Np, sizeof(double) * N, N, cudaMemcpyDeviceToHost, ctx->stream));
+  } else if (which == GPR_FETCH_ALPHA) {
+    if (!m->have_factor) return fail(ctx, GPR_ERR_STATE, "fetch alpha: no factorization in the cache");
+    CK(cudaMemcpyAsync(out, m->d_wt + (int64_t)(m->train_axis - 1) * Np, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  } else if (which == GPR_FETCH_WT) {
+    if (!m->have_factor) return fail(ctx, GPR_ERR_STATE, "fetch wt: no factorization in the cache");
+    CK(cudaMemcpy2DAsync(out, sizeof(double) * N, m->d_wt, sizeof(double) * Np, sizeof(double) * N, m->ny, cudaMemcpyDeviceToHost, ctx->stream));
+  } else if (which == GPR_FETCH_KINV) {
+    if (!m->have_inverse) return fail(ctx, GPR_ERR_STATE, "fetch K^-1: cache holds no inverse");
+    if (!m->kinv_symmetric) {
+      dim3 grid((unsigned)((Np + 31) / 32), (unsigned)((Np + 31) / 32)), block(32, 8);
+      symmetrize_from_upper_kernel<<<grid, block, 0, ctx->stream>>>(m->d_Kinv, Np, Np);
+      ctx->launches++;
+      CK(cudaGetLastError());
+      m->kinv_symmetric = true;
+    }
+    CK(cudaMemcpy2DAsync(out, sizeof(double) * N, m->d_Kinv, sizeof(double) * Np, sizeof(double) * N, N, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    return fail(ctx, GPR_ERR_ARG, "unknown fetch selector");
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GPR_OK;
+}
+
+int gpr_timings(gpr_model* m, double* ms, int n) {
+  if (!m || !ms) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < GPR_T_COUNT; ++i) timer_collect(m->tm, i);
+  for (int i = 0; i < n && i < GPR_T_COUNT; ++i) ms[i] = m->tm.acc_ms[i];
+  return GPR_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// prediction
+// ---------------------------------------------------------------------------
+namespace {
+
+double prior_diag(const gpr_model* m) {
+  // sum over ALL components (noise included) of hp_c[1]^2, no jitter (src/predict.jl:55-58,67)
+  double s = 0.0;
+  for (int c = 0; c < m->ncomp; ++c) { const double v = m->hp_host[m->spec.hp_off[c]]; s += v * v; }
+  return s;
+}
+
+// Launch the streaming row reduction of K (rows_pad x cols, ld) into out[0..rows_valid)
+int row_reduce(gpr_model* m, int mode, const double* K, int64_t ld, int64_t rows_pad, int64_t rows_valid, int64_t cols,
+               const double* w, double base, double sign, double* out) {
+  gpr_ctx* ctx = m->ctx;
+  const int64_t row_ctas = rows_pad / 128;
+  int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 16 / std::max<int64_t>(row_ctas, 1), cols / 64));
+  if (nsplit < 1) nsplit = 1;
+  const int64_t cps = (cols + nsplit - 1) / nsplit;
+  nsplit = (int)((cols + cps - 1) / cps);
+  int rc = ensure(ctx, m->w_part, (size_t)nsplit * rows_pad);
+  if (rc) return rc;
+  dim3 grid((unsigned)row_ctas, (unsigned)nsplit);
+  if (mode == 0) rowreduce_kernel<0><<<grid, 64, 0, ctx->stream>>>(K, ld, rows_pad, cols, cps, w, m->w_part.p);
+  else rowreduce_kernel<1><<<grid, 64, 0, ctx->stream>>>(K, ld, rows_pad, cols, cps, w, m->w_part.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  rowreduce_finalize_kernel<<<(unsigned)((rows_valid + 255) / 256), 256, 0, ctx->stream>>>(m->w_part.p, nsplit, rows_pad, rows_valid, base, sign, out);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return GPR_OK;
+}
+
+// One tile of test points resident on the device: d_xp is D x mt (mt valid points, global index m0..m0+mt).
+// Writes mean (mt x ny, column stride ldmean) and var (mt) to device memory.
+int predict_tile(gpr_model* m, const double* d_xp, int64_t mt, int64_t m0, int same_x, double* d_mean, int64_t ldmean,
+                 double* d_var) {
+  gpr_ctx* ctx = m->ctx;
+  const int64_t Np = m->Np, N = m->N;
+  const int64_t mtp = round_up(mt, 128);
+  int rc = ensure(ctx, m->w_kxp, (size_t)mtp * Np);
+  if (rc) return rc;
+  double* Kxp = m->w_kxp.p;
+  {
+    Scope s(m->tm, GPR_T_PRED_KSTAR, ctx->stream);
+    KBuildArgs a{};
+    a.out = Kxp; a.ldo = mtp; a.R = mt; a.C = N; a.Rp = mtp; a.Cp = Np;
+    a.x1 = d_xp; a.x2 = m->d_x; a.D = m->D; a.hp = m->d_hp; a.spec = m->spec;
+    a.eps = m->eps_host; a.same = same_x; a.add_noise = 0; a.pad_identity = 0; a.sigma_one = 0; a.row_scale = nullptr;
+    a.diag_shift = -m0;
+    rc = launch_kbuild(ctx, DM_EUCLID, a);
+    if (rc) return rc;
+  }
+  {
+    Scope s(m->tm, GPR_T_PRED_MEAN, ctx->stream);
+    for (int e = 0; e < m->ny; ++e) {
+      rc = row_reduce(m, 0, Kxp, mtp, mtp, mt, N, m->d_wt + (int64_t)e * Np, 0.0, 1.0, d_mean + (int64_t)e * ldmean);
+      if (rc) return rc;
+    }
+  }
+  if (d_var) {
+    CudaBE be{ctx};
+    Blocked<CudaBE> blk(be, m->d_dinv);
+    {
+      Scope s(m->tm, GPR_T_PRED_TRSM, ctx->stream);
+      blk.trsm_RUN(m->d_U, Np, Np, 0, Kxp, mtp, mtp, 1.0);   // Kxp <- Kxp U^-1  (rdiv!, src/predict.jl:90)
+    }
+    {
+      Scope s(m->tm, GPR_T_PRED_ROWNORM, ctx->stream);
+      rc = row_reduce(m, 1, Kxp, mtp, mtp, mt, Np, nullptr, prior_diag(m), -1.0, d_var);
+      if (rc) return rc;
+    }
+  }
+  return check_pending(ctx, "predict_tile");
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpr_predict_device(gpr_model* m, const double* d_xp, int64_t M, int same_x, double* d_mean, double* d_var) {
+  if (!m) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  if (!d_xp || !d_mean || M < 1) return fail(ctx, GPR_ERR_ARG, "NULL or empty argument");
+  if (!m->have_factor || m->factor_destroyed) return fail(ctx, GPR_ERR_STATE, "predict: call gpr_update_cache first");
+  if (same_x && M != m->N) return fail(ctx, GPR_ERR_ARG, "same_x requires M == N");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t MT = ctx->predict_tile;
+  for (int64_t m0 = 0; m0 < M; m0 += MT) {
+    const int64_t mt = std::min(MT, M - m0);
+    int rc = predict_tile(m, d_xp + m0 * m->D, mt, m0, same_x, d_mean + m0, M, d_var ? d_var + m0 : nullptr);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GPR_OK;
+}
+
+int gpr_predict(gpr_model* m, const double* xp, int64_t M, int same_x, double* mean, double* var_diag, double* cov_full) {
+  if (!m) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  if (!xp || !mean || M < 1) return fail(ctx, GPR_ERR_ARG, "NULL or empty argument");
+  if (!m->have_factor || m->factor_destroyed) return fail(ctx, GPR_ERR_STATE, "predict: call gpr_update_cache first");
+  if (same_x && M != m->N) return fail(ctx, GPR_ERR_ARG, "same_x requires M == N");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t Np = m->Np, N = m->N;
+  const int D = m->D, ny = m->ny;
+
+  if (cov_full) {
+    // dense path (src/predict.jl:42-49,83-87): needs V = K* U^-1 for all test points at once
+    const int64_t Mp = round_up(M, 128);
+    int rc = ensure(ctx, m->w_xp, (size_t)D * M); if (rc) return rc;
+    rc = ensure(ctx, m->w_mean, (size_t)Mp * ny); if (rc) return rc;
+    rc = ensure(ctx, m->w_var, (size_t)Mp); if (rc) return rc;
+    double* d_sigma = nullptr;
+    CK(cudaMalloc(&d_sigma, sizeof(double) * Mp * Mp));
+    cudaError_t e = cudaMemcpyAsync(m->w_xp.p, xp, sizeof(double) * D * M, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d_sigma); return fail_cuda(ctx, e, "upload xp", __LINE__); }
+    rc = predict_tile(m, m->w_xp.p, M, 0, same_x, m->w_mean.p, Mp, m->w_var.p);   // leaves V in w_kxp (Mp x Np)
+    if (!rc) {
+      KBuildArgs a{};
+      a.out = d_sigma; a.ldo = Mp; a.R = M; a.C = M; a.Rp = Mp; a.Cp = Mp;
+      a.x1 = m->w_xp.p; a.x2 = m->w_xp.p; a.D = D; a.hp = m->d_hp; a.spec = m->spec;
+      a.eps = m->eps_host; a.same = 1; a.add_noise = 1; a.pad_identity = 0; a.sigma_one = 0; a.row_scale = nullptr; a.diag_shift = 0;
+      rc = launch_kbuild(ctx, DM_EUCLID, a);   // kernel!(Sigma, covar, params, xp)  (src/predict.jl:45)
+    }
+    if (!rc) {
+      CudaBE be{ctx};
+      be.gemm('N', 'T', Mp, Mp, Np, -1.0, m->w_kxp.p, Mp, m->w_kxp.p, Mp, 1.0, d_sigma, Mp, 0);   // Sigma -= V V^T
+      rc = check_pending(ctx, "predict cov");
+    }
+    if (!rc) {
+      e = cudaMemcpy2DAsync(cov_full, sizeof(double) * M, d_sigma, sizeof(double) * Mp, sizeof(double) * M, M, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpy2DAsync(mean, sizeof(double) * M, m->w_mean.p, sizeof(double) * Mp, sizeof(double) * M, ny, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess && var_diag) e = cudaMemcpyAsync(var_diag, m->w_var.p, sizeof(double) * M, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) rc = fail_cuda(ctx, e, "download cov", __LINE__);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_sigma);
+    (void)N;
+    return rc;
+  }
+
+  const int64_t MT = std::min<int64_t>(ctx->predict_tile, round_up(M, 128));
+  int rc = ensure(ctx, m->w_xp, (size_t)D * MT); if (rc) return rc;
+  rc = ensure(ctx, m->w_mean, (size_t)MT * ny); if (rc) return rc;
+  rc = ensure(ctx, m->w_var, (size_t)MT); if (rc) return rc;
+  for (int64_t m0 = 0; m0 < M; m0 += MT) {
+    const int64_t mt = std::min(MT, M - m0);
+    CK(cudaMemcpyAsync(m->w_xp.p, xp + m0 * D, sizeof(double) * D * mt, cudaMemcpyHostToDevice, ctx->stream));
+    rc = predict_tile(m, m->w_xp.p, mt, m0, same_x, m->w_mean.p, MT, var_diag ? m->w_var.p : nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(mean + m0, sizeof(double) * M, m->w_mean.p, sizeof(double) * MT, sizeof(double) * mt, ny, cudaMemcpyDeviceToHost, ctx->stream));
+    if (var_diag) CK(cudaMemcpyAsync(var_diag + m0, m->w_var.p, sizeof(double) * mt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return GPR_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// split kernel / split predict
+// ---------------------------------------------------------------------------
+namespace {
+
+struct SplitBufs {
+  double *A = nullptr, *B = nullptr, *C = nullptr, *Ct = nullptr;   // per non-noise component slices
+  double *d_xe = nullptr, *d_xq = nullptr;
+  int64_t nep = 0, nqp = 0;
+  void release() { cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(Ct); cudaFree(d_xe); cudaFree(d_xq); A = B = C = Ct = d_xe = d_xq = nullptr; }
+};
+
+// Builds A (nep x nqp x k), B (nep x Np x k) and, per request, C (Np x nqp x k; optionally row-scaled by wt)
+// and Ct (nqp x Np x k).  d_hp: device global hp.  x: D x N device.
+int split_build(gpr_ctx* ctx, const KSpec& spec, int D, const double* d_hp, const double* d_xe, int64_t ne,
+                const double* d_xq, int64_t nq, const double* d_x, int64_t N, int64_t Np, double eps, SplitBufs& sb,
+                bool want_C, const double* c_row_scale, bool want_Ct) {
+  (void)eps;
+  const int64_t nep = sb.nep, nqp = sb.nqp;
+  int k = 0;
+  for (int c = 0; c < spec.ncomp; ++c) {
+    if (spec.type[c] == KT_NOISE) continue;
+    KSpec one{};
+    one.ncomp = 1; one.type[0] = spec.type[c]; one.hp_off[0] = spec.hp_off[c];
+    KBuildArgs a{};
+    a.D = D; a.hp = d_hp; a.spec = one; a.eps = 0.0; a.same = 0; a.add_noise = 0; a.pad_identity = 0; a.diag_shift = 0;
+    // A[:, :, k] = exp(-sum (l xq)^2 - 2 sum l^2 xe xq), sigma := 1   (split_kernel.jl:152-155)
+    a.out = sb.A + (int64_t)k * nep * nqp; a.ldo = nep; a.R = ne; a.C = nq; a.Rp = nep; a.Cp = nqp;
+    a.x1 = d_xe; a.x2 = d_xq; a.sigma_one = 1; a.row_scale = nullptr;
+    int rc = launch_kbuild(ctx, DM_SPLIT_A, a); if (rc) return rc;
+    // B[:, :, k] = exp(-|l (xe - xs)|^2), sigma := 1                    (split_kernel.jl:156)
+    a.out = sb.B + (int64_t)k * nep * Np; a.ldo = nep; a.R = ne; a.C = N; a.Rp = nep; a.Cp = Np;
+    a.x1 = d_xe; a.x2 = d_x; a.sigma_one = 1;
+    rc = launch_kbuild(ctx, DM_EUCLID, a); if (rc) return rc;
+    // C[:, :, k] = sigma^2 exp(+2 sum l^2 xs xq)                         (split_kernel.jl:157)
+    if (want_C) {
+      a.out = sb.C + (int64_t)k * Np * nqp; a.ldo = Np; a.R = N; a.C = nq; a.Rp = Np; a.Cp = nqp;
+      a.x1 = d_x; a.x2 = d_xq; a.sigma_one = 0; a.row_scale = c_row_scale;
+      rc = launch_kbuild(ctx, DM_SPLIT_C, a); if (rc) return rc;
+    }
+    if (want_Ct) {
+      a.out = sb.Ct + (int64_t)k * nqp * Np; a.ldo = nqp; a.R = nq; a.C = N; a.Rp = nqp; a.Cp = Np;
+      a.x1 = d_xq; a.x2 = d_x; a.sigma_one = 0; a.row_scale = nullptr;
+      rc = launch_kbuild(ctx, DM_SPLIT_C, a); if (rc) return rc;
+    }
+    ++k;
+  }
+  return GPR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpr_split_kernel(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, const double* hp, const double* xe,
+                     int64_t ne, const double* xq, int64_t nq, const double* x, int64_t N, double* A, double* B,
+                     double* C) {
+  if (!ctx) return GPR_ERR_ARG;
+  if (!hp || !xe || !xq || !x || !A || !B || !C || ne < 1 || nq < 1 || N < 1) return fail(ctx, GPR_ERR_ARG, "NULL or empty argument");
+  CK(cudaSetDevice(ctx->device));
+  KSpec spec; int P = 0, nk = 0;
+  int rc = make_spec(ctx, comp_types, ncomp, D, &spec, &P, &nk);
+  if (rc) return rc;
+  SplitBufs sb; sb.nep = ne; sb.nqp = nq;   // unpadded: plain host-shaped outputs
+  double *d_x = nullptr, *d_hp = nullptr;
+  cudaError_t e = cudaMalloc(&sb.A, sizeof(double) * ne * nq * nk);
+  if (e == cudaSuccess) e = cudaMalloc(&sb.B, sizeof(double) * ne * N * nk);
+  if (e == cudaSuccess) e = cudaMalloc(&sb.C, sizeof(double) * N * nq * nk);
+  if (e == cudaSuccess) e = cudaMalloc(&sb.d_xe, sizeof(double) * D * ne);
+  if (e == cudaSuccess) e = cudaMalloc(&sb.d_xq, sizeof(double) * D * nq);
+  if (e == cudaSuccess) e = cudaMalloc(&d_x, sizeof(double) * D * N);
+  if (e == cudaSuccess) e = cudaMalloc(&d_hp, sizeof(double) * P);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sb.d_xe, xe, sizeof(double) * D * ne, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sb.d_xq, xq, sizeof(double) * D * nq, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, x, sizeof(double) * D * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_hp, hp, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream);
+  rc = GPR_OK;
+  if (e == cudaSuccess) {
+    rc = split_build(ctx, spec, D, d_hp, sb.d_xe, ne, sb.d_xq, nq, d_x, N, N, 0.0, sb, true, nullptr, false);
+    if (!rc) e = cudaMemcpyAsync(A, sb.A, sizeof(double) * ne * nq * nk, cudaMemcpyDeviceToHost, ctx->stream);
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(B, sb.B, sizeof(double) * ne * N * nk, cudaMemcpyDeviceToHost, ctx->stream);
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(C, sb.C, sizeof(double) * N * nq * nk, cudaMemcpyDeviceToHost, ctx->stream);
+    if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaStreamSynchronize(ctx->stream);
+  sb.release(); cudaFree(d_x); cudaFree(d_hp);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "gpr_split_kernel", __LINE__);
+  return GPR_OK;
+}
+
+int gpr_split_predict(gpr_model* m, const double* xe, int64_t ne, const double* xq, int64_t nq, int64_t e_lo,
+                      int64_t e_hi, double* mean, double* var) {
+  if (!m) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  if (!xe || !xq || !mean || ne < 1 || nq < 1) return fail(ctx, GPR_ERR_ARG, "NULL or empty argument");
+  if (!m->have_factor || m->factor_destroyed) return fail(ctx, GPR_ERR_STATE, "split predict: call gpr_update_cache first");
+  if (m->ny != 1) return fail(ctx, GPR_ERR_UNSUPPORTED, "split predict needs a vector y (Diagonal(wt), src/split_predict.jl:13)");
+  if (var && (e_lo < 1 || e_hi > ne || e_lo > e_hi + 1)) return fail(ctx, GPR_ERR_ARG, "var_range out of bounds");
+  CK(cudaSetDevice(ctx->device));
+  const int D = m->D, nk = m->nk;
+  const int64_t N = m->N, Np = m->Np;
+  SplitBufs sb; sb.nep = round_up(ne, 128); sb.nqp = round_up(nq, 128);
+  const int64_t nep = sb.nep, nqp = sb.nqp;
+  double *d_bcw = nullptr, *d_mu = nullptr, *d_var = nullptr;
+  int rc = GPR_OK;
+  cudaError_t e = cudaMalloc(&sb.A, sizeof(double) * nep * nqp * nk);
+  if (e == cudaSuccess) e = cudaMalloc(&sb.B, sizeof(double) * nep * Np * nk);
+  if (e == cudaSuccess) e = cudaMalloc(&sb.C, sizeof(double) * Np * nqp * nk);
+  if (e == cudaSuccess && var) e = cudaMalloc(&sb.Ct, sizeof(double) * nqp * Np * nk);
+  if (e == cudaSuccess) e = cudaMalloc(&sb.d_xe, sizeof(double) * D * ne);
+  if (e == cudaSuccess) e = cudaMalloc(&sb.d_xq, sizeof(double) * D * nq);
+  if (e == cudaSuccess) e = cudaMalloc(&d_bcw, sizeof(double) * nep * nqp);
+  if (e == cudaSuccess) e = cudaMalloc(&d_mu, sizeof(double) * nep * nqp);
+  if (e == cudaSuccess && var) e = cudaMalloc(&d_var, sizeof(double) * nqp * std::max<int64_t>(1, ctx->predict_tile / nqp));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sb.d_xe, xe, sizeof(double) * D * ne, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sb.d_xq, xq, sizeof(double) * D * nq, cudaMemcpyHostToDevice, ctx->stream);
+  auto cleanup = [&]() { cudaStreamSynchronize(ctx->stream); sb.release(); cudaFree(d_bcw); cudaFree(d_mu); cudaFree(d_var); };
+  if (e != cudaSuccess) { cleanup(); return fail_cuda(ctx, e, "split predict alloc", __LINE__); }
+
+  // C is built pre-multiplied by wt:  Cw = Diagonal(wt) * C[:, :, k]   (split_predict.jl:13)
+  rc = split_build(ctx, m->spec, D, m->d_hp, sb.d_xe, ne, sb.d_xq, nq, m->d_x, N, Np, 0.0, sb, true, m->d_wt, var != nullptr);
+  if (rc) { cleanup(); return rc; }
+  CudaBE be{ctx};
+  for (int k = 0; k < nk; ++k) {
+    // BCw = B[:, :, k] * Cw ; BCw .*= A[:, :, k] ; mu .+= BCw   (split_predict.jl:14-16)
+    be.gemm('N', 'N', nep, nqp, Np, 1.0, sb.B + (int64_t)k * nep * Np, nep, sb.C + (int64_t)k * Np * nqp, Np, 0.0, d_bcw, nep, 0);
+    hadamard_acc_kernel<<<(unsigned)std::min<int64_t>((nep * nqp + 255) / 256, 65535), 256, 0, ctx->stream>>>(
+        d_mu, nep, sb.A + (int64_t)k * nep * nqp, nep, d_bcw, nep, nep, nqp, k == 0);
+    ctx->launches++;
+  }
+  rc = check_pending(ctx, "split mean");
+  if (!rc) {
+    e = cudaMemcpy2DAsync(mean, sizeof(double) * ne, d_mu, sizeof(double) * nep, sizeof(double) * ne, nq, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail_cuda(ctx, e, "split mean download", __LINE__);
+  }
+  if (!rc && var) {
+    const double prior = prior_diag(m);
+    for (int64_t i = 0; i < ne * nq; ++i) var[i] = prior;   // fill!(Sigma.diag, sum sigma^2)  (src/predict.jl:55-58)
+    const int64_t EB = std::max<int64_t>(1, ctx->predict_tile / nqp);
+    rc = ensure(ctx, m->w_kxp, (size_t)EB * nqp * Np);
+    Blocked<CudaBE> blk(be, m->d_dinv);
+    for (int64_t e0 = e_lo - 1; !rc && e0 < e_hi; e0 += EB) {
+      const int64_t ec = std::min<int64_t>(EB, e_hi - e0);
+      const int64_t rows = ec * nqp;
+      {
+        Scope s(m->tm, GPR_T_PRED_KSTAR, ctx->stream);
+        split_assemble_kernel<<<(unsigned)std::min<int64_t>((rows * Np + 255) / 256, (int64_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(
+            m->w_kxp.p, rows, sb.A, sb.B, sb.Ct, nep, nqp, Np, nk, e0, ec, ne, nq, N);
+        ctx->launches++;
+      }
+      {
+        Scope s(m->tm, GPR_T_PRED_TRSM, ctx->stream);
+        blk.trsm_RUN(m->d_U, Np, Np, 0, m->w_kxp.p, rows, rows, 1.0);
+      }
+      {
+        Scope s(m->tm, GPR_T_PRED_ROWNORM, ctx->stream);
+        rc = row_reduce(m, 1, m->w_kxp.p, rows, rows, rows, Np, nullptr, prior, -1.0, d_var);
+      }
+      if (rc) break;
+      rc = check_pending(ctx, "split variance");
+      if (rc) break;
+      // var[(e-1)*nq + q]  (q fastest within e: split_predict.jl:48)
+      e = cudaMemcpy2DAsync(var + e0 * nq, sizeof(double) * nq, d_var, sizeof(double) * nqp, sizeof(double) * nq, ec, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) rc = fail_cuda(ctx, e, "split variance download", __LINE__);
+    }
+  }
+  cleanup();
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------
+int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, double alpha, const double* A,
+                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int reps,
+                  double* ms) {
+  if (!ctx) return GPR_ERR_ARG;
+  if (!A || !B || !C) return fail(ctx, GPR_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  const bool aT = (transA == 'T'), bT = (transB == 'T');
+  const int64_t a_cols = aT ? M : K, b_cols = bT ? K : N;
+  double *dA = nullptr, *dB = nullptr, *dC = nullptr, *dC0 = nullptr;
+  cudaError_t e = cudaMalloc(&dA, sizeof(double) * lda * a_cols);
+  if (e == cudaSuccess) e = cudaMalloc(&dB, sizeof(double) * ldb * b_cols);
+  if (e == cudaSuccess) e = cudaMalloc(&dC, sizeof(double) * ldc * N);
+  if (e == cudaSuccess) e = cudaMalloc(&dC0, sizeof(double) * ldc * N);
+  if (e == cudaSuccess) e = cudaMemcpy(dA, A, sizeof(double) * lda * a_cols, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dB, B, sizeof(double) * ldb * b_cols, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dC0, C, sizeof(double) * ldc * N, cudaMemcpyHostToDevice);
+  float total = 0.f;
+  if (e == cudaSuccess) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (reps < 1) reps = 1;
+    for (int r = 0; r < reps && e == cudaSuccess; ++r) {
+      e = cudaMemcpyAsync(dC, dC0, sizeof(double) * ldc * N, cudaMemcpyDeviceToDevice, ctx->stream);
+      cudaEventRecord(e0, ctx->stream);
+      if (e == cudaSuccess) e = launch_dgemm128(ctx->stream, transA, transB, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, flags);
+      ctx->launches++;
+      cudaEventRecord(e1, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      float t = 0.f; cudaEventElapsedTime(&t, e0, e1);
+      if (r > 0 || reps == 1) total += t;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e == cudaSuccess) e = cudaMemcpy(C, dC, sizeof(double) * ldc * N, cudaMemcpyDeviceToHost);
+  }
+  if (ms) *ms = total / (float)(reps > 1 ? reps - 1 : 1);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dC0);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "gpr_dbg_dgemm", __LINE__);
+  return GPR_OK;
+}
+
+int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, double* ms) {
+  if (!ctx) return GPR_ERR_ARG;
+  if (!A || N < 1) return fail(ctx, GPR_ERR_ARG, "NULL or empty argument");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t Np = round_up(N, 128);
+  double *dA = nullptr, *dinv = nullptr;
+  cudaError_t e = cudaMalloc(&dA, sizeof(double) * Np * Np);
+  if (e == cudaSuccess) e = cudaMalloc(&dinv, sizeof(double) * Np * 128);
+  int rc = GPR_OK;
+  long long h_info = 0;
+  float t = 0.f;
+  if (e == cudaSuccess) {
+    // identity padding
+    std::vector<double> pad;
+    if (Np != N) {
+      pad.assign((size_t)Np * Np, 0.0);
+      for (int64_t j = 0; j < N; ++j) memcpy(&pad[(size_t)j * Np], A + j * N, sizeof(double) * N);
+      for (int64_t j = N; j < Np; ++j) pad[(size_t)j * Np + j] = 1.0;
+      e = cudaMemcpy(dA, pad.data(), sizeof(double) * Np * Np, cudaMemcpyHostToDevice);
+    } else {
+      e = cudaMemcpy(dA, A, sizeof(double) * Np * Np, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_info, 0, sizeof(long long), ctx->stream);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    CudaBE be{ctx};
+    Blocked<CudaBE> blk(be, dinv);
+    cudaEventRecord(e0, ctx->stream);
+    blk.potrf(dA, Np, Np, 0);
+    if (mode >= 1) blk.trtri(dA, Np, Np, 0);
+    if (mode >= 2) blk.lauum(dA, Np, Np, 0);
+    cudaEventRecord(e1, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_info, ctx->d_info, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    rc = check_pending(ctx, "gpr_dbg_factor");
+    if (e == cudaSuccess && !rc)
+      e = cudaMemcpy2D(A, sizeof(double) * N, dA, sizeof(double) * Np, sizeof(double) * N, N, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dA); cudaFree(dinv);
+  if (info) *info = h_info;
+  if (ms) *ms = t;
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "gpr_dbg_factor", __LINE__);
+  return h_info ? GPR_ERR_NOT_POSDEF : GPR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+/*
+ * libgpr_sm100a.so -- C ABI of the B200-native exact-GP hot path.
+ *
+ * Drop-in boundary for srinix007/GaussianProcessRegression.jl (reference paths
+ * are relative to /root/reference).  The reference has no FFI; its extension
+ * seam is the cache-based non-allocating API:
+ *     update_cache!(tc, hp, md)            src/cost.jl:74-111
+ *     loss(::MarginalLikelihood, md, tc)   src/cost.jl:113-117
+ *     grad!(dL, ::MarginalLikelihood, md, tc)  src/cost.jl:119-127
+ *     loss_grad! / log_loss_grad!          src/cost.jl:50-70
+ *     update_cache!(pc, md)                src/predict.jl:29-34
+ *     predict_mean! / predict!             src/predict.jl:36-102
+ *     kernel! (SplitKernel), split predict src/split_kernel.jl:137-159, src/split_predict.jl:5-53
+ *     kernel / kernel! / grad              src/covariance.jl:29-58, src/compose_covar.jl:35-77, src/deriv_covar.jl:2-32
+ * Each entry point below names the reference interface it replaces.  The
+ * Julia glue that binds these with ccall is in julia/GPRsm100a.jl and
+ * INTEGRATION.md; in this repository the executed binding is the ctypes layer
+ * gaussianprocessregression.jl_b200/gpr_sm100a/_ffi.py.
+ *
+ * Conventions
+ *   - All matrices are column major Float64, exactly as Julia passes them:
+ *     x is D x N (one point = D contiguous doubles), y is N x ny,
+ *     K(x, xp) is N x M, predictive outputs have the test index fastest.
+ *   - Hyper-parameters: concatenation in component order; SquaredExp and
+ *     Matern52 take [sigma, l_1..l_D] (l multiplies x, no 1/2), WhiteNoise takes [sigma_n]
+ *     (src/covariance.jl:27,60,85-95; src/compose_covar.jl:21-28).
+ *   - Host pointers unless the function name ends in _device.  The caller owns
+ *     every host buffer; the library copies what it needs and retains no
+ *     pointer beyond the call.  Handles own all device memory.
+ *   - Return value: 0 = ok; GPR_ERR_NOT_POSDEF (1) = the Cholesky hit a
+ *     non-positive pivot, *info holds its 1-based index (LAPACK dpotrf info; the
+ *     glue throws PosDefException(info) like cholesky!(...; check=true));
+ *     negative = argument / CUDA error, text via gpr_last_error().
+ *   - Calls on one context are synchronous and must not be issued
+ *     concurrently; distinct contexts may be used from distinct threads.
+ *   - There is no CPU fallback: every entry point fails with
+ *     GPR_ERR_CUDA if no sm_100-class device is usable.
+ */
+#ifndef GPR_SM100A_H
+#define GPR_SM100A_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPR_OK 0
+#define GPR_ERR_NOT_POSDEF 1
+#define GPR_ERR_ARG (-1)
+#define GPR_ERR_CUDA (-2)
+#define GPR_ERR_MEMORY (-3)
+#define GPR_ERR_STATE (-4)
+#define GPR_ERR_UNSUPPORTED (-5)
+
+/* component tags: SquaredExp, WhiteNoise (src/covariance.jl:15-17); Matern52 is an extension */
+#define GPR_KERN_SE 1
+#define GPR_KERN_NOISE 2
+#define GPR_KERN_MATERN52 3
+
+/* gpr_fetch selectors (cache internals pinned by test/test_loss.jl:46-48) */
+#define GPR_FETCH_U 0      /* N x N: upper = U, strict lower = K (tc.kchol_base) */
+#define GPR_FETCH_ALPHA 1  /* N      (tc.alpha = K^-1 y[:, train_axis]) */
+#define GPR_FETCH_KINV 2   /* N x N  (tc.K^-1, full symmetric) */
+#define GPR_FETCH_WT 3     /* N x ny (pc.wt = K^-1 y) */
+
+/* gpr_timings slots (milliseconds of the last evaluation, CUDA events on the library stream) */
+#define GPR_T_KBUILD 0
+#define GPR_T_POTRF 1
+#define GPR_T_POTRS 2
+#define GPR_T_TRTRI 3
+#define GPR_T_LAUUM 4
+#define GPR_T_GRAD 5
+#define GPR_T_TOTAL 6
+#define GPR_T_PRED_KSTAR 7
+#define GPR_T_PRED_MEAN 8
+#define GPR_T_PRED_TRSM 9
+#define GPR_T_PRED_ROWNORM 10
+#define GPR_T_COUNT 16
+
+typedef struct gpr_ctx gpr_ctx;
+typedef struct gpr_model gpr_model;
+
+int gpr_version(void);
+
+/* one context per GPU / per thread */
+int gpr_ctx_create(int device, gpr_ctx** ctx);
+int gpr_ctx_destroy(gpr_ctx* ctx);
+const char* gpr_last_error(gpr_ctx* ctx);          /* ctx may be NULL: last error of a failed gpr_ctx_create */
+int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value);   /* "predict_tile" (test points per tile) */
+int64_t gpr_ctx_launch_count(gpr_ctx* ctx);        /* kernels launched by this context so far */
+
+/* dim_hp(K, dim): src/covariance.jl:27,60; src/compose_covar.jl:26-28 */
+int gpr_dim_hp(const int* comp_types, int ncomp, int D);
+
+/* GPRModel(cov, hp, x, y; train_axis): src/models.jl:17-37.  train_axis is 1-based. */
+int gpr_model_create(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, int64_t N, const double* x,
+                     const double* y, int ny, int train_axis, gpr_model** model);
+int gpr_model_destroy(gpr_model* model);
+int gpr_model_set_y(gpr_model* model, const double* y);   /* md.y .+= dy  (src/update_model.jl:36) */
+int gpr_model_set_x(gpr_model* model, const double* x);
+
+/* kernel(K, hp, x[, xp]) / kernel!: src/covariance.jl:29-58, src/compose_covar.jl:35-77.
+ * out is N x M.  same_x: the reference's `x === xp` (adds eps per non-noise component on the diagonal);
+ * add_noise: self-covariance form (adds sigma_n^2 of the first WhiteNoise on the diagonal). */
+int gpr_kernel(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, const double* hp, const double* x, int64_t N,
+               const double* xp, int64_t M, int same_x, double eps, int add_noise, double* out);
+
+/* grad(cov, i, hp, x) for one non-noise component: src/deriv_covar.jl:2-29.
+ * li: 0 = sigma, d = l_d (1..D).  out is N x N.  (WhiteNoise returns 2*sigma_n*I on the host side.) */
+int gpr_kernel_grad(gpr_ctx* ctx, int comp_type, int D, const double* hp_comp, const double* x, int64_t N, int li,
+                    double eps, double* out);
+
+/* update_cache!(tc, hp, md) for MllLossCache (want_inverse = 0) / MllGradCache (want_inverse = 1),
+ * and update_cache!(pc, md) of the predict caches: src/cost.jl:74-111, src/predict.jl:29-34.
+ * Builds K, factors it (upper), solves for all columns of y, optionally forms K^-1. */
+int gpr_update_cache(gpr_model* model, const double* hp, int P, double eps, int want_inverse, int64_t* info);
+/* loss(::MarginalLikelihood, md, tc): src/cost.jl:113-117, src/loss_grad.jl:39-41 */
+int gpr_loss(gpr_model* model, double* F);
+/* grad!(dL, ::MarginalLikelihood, md, tc): src/cost.jl:119-127, src/loss_grad.jl:43-52.  log_scale: G .*= hp (src/cost.jl:65) */
+int gpr_grad(gpr_model* model, int log_scale, double* G);
+/* loss_grad! (log_scale = 0) / log_loss_grad! (log_scale = 1, hp_in holds log hp): src/cost.jl:50-70.
+ * F and G may each be NULL (Optim only_fg! contract). */
+int gpr_nlml_grad(gpr_model* model, const double* hp_in, int P, int log_scale, double eps, double* F, double* G,
+                  int64_t* info);
+int gpr_fetch(gpr_model* model, int which, double* out);
+
+/* predict_mean! / predict!: src/predict.jl:36-102.  Requires gpr_update_cache.  xp is D x M.
+ * mean: M x ny.  var_diag (nullable): M, the Diagonal path (prior = sum of hp_c[1]^2, no jitter).
+ * cov_full (nullable): M x M, the dense path (prior = kernel(cov, hp, xp) incl. jitter and noise). */
+int gpr_predict(gpr_model* model, const double* xp, int64_t M, int same_x, double* mean, double* var_diag,
+                double* cov_full);
+/* same, test points and outputs resident in device memory (mean ld = M) */
+int gpr_predict_device(gpr_model* model, const double* d_xp, int64_t M, int same_x, double* d_mean, double* d_var_diag);
+
+/* kernel!(Kxps::SplitKernel, cov, hp, Cmap(+, xe, xq), x): src/split_kernel.jl:137-159.
+ * A: ne x nq x k, B: ne x N x k, C: N x nq x k, k = number of non-noise components. */
+int gpr_split_kernel(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, const double* hp, const double* xe,
+                     int64_t ne, const double* xq, int64_t nq, const double* x, int64_t N, double* A, double* B,
+                     double* C);
+/* predict!(mu, Sigma::Diagonal, md, Cmap(+, xe, xq), pc): src/predict.jl:51-71, src/split_predict.jl:5-53.
+ * mean: ne x nq (e fastest).  var (nullable): ne*nq, laid out q fastest within e; entries of rows
+ * e in [e_lo, e_hi] (1-based inclusive, the cache's var_range, default 1:3) get the posterior variance,
+ * all others keep the prior. */
+int gpr_split_predict(gpr_model* model, const double* xe, int64_t ne, const double* xq, int64_t nq, int64_t e_lo,
+                      int64_t e_hi, double* mean, double* var);
+
+int gpr_timings(gpr_model* model, double* ms, int n);
+
+/* diagnostics (used by tests / bench only): the DMMA tile GEMM on host matrices, C = alpha op(A) op(B) + beta C.
+ * M, N multiples of 128, K multiple of 16; transA/transB in {'N','T'} (TT unsupported).
+ * reps > 1 re-runs the kernel and returns the mean kernel time in *ms. */
+int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, double alpha, const double* A,
+                  int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int reps,
+                  double* ms);
+/* factor (and optionally invert) a host SPD matrix in place through the blocked path; A is N x N.
+ * mode 0: potrf (upper = U), 1: potrf + trtri (upper = U^-1), 2: potrf + trtri + lauum (upper = A^-1). */
+int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPR_SM100A_H */

@@ -1,0 +1,103 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into libgpr_sm100a.so.
+// Plain-loop CPU backend for csrc/blocked.hpp so that the recursion / index
+// arithmetic of the blocked potrf / trsm / trtri / lauum / potrs drivers can be
+// checked in the CPU test-suite (pytest -m "not gpu").  The product library
+// instantiates the same template with the CUDA backend only.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../gaussianprocessregression.jl_b200/csrc/blocked.hpp"
+
+namespace {
+
+struct CpuBE {
+  long long info = 0;
+  long long gemm_calls = 0;
+  void gemm(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+            const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags) {
+    gemm_calls++;
+    // like the GPU kernel: a tile reads all of its operands before it stores, so C may alias A or B
+    std::vector<double> tmp((size_t)M * N);
+    for (int64_t n = 0; n < N; ++n)
+      for (int64_t m = 0; m < M; ++m) {
+        double s = 0.0;
+        for (int64_t k = 0; k < K; ++k) {
+          const double a = (tA == 'T') ? A[k + m * lda] : A[m + k * lda];
+          const double b = (tB == 'T') ? B[n + k * ldb] : B[k + n * ldb];
+          s += a * b;
+        }
+        tmp[m + n * M] = s;
+      }
+    for (int64_t n = 0; n < N; ++n)
+      for (int64_t m = 0; m < M; ++m) {
+        if ((flags & gpr::BLK_UPPER_ONLY) && m > n) continue;
+        double r = alpha * tmp[m + n * M];
+        if (beta != 0.0) r += beta * C[m + n * ldc];
+        C[m + n * ldc] = r;
+      }
+  }
+  void potrf_leaf(double* A, int64_t lda, double* dinv, int64_t goff) {
+    const int n = gpr::LEAF;
+    for (int k = 0; k < n; ++k) {
+      double p = A[k + k * lda];
+      if (!(p > 0.0)) { if (!info) info = goff + k + 1; memset(dinv, 0, sizeof(double) * n * n); return; }
+      const double d = std::sqrt(p);
+      A[k + k * lda] = d;
+      for (int j = k + 1; j < n; ++j) A[k + j * lda] /= d;
+      for (int j = k + 1; j < n; ++j)
+        for (int i = k + 1; i <= j; ++i) A[i + j * lda] -= A[k + i * lda] * A[k + j * lda];
+    }
+    for (int j = 0; j < n; ++j) {
+      for (int i = n - 1; i >= 0; --i) {
+        if (i > j) { dinv[i + j * n] = 0.0; continue; }
+        double s = (i == j) ? 1.0 : 0.0;
+        for (int k = i + 1; k <= j; ++k) s -= A[i + k * lda] * dinv[k + j * n];
+        dinv[i + j * n] = s / A[i + i * lda];
+      }
+    }
+  }
+  void copy_upper_128(double* dst, int64_t ldd, const double* src) {
+    for (int c = 0; c < gpr::LEAF; ++c)
+      for (int r = 0; r <= c; ++r) dst[r + c * ldd] = src[r + c * gpr::LEAF];
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// A: n x n column major (n % 128 == 0), factored in place.  mode 0: potrf, 1: +trtri, 2: +lauum.
+long long hl_factor(double* A, int64_t n, int mode, long long* gemm_calls) {
+  CpuBE be;
+  std::vector<double> dinv((size_t)n * 128);
+  gpr::Blocked<CpuBE> blk(be, dinv.data());
+  blk.potrf(A, n, n, 0);
+  if (mode >= 1) blk.trtri(A, n, n, 0);
+  if (mode >= 2) blk.lauum(A, n, n, 0);
+  if (gemm_calls) *gemm_calls = be.gemm_calls;
+  return be.info;
+}
+
+// potrf(A) then B (n x m) <- A^-1 B
+long long hl_potrs(double* A, int64_t n, double* B, int64_t m) {
+  CpuBE be;
+  std::vector<double> dinv((size_t)n * 128);
+  gpr::Blocked<CpuBE> blk(be, dinv.data());
+  blk.potrf(A, n, n, 0);
+  blk.potrs(A, n, n, B, n, m);
+  return be.info;
+}
+
+// potrf(A) then B (m x n) <- B U^-1
+long long hl_trsm_run(double* A, int64_t n, double* B, int64_t m) {
+  CpuBE be;
+  std::vector<double> dinv((size_t)n * 128);
+  gpr::Blocked<CpuBE> blk(be, dinv.data());
+  blk.potrf(A, n, n, 0);
+  blk.trsm_RUN(A, n, n, 0, B, m, m, 1.0);
+  return be.info;
+}
+
+}  // extern "C"
