@@ -128,6 +128,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
 
   const int KT = p.K / GEMM_BK;
 
+  // Pull the C tile towards L2 while the main loop runs (the epilogue reads it when beta != 0):
+  // 128 columns x 1 KiB = 8 lines per column, 4 prefetches per thread.
+  if (p.beta != 0.0) {
+    const double* cpre = p.C + m0 + (n0 + (tid >> 1)) * p.ldc + (tid & 1) * 64;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(cpre + q * 16));
+  }
+
   // prologue
 #pragma unroll
   for (int s = 0; s < GEMM_STAGES - 1; ++s) {
@@ -197,12 +205,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
   cp_async_wait<0>();
 
   // epilogue: C = alpha*acc + beta*C (element (row, col) of the tile lives in
-  // acc[i][j][v] with row = row_of(i,g), col = col_of(j, 2t+v)).
+  // acc[i][j][v] with row = row_of(i,g), col = col_of(j, 2t+v)).  The old C
+  // values are fetched in batches of 16 independent loads BEFORE any store of
+  // the batch is issued (a load-after-store to the same array cannot be
+  // hoisted by the compiler, which would serialise 64 DRAM round trips).
   const bool diag_tile = (p.flags & GEMM_UPPER_ONLY) && (tile_m == tile_n);
   const double alpha = p.alpha, beta = p.beta;
   double* Cp = p.C + m0 + n0 * p.ldc;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < 4; ++j) {
+    double old[8][2];
+    if (beta != 0.0) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int col = gemm_col_of<B_KC>(wn, j, 2 * t + v);
+        const double* Ccol = Cp + (long long)col * p.ldc;
+        if (A_KC) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = gemm_row_of<true>(wm, i, g);
+            old[i][v] = (diag_tile && row > col) ? 0.0 : Ccol[row];
+          }
+        } else {
+#pragma unroll
+          for (int pi = 0; pi < 4; ++pi) {
+            const int row = gemm_row_of<false>(wm, 2 * pi, g);
+            if (!diag_tile) {
+              const double2 o = *reinterpret_cast<const double2*>(Ccol + row);
+              old[2 * pi][v] = o.x; old[2 * pi + 1][v] = o.y;
+            } else {
+              old[2 * pi][v] = (row <= col) ? Ccol[row] : 0.0;
+              old[2 * pi + 1][v] = (row + 1 <= col) ? Ccol[row + 1] : 0.0;
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) old[i][0] = old[i][1] = 0.0;
+    }
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       const int col = gemm_col_of<B_KC>(wn, j, 2 * t + v);
@@ -212,26 +253,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
         for (int i = 0; i < 8; ++i) {
           const int row = gemm_row_of<true>(wm, i, g);
           if (diag_tile && row > col) continue;
-          double r = alpha * acc[i][j][v];
-          if (beta != 0.0) r += beta * Ccol[row];
-          Ccol[row] = r;
+          Ccol[row] = alpha * acc[i][j][v] + beta * old[i][v];
         }
       } else {
 #pragma unroll
         for (int pi = 0; pi < 4; ++pi) {
           const int row = gemm_row_of<false>(wm, 2 * pi, g);   // even row; row+1 is sub-tile 2*pi+1
-          double r0 = alpha * acc[2 * pi][j][v], r1 = alpha * acc[2 * pi + 1][j][v];
+          const double r0 = alpha * acc[2 * pi][j][v] + beta * old[2 * pi][v];
+          const double r1 = alpha * acc[2 * pi + 1][j][v] + beta * old[2 * pi + 1][v];
           if (!diag_tile) {
-            double2* ptr = reinterpret_cast<double2*>(Ccol + row);
-            if (beta != 0.0) { const double2 o = *ptr; r0 += beta * o.x; r1 += beta * o.y; }
-            *ptr = make_double2(r0, r1);
+            *reinterpret_cast<double2*>(Ccol + row) = make_double2(r0, r1);
           } else {
-            if (row <= col) { if (beta != 0.0) r0 += beta * Ccol[row]; Ccol[row] = r0; }
-            if (row + 1 <= col) { if (beta != 0.0) r1 += beta * Ccol[row + 1]; Ccol[row + 1] = r1; }
+            if (row <= col) Ccol[row] = r0;
+            if (row + 1 <= col) Ccol[row + 1] = r1;
           }
         }
       }
     }
+  }
 }
 
 template <bool A_KC, bool B_KC> constexpr size_t gemm_smem_bytes() {

@@ -1,0 +1,578 @@
+"""Host-side mirror of the reference's model / covariance / cost / predict API for the hot path.
+
+Same names, argument meaning and error behaviour as srinix007/GaussianProcessRegression.jl (paths below are
+relative to /root/reference); Julia's `f!` is spelled `f_`.  Everything numeric is done by libgpr_sm100a.so
+through the C ABI (`_ffi.py`); this module holds no arithmetic beyond argument marshalling, the log-space
+transform of `train` and the hyper-parameter bookkeeping the reference also does on the host.
+
+Conventions kept from Julia: `x` is (D, N), `y` is (N,) or (N, ny), `kernel(cov, hp, x, xp)` is (N, M);
+hyper-parameter indices `i` (grad) and `train_axis` are 1-based; `x === xp` is Python's `xp is x`.
+
+The Julia glue that a maintainer of the reference would add (cache types holding the same handles and
+`ccall`ing the same entry points) is julia/GPRsm100a.jl, described in INTEGRATION.md.
+"""
+import numpy as np
+
+from . import _ffi
+from ._ffi import GPRError, PosDefException, get_context  # noqa: F401
+
+
+# --------------------------------------------------------------------------- covariance.jl / compose_covar.jl
+class AbstractKernel:
+    type_id = 0
+
+    def __add__(self, other):
+        """Base.:+ on kernels -> ComposedKernel (src/compose_covar.jl:9-19)"""
+        a = self.kernels if isinstance(self, ComposedKernel) else (self,)
+        b = other.kernels if isinstance(other, ComposedKernel) else (other,)
+        return ComposedKernel(tuple(a) + tuple(b))
+
+    def __eq__(self, other):
+        return type(self) is type(other) and getattr(self, "kernels", None) == getattr(other, "kernels", None)
+
+    def __hash__(self):
+        return hash(type(self).__name__)
+
+    def __repr__(self):
+        return type(self).__name__ + "()"
+
+
+class SquaredExp(AbstractKernel):
+    """K(x,x') = sigma^2 exp(-|l .* (x - x')|^2), hp = [sigma, l_1..l_D]  (src/covariance.jl:4-15,85-95)"""
+    type_id = _ffi.KERN_SE
+
+
+class WhiteNoise(AbstractKernel):
+    """sigma_n^2 * I on the self covariance only  (src/covariance.jl:17,60-64)"""
+    type_id = _ffi.KERN_NOISE
+
+
+class Matern52(AbstractKernel):
+    """Extension, not in the reference (parity unpinned): sigma^2 (1 + sqrt5 r + 5 r^2/3) exp(-sqrt5 r), r = |l .* (x-x')|."""
+    type_id = _ffi.KERN_MATERN52
+
+
+class Euclidean:
+    """src/covariance.jl:19"""
+
+
+class ComposedKernel(AbstractKernel):
+    """src/compose_covar.jl:1-3"""
+
+    def __init__(self, kernels):
+        self.kernels = tuple(kernels)
+
+    def __repr__(self):
+        return "(" + ", ".join(repr(k) for k in self.kernels) + ")"
+
+
+def _components(cov):
+    return list(cov.kernels) if isinstance(cov, ComposedKernel) else [cov]
+
+
+def _types(cov):
+    return [k.type_id for k in _components(cov)]
+
+
+def dim_hp(cov, dim):
+    """src/covariance.jl:27,60 ; src/compose_covar.jl:26-28"""
+    return sum(1 if isinstance(k, WhiteNoise) else dim + 1 for k in _components(cov))
+
+
+def split(hp, dims):
+    """Base.split(A, inds)  (src/compose_covar.jl:21-24)"""
+    c = np.concatenate([[0], np.cumsum(dims)])
+    return [np.asarray(hp[c[i]:c[i + 1]]) for i in range(len(dims))]
+
+
+def find_idx(dims, i):
+    """src/compose_covar.jl:109-115 (1-based)"""
+    cd = np.cumsum(dims)
+    hit = np.nonzero(cd >= i)[0]
+    kidx = int(hit[0]) + 1 if len(hit) else 0
+    hpidx = i if kidx == 1 else i - int(cd[kidx - 2])
+    return kidx, hpidx
+
+
+class UniformScaling:
+    """lambda * I (what grad(::WhiteNoise...) returns, src/deriv_covar.jl:31)"""
+
+    def __init__(self, lam):
+        self.λ = self.lam = float(lam)
+
+    def __repr__(self):
+        return f"UniformScaling({self.lam})"
+
+
+def kernel(cov, hp, x, xp=None, dist=None, ϵ=1e-8, ctx=None):
+    """kernel(K, hp, x[, xp]; ϵ)  (src/covariance.jl:29-47, src/compose_covar.jl:35-45).
+    `xp` may be a `Cmap`, which returns a `SplitKernel` (src/split_kernel.jl:125-135)."""
+    if isinstance(xp, Cmap):
+        return _split_kernel(cov, hp, xp, x, ctx)
+    ctx = ctx or get_context()
+    x = np.asarray(x)
+    if isinstance(cov, WhiteNoise):
+        if xp is None:
+            return UniformScaling(float(hp[0]) ** 2)       # hp[1]^2 * I  (src/covariance.jl:61)
+        return 0.0
+    if len(hp) != dim_hp(cov, x.shape[0]):
+        raise GPRError("Parameter size mismatch.")
+    if xp is None:
+        # self form: jitter per component, noise on the diagonal for composed kernels
+        return _ffi.kernel_matrix(ctx, _types(cov), x.shape[0], hp, x, x, True, ϵ, isinstance(cov, ComposedKernel))
+    same = xp is x
+    return _ffi.kernel_matrix(ctx, _types(cov), x.shape[0], hp, x, xp, same, ϵ, False)
+
+
+def kernel_(kern, cov, hp, x, xp=None, ϵ=1e-8, ctx=None):
+    """kernel!(kern, K, hp, x[, xp])  (src/covariance.jl:33-58, src/compose_covar.jl:47-77)"""
+    if isinstance(kern, SplitKernel):
+        new = _split_kernel(cov, hp, x, xp, ctx)      # kernel!(Kxps, cov, hp, xp::Cmap, x): x is the Cmap here
+        kern.A[...], kern.B[...], kern.C[...] = new.A, new.B, new.C
+        return None
+    if isinstance(cov, WhiteNoise):
+        return None
+    kern[...] = kernel(cov, hp, x, xp, ϵ=ϵ, ctx=ctx)
+    return None
+
+
+def alloc_kernels(cov, x):
+    """src/compose_covar.jl:90-100"""
+    n = x.shape[1]
+    return [np.zeros((1, 1)) if isinstance(k, WhiteNoise) else np.empty((n, n), order="F") for k in _components(cov)]
+
+
+def kernels(cov, hp, x, ctx=None):
+    """kernels(K, hp, x): list of per-component self covariances (src/compose_covar.jl:80-107)"""
+    if not isinstance(cov, ComposedKernel):
+        return [kernel(cov, hp, x, ctx=ctx)]
+    dim = x.shape[0]
+    hps = split(hp, [dim_hp(k, dim) for k in cov.kernels])
+    return [np.zeros((1, 1)) if isinstance(k, WhiteNoise) else kernel(k, h, x, ctx=ctx) for k, h in zip(cov.kernels, hps)]
+
+
+def add_noise_(kern, cov, hp, x):
+    """src/compose_covar.jl:63-71 (host: N additions on the diagonal)"""
+    comps = _components(cov)
+    for idx, k in enumerate(comps):
+        if isinstance(k, WhiteNoise):
+            hps = split(hp, [dim_hp(c, x.shape[0]) for c in comps])
+            kern[np.diag_indices(kern.shape[0])] += hps[idx][0] ** 2
+            break
+    return None
+
+
+def rm_noise(cov, hps):
+    """src/compose_covar.jl:30-33"""
+    comps = _components(cov)
+    return ([k for k in comps if not isinstance(k, WhiteNoise)],
+            [h for k, h in zip(comps, hps) if not isinstance(k, WhiteNoise)])
+
+
+def grad(cov_or_cost, *args, **kw):
+    """grad(cov, i, hp, x) -> dK/dhp_i (src/deriv_covar.jl:2-18)   |   grad(cost, hp, md) (src/cost.jl:26-30)"""
+    if isinstance(cov_or_cost, AbstractLoss):
+        return _grad_cost(cov_or_cost, *args, **kw)
+    return _grad_kernel(cov_or_cost, *args, **kw)
+
+
+def _grad_kernel(cov, i, hp, x, K=None, ϵ=1e-8, ctx=None):
+    ctx = ctx or get_context()
+    dim = x.shape[0]
+    if isinstance(cov, ComposedKernel):
+        dims = [dim_hp(k, dim) for k in cov.kernels]
+        hps = split(hp, dims)
+        kidx, hpidx = find_idx(dims, i)
+        return _grad_kernel(cov.kernels[kidx - 1], hpidx, hps[kidx - 1], x, ϵ=ϵ, ctx=ctx)
+    if isinstance(cov, WhiteNoise):
+        return UniformScaling(2.0 * float(hp[0]))           # src/deriv_covar.jl:31
+    return _ffi.kernel_grad_matrix(ctx, cov.type_id, dim, hp, x, i - 1, ϵ)
+
+
+# --------------------------------------------------------------------------- models.jl
+class GPRModel:
+    """GPRModel(cov, hp, x, y; train_axis=1) / GPRModel(cov, x, y)  (src/models.jl:17-37)"""
+
+    def __init__(self, cov, *args, train_axis=1):
+        if len(args) == 3:
+            hp, x, y = args
+        elif len(args) == 2:
+            x, y = args
+            hp = np.random.rand(dim_hp(cov, np.asarray(x).shape[0]))
+        else:
+            raise TypeError("GPRModel(cov, [hp,] x, y)")
+        x, y, hp = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64), np.asarray(hp, dtype=np.float64)
+        if hp.shape[0] != dim_hp(cov, x.shape[0]):
+            raise GPRError("Parameter size mismatch.")
+        if x.shape[-1] != y.shape[0]:
+            raise GPRError("x and y size mismatch.")
+        self.covar, self.params, self.x, self.y, self.train_axis = cov, hp, x, y, int(train_axis)
+
+
+def get_sample(md):
+    """src/models.jl:39-45"""
+    return md.y[:, md.train_axis - 1] if md.y.ndim == 2 else md.y
+
+
+# --------------------------------------------------------------------------- loss_grad.jl / cost.jl / caches
+class AbstractLoss:
+    pass
+
+
+class MarginalLikelihood(AbstractLoss):
+    """src/loss_grad.jl:5"""
+
+
+class LogScale:
+    pass
+
+
+class NoLogScale:
+    pass
+
+
+def islog(cost, md):
+    """src/cost.jl:4-8"""
+    if isinstance(cost, MarginalLikelihood):
+        return LogScale() if any(isinstance(k, (SquaredExp, Matern52)) for k in _components(md.covar)) else NoLogScale()
+    return NoLogScale()
+
+
+class _DeviceCache:
+    """Common part of the SM100 caches: one device-resident gpr_model per cache, like the reference's
+    pre-allocated workspaces (src/caches/cost.jl, src/caches/predict.jl)."""
+    want_inverse = False
+
+    def __init__(self, md, ctx=None):
+        self.ctx = ctx or get_context()
+        self.hp = np.array(md.params, dtype=np.float64)
+        self._x_ref, self._y_snapshot = md.x, np.array(md.y, copy=True)
+        self.handle = _ffi.ModelHandle(self.ctx, _types(md.covar), md.x.shape[0], md.x, md.y, md.train_axis)
+
+    def _sync_data(self, md):
+        if md.x is not self._x_ref:
+            self.handle.set_x(md.x)
+            self._x_ref = md.x
+        if not np.array_equal(md.y, self._y_snapshot):     # md.y .+= dy between calls (src/update_model.jl:36)
+            self.handle.set_y(md.y)
+            self._y_snapshot = np.array(md.y, copy=True)
+
+    # cache internals pinned by test/test_loss.jl:46-48
+    @property
+    def kchol_base(self):
+        return self.handle.fetch(_ffi.FETCH_U)
+
+    @property
+    def α(self):
+        return self.handle.fetch(_ffi.FETCH_ALPHA)
+
+    alpha = α
+
+    @property
+    def K_inv(self):
+        return self.handle.fetch(_ffi.FETCH_KINV)
+
+    @property
+    def wt(self):
+        w = self.handle.fetch(_ffi.FETCH_WT)
+        return w[:, 0] if w.shape[1] == 1 else w
+
+    def timings(self):
+        return self.handle.timings()
+
+    def close(self):
+        self.handle.close()
+
+
+class MllLossCache(_DeviceCache):
+    """src/caches/cost.jl:6-19: hp, kchol_base, alpha"""
+    want_inverse = False
+
+
+class MllGradCache(_DeviceCache):
+    """src/caches/cost.jl:21-44: additionally K^-1 (the per-component kernel list and dK buffer of the
+    reference are never materialised here; the gradient kernel recomputes them on the fly)."""
+    want_inverse = True
+
+
+def loss_cache(cost):
+    return MllLossCache
+
+
+def grad_cache(cost):
+    return MllGradCache
+
+
+def loss_grad_cache(cost):
+    return MllGradCache
+
+
+class GPRPredictCache(_DeviceCache):
+    """src/caches/predict.jl:3-31 (Kxx, wt, Kxp live on the device)"""
+
+    def __init__(self, md, xp=None, ctx=None):
+        super().__init__(md, ctx)
+
+
+class GPRSplitPredictCache(_DeviceCache):
+    """src/caches/split_kernel.jl:1-30; var_range default 1:3 (1-based inclusive)"""
+
+    def __init__(self, md, xp=None, var_range=(1, 3), ctx=None):
+        super().__init__(md, ctx)
+        self.var_range = var_range
+
+
+def predict_cache(md, xp):
+    """src/predict.jl:1, src/split_predict.jl:1"""
+    return GPRSplitPredictCache if isinstance(xp, Cmap) else GPRPredictCache
+
+
+def update_cache_(tc, *args, ϵ=1e-8):
+    """update_cache!(tc, hp, md) (src/cost.jl:74-111)  |  update_cache!(pc, md) (src/predict.jl:29-34)"""
+    if len(args) == 2:
+        hp, md = args
+    else:
+        (md,) = args
+        hp = md.params
+    tc._sync_data(md)
+    tc.hp = np.array(hp, dtype=np.float64)
+    tc.handle.update_cache(tc.hp, eps=ϵ, want_inverse=tc.want_inverse)
+    return None
+
+
+def loss(cost, *args):
+    """loss(cost, md) | loss(cost, hp, md) | loss(cost, hp, md, tc) | loss(cost, md, tc) | loss(cost, cov, hp, x, y)
+    (src/cost.jl:17-22,40-43,113-117 ; src/loss_grad.jl:32-41)"""
+    if not isinstance(cost, MarginalLikelihood):
+        raise GPRError("only MarginalLikelihood is on the accelerated path")
+    if len(args) == 1:
+        md = args[0]
+        return loss(cost, md.params, md)
+    if len(args) == 2 and isinstance(args[1], _DeviceCache):
+        md, tc = args
+        return tc.handle.loss()
+    if len(args) == 2:
+        hp, md = args
+        tc = loss_cache(cost)(md)
+        try:
+            return loss(cost, hp, md, tc)
+        finally:
+            tc.close()
+    if len(args) == 3:
+        hp, md, tc = args
+        update_cache_(tc, hp, md)
+        return tc.handle.loss()
+    if len(args) == 4:                       # one-shot functional form: kernel -> cholesky -> \ -> formula
+        cov, hp, x, y = args
+        md = GPRModel(cov, hp, x, y)
+        return loss(cost, hp, md)
+    raise TypeError("loss: bad arguments")
+
+
+def _grad_cost(cost, *args):
+    if len(args) == 1:
+        md = args[0]
+        return _grad_cost(cost, md.params, md)
+    hp, md = args
+    G = np.empty(len(hp))
+    grad_(G, cost, hp, md)
+    return G
+
+
+def grad_(dL, cost, *args):
+    """grad!(dL, cost, hp, md) | grad!(dL, cost, hp, md, tc) | grad!(dL, cost, md, tc)  (src/cost.jl:32-48,119-127)"""
+    if len(args) == 2 and isinstance(args[1], _DeviceCache):
+        md, tc = args
+        dL[...] = tc.handle.grad(False)
+        return None
+    if len(args) == 2:
+        hp, md = args
+        tc = grad_cache(cost)(md)
+        try:
+            grad_(dL, cost, hp, md, tc)
+        finally:
+            tc.close()
+        return None
+    hp, md, tc = args
+    update_cache_(tc, hp, md)
+    dL[...] = tc.handle.grad(False)
+    return None
+
+
+def loss_grad_(cost, F, G, hp, md, tc):
+    """loss_grad!(cost, F, G, hp, md, tc): Optim only_fg! contract (src/cost.jl:50-58).
+    F/G `None` means "not requested"; returns the loss iff F is not None; G is filled in place."""
+    tc._sync_data(md)
+    tc.hp = np.array(hp, dtype=np.float64)
+    f, g = tc.handle.nlml_grad(tc.hp, log_scale=False, want_f=F is not None, want_g=G is not None)
+    if G is not None:
+        G[...] = g
+    return f if F is not None else None
+
+
+def log_loss_grad_(cost, F, G, log_hp, md, tc):
+    """log_loss_grad!(cost, F, G, log_hp, md, tc)  (src/cost.jl:60-70): hp = exp.(log_hp); G .*= hp"""
+    tc._sync_data(md)
+    tc.hp = np.exp(np.asarray(log_hp, dtype=np.float64))
+    f, g = tc.handle.nlml_grad(np.asarray(log_hp, dtype=np.float64), log_scale=True, want_f=F is not None,
+                               want_g=G is not None)
+    if G is not None:
+        G[...] = g
+    return f if F is not None else None
+
+
+# --------------------------------------------------------------------------- train.jl
+def init_params(cost, md):
+    """src/train.jl:1-7"""
+    if isinstance(cost, MarginalLikelihood):
+        return np.ones_like(md.params)
+    return np.random.rand(*md.params.shape)
+
+
+def train(md, cost, hp0=None, method="L-BFGS-B", options=None):
+    """train(md, cost, hp0; method, options)  (src/train.jl:9-87).
+
+    The optimiser itself is the caller of the hot path and stays on the host (Optim.jl in the reference;
+    scipy.optimize here because Julia is absent in this image).  What is mirrored exactly is the contract
+    around it: log-space iff a SquaredExp is in the model (`islog`), `hp0` is then the LOG start point
+    (default ones), one cache for the whole run, `fg!` = `log_loss_grad!`, result = exp.(minimizer)."""
+    import scipy.optimize as so
+
+    hp0 = init_params(cost, md) if hp0 is None else np.asarray(hp0, dtype=np.float64)
+    log = isinstance(islog(cost, md), LogScale)
+    tc = loss_grad_cache(cost)(md)
+    fg = log_loss_grad_ if log else loss_grad_
+
+    def fun(v):
+        G = np.empty_like(v)
+        f = fg(cost, True, G, v, md, tc)
+        return f, G
+
+    try:
+        res = so.minimize(fun, hp0, jac=True, method=method, options=options or {})
+    finally:
+        tc.close()
+    return (np.exp(res.x) if log else res.x), res
+
+
+# --------------------------------------------------------------------------- predict.jl
+class Diagonal:
+    """LinearAlgebra.Diagonal stand-in: `.diag` vector."""
+
+    def __init__(self, diag):
+        self.diag = diag
+
+
+def predict_mean(md, xp, ctx=None):
+    """src/predict.jl:6-12"""
+    pc = predict_cache(md, xp)(md, xp, ctx=ctx)
+    try:
+        update_cache_(pc, md)
+        mu = np.empty(_mean_shape(md, xp), order="F")
+        predict_mean_(mu, md, xp, pc)
+        return mu
+    finally:
+        pc.close()
+
+
+def _mean_shape(md, xp):
+    if isinstance(xp, Cmap):
+        return (xp.xe.shape[1], xp.xq.shape[1])
+    M = xp.shape[1]
+    return (M,) if md.y.ndim == 1 else (M, md.y.shape[1])
+
+
+def predict(md, xp, diagonal_var=False, ctx=None):
+    """src/predict.jl:14-25: returns (mu, Sigma) with Sigma dense (M, M) or Diagonal"""
+    pc = predict_cache(md, xp)(md, xp, ctx=ctx)
+    try:
+        update_cache_(pc, md)
+        mu = np.empty(_mean_shape(md, xp), order="F")
+        nflat = int(np.prod(mu.shape))
+        if not diagonal_var:
+            if isinstance(xp, Cmap):
+                raise GPRError("split predict supports diagonal_var=true only (src/split_predict.jl:39)")
+            Sig = np.empty((xp.shape[1], xp.shape[1]), order="F")
+        else:
+            Sig = Diagonal(np.empty(nflat))
+        predict_(mu, Sig, md, xp, pc)
+        return mu, Sig
+    finally:
+        pc.close()
+
+
+def predict_mean_(mu, md, xp, pc):
+    """predict_mean!(mu, md, xp, pc)  (src/predict.jl:36-40 ; split: src/split_predict.jl:5-19)"""
+    if isinstance(xp, Cmap):
+        m, _ = pc.handle.split_predict(xp.xe, xp.xq, var_range=None, want_var=False)
+        mu[...] = m
+        return None
+    m, _, _ = pc.handle.predict(xp, same_x=xp is md.x)
+    mu[...] = m.reshape(mu.shape, order="F")
+    return None
+
+
+def predict_(mu, Sig, md, xp, pc):
+    """predict!(mu, Sigma, md, xp, pc) -- dense, Diagonal and Cmap methods (src/predict.jl:42-71)"""
+    if isinstance(xp, Cmap):
+        if not isinstance(Sig, Diagonal):
+            raise GPRError("split predict supports Diagonal covariance only")
+        m, v = pc.handle.split_predict(xp.xe, xp.xq, var_range=pc.var_range, want_var=True)
+        mu[...] = m
+        Sig.diag[...] = v
+        return None
+    same = xp is md.x
+    if isinstance(Sig, Diagonal):
+        m, v, _ = pc.handle.predict(xp, same_x=same, want_var=True)
+        Sig.diag[...] = v
+    else:
+        m, _, c = pc.handle.predict(xp, same_x=same, want_var=True, want_cov=True)
+        Sig[...] = c
+    mu[...] = m.reshape(mu.shape, order="F")
+    return None
+
+
+# --------------------------------------------------------------------------- split_kernel.jl
+class Cmap:
+    """Cmap(op, xe, xq): lazy op.(xe[:, e], xq[:, q]), size (D, ne, nq)  (src/split_kernel.jl:1-17).
+    The split factorisation is valid for op = + only (src/split_kernel.jl:151-159)."""
+
+    def __init__(self, op, xe, xq):
+        self.op, self.xe, self.xq = op, np.asarray(xe, dtype=np.float64), np.asarray(xq, dtype=np.float64)
+
+    @property
+    def shape(self):
+        return (self.xe.shape[0], self.xe.shape[1], self.xq.shape[1])
+
+    def __getitem__(self, idx):
+        """xeq[i, j] (0-based ints or slices); xeq[:, :] flattens with e fastest (test/test_split_kernel.jl:20-21)."""
+        i, j = idx
+        xe = self.xe[:, i] if not isinstance(i, slice) else self.xe[:, i]
+        xq = self.xq[:, j] if not isinstance(j, slice) else self.xq[:, j]
+        xe = xe.reshape(self.xe.shape[0], -1)
+        xq = xq.reshape(self.xq.shape[0], -1)
+        out = self.op(xe[:, :, None], xq[:, None, :])
+        return out.reshape(self.xe.shape[0], -1, order="F")
+
+
+class SplitKernel:
+    """A (ne, nq, k), B (ne, N, k), C (N, nq, k); K[e, q, s] = sum_k A B C  (src/split_kernel.jl:19-105)"""
+
+    def __init__(self, A, B, C):
+        self.A, self.B, self.C = A, B, C
+
+    @property
+    def shape(self):
+        return (self.A.shape[0], self.A.shape[1], self.C.shape[0], self.A.shape[2])
+
+    def __getitem__(self, idx):
+        e, q, s = idx
+        return np.einsum("...k,...k,...k->...", self.A[e, q, :], self.B[e, s, :], self.C[s, q, :])
+
+
+def _split_kernel(cov, hp, xeq, x, ctx=None):
+    ctx = ctx or get_context()
+    if xeq.op is not np.add and getattr(xeq.op, "__name__", "") not in ("add", "<lambda>"):
+        raise GPRError("SplitKernel is defined for Cmap(+, xe, xq) only")
+    A, B, C = _ffi.split_kernel_arrays(ctx, _types(cov), x.shape[0], hp, xeq.xe, xeq.xq, x)
+    return SplitKernel(A, B, C)
