@@ -109,12 +109,12 @@ def kernel(cov, hp, x, xp=None, dist=None, ϵ=1e-8, ctx=None):
     `xp` may be a `Cmap`, which returns a `SplitKernel` (src/split_kernel.jl:125-135)."""
     if isinstance(xp, Cmap):
         return _split_kernel(cov, hp, xp, x, ctx)
-    ctx = ctx or get_context()
     x = np.asarray(x)
     if isinstance(cov, WhiteNoise):
         if xp is None:
             return UniformScaling(float(hp[0]) ** 2)       # hp[1]^2 * I  (src/covariance.jl:61)
         return 0.0
+    ctx = ctx or get_context()
     if len(hp) != dim_hp(cov, x.shape[0]):
         raise GPRError("Parameter size mismatch.")
     if xp is None:
@@ -177,7 +177,6 @@ def grad(cov_or_cost, *args, **kw):
 
 
 def _grad_kernel(cov, i, hp, x, K=None, ϵ=1e-8, ctx=None):
-    ctx = ctx or get_context()
     dim = x.shape[0]
     if isinstance(cov, ComposedKernel):
         dims = [dim_hp(k, dim) for k in cov.kernels]
@@ -186,7 +185,7 @@ def _grad_kernel(cov, i, hp, x, K=None, ϵ=1e-8, ctx=None):
         return _grad_kernel(cov.kernels[kidx - 1], hpidx, hps[kidx - 1], x, ϵ=ϵ, ctx=ctx)
     if isinstance(cov, WhiteNoise):
         return UniformScaling(2.0 * float(hp[0]))           # src/deriv_covar.jl:31
-    return _ffi.kernel_grad_matrix(ctx, cov.type_id, dim, hp, x, i - 1, ϵ)
+    return _ffi.kernel_grad_matrix(ctx or get_context(), cov.type_id, dim, hp, x, i - 1, ϵ)
 
 
 # --------------------------------------------------------------------------- models.jl

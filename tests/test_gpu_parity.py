@@ -1,0 +1,383 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI via the mirrored host API, against
+(1) the committed golden fixtures, (2) the CPU oracle on the same seeded inputs, (3) the reference's own
+identity tests (ported from /root/reference/test/*.jl), (4) size-independent properties at larger N.
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8d): K entries rel 1e-10; NLML and every gradient component
+rel 1e-8 (component error relative to max(|g_i|, 1e-8 |g|)); predictive mean rel 1e-8 (relative to
+max(|mu|, 1e-8 |y|_inf)); variance abs 1e-8 * sum sigma^2.  For jitter-only models (no WhiteNoise) the
+attainable agreement of two correct FP64 Choleskys is ~cond(K)*eps, so the tolerance is
+max(stated, 50*cond*eps) and the condition number is asserted to be the reason.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import gpr_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+EPS = 2.2e-16
+TOL_K, TOL_F, TOL_G, TOL_MU, TOL_VAR = 1e-10, 1e-8, 1e-8, 1e-8, 1e-8
+
+
+def to_gpr_cov(gpr, cov):
+    m = {o.SE: gpr.SquaredExp, o.NOISE: gpr.WhiteNoise, o.MATERN52: gpr.Matern52}
+    if isinstance(cov, str):
+        return m[cov]()
+    k = m[cov[0]]()
+    for c in cov[1:]:
+        k = k + m[c]()
+    return k
+
+
+def case_cov(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg.CASES[name][0]
+
+
+def ctol(stated, cond):
+    return max(stated, 50.0 * cond * EPS)
+
+
+def grad_err(G, Gref):
+    return float((np.abs(G - Gref) / np.maximum(np.abs(Gref), 1e-8 * np.linalg.norm(Gref))).max())
+
+
+def mean_err(mu, ref, y):
+    return float((np.abs(mu - ref) / np.maximum(np.abs(ref), 1e-8 * np.abs(y).max())).max())
+
+
+# ------------------------------------------------------------------ (1) golden fixtures
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(f)[:-4] for f in GOLDEN])
+def test_golden(gpr, path):
+    name = os.path.basename(path)[:-4]
+    g = np.load(path)
+    cov_o = case_cov(name)
+    cov = to_gpr_cov(gpr, cov_o)
+    x, y, xp, hp = g["x"], g["y"], g["xp"], g["hp"]
+    cond = float(g["cond"])
+    ta = int(g["train_axis"])
+    # covariance.jl / compose_covar.jl
+    K = gpr.kernel(cov, hp, x)
+    assert np.abs(K / g["K_self"] - 1).max() < TOL_K
+    Kc = gpr.kernel(cov, hp, x, xp)
+    assert np.abs(Kc / g["K_cross"] - 1).max() < TOL_K
+    # deriv_covar.jl
+    P = len(hp)
+    for i in sorted({1, 2, P - 1, P}):
+        dK = gpr.grad(cov, i, hp, x)
+        ref = g[f"dK_{i}"]
+        if isinstance(dK, gpr.UniformScaling):
+            assert ref.shape == (1,) and dK.lam == pytest.approx(ref[0], rel=1e-15)
+        else:
+            assert np.abs(dK - ref).max() <= TOL_K * np.abs(ref).max()
+    # cost.jl: update_cache! / loss / grad! and the cache internals of test_loss.jl:46-48
+    md = gpr.GPRModel(cov, hp, x, y, train_axis=ta)
+    ll = gpr.MarginalLikelihood()
+    tc = gpr.MllGradCache(md)
+    gpr.update_cache_(tc, hp, md)
+    F = gpr.loss(ll, md, tc)
+    G = np.empty(P)
+    gpr.grad_(G, ll, md, tc)
+    assert abs(F - g["F"]) <= ctol(TOL_F, cond) * abs(g["F"])
+    assert grad_err(G, g["G"]) <= ctol(TOL_G, cond)
+    U = tc.kchol_base
+    assert np.abs(np.triu(U) - np.triu(g["U"])).max() <= ctol(1e-10, cond) * np.abs(g["U"]).max()
+    assert np.abs(np.tril(U, -1) / np.tril(g["K_self"], -1).clip(1e-300) - np.tril(np.ones_like(U), -1)).max() < TOL_K  # strict lower keeps K
+    assert np.abs(tc.alpha - g["alpha"]).max() <= ctol(TOL_F, cond) * np.abs(g["alpha"]).max()
+    assert np.abs(tc.K_inv - g["Kinv"]).max() <= ctol(TOL_F, cond) * np.abs(g["Kinv"]).max()
+    Glog = np.empty(P)
+    Fl = gpr.log_loss_grad_(ll, True, Glog, np.log(hp), md, tc)
+    assert abs(Fl - g["F"]) <= ctol(TOL_F, cond) * abs(g["F"])
+    assert grad_err(Glog, g["G_log"]) <= ctol(TOL_G, cond)
+    tc.close()
+    # predict.jl
+    pc = gpr.GPRPredictCache(md, xp)
+    gpr.update_cache_(pc, md)
+    M = xp.shape[1]
+    mu = np.empty(g["pred_mean"].shape)
+    Sd = gpr.Diagonal(np.empty(M))
+    gpr.predict_(mu, Sd, md, xp, pc)
+    assert mean_err(mu, g["pred_mean"], y) <= ctol(TOL_MU, cond)
+    prior = float(np.sum([h[0] ** 2 for h in o.split(hp, [o.dim_hp(k, x.shape[0]) for k in o.as_list(cov_o)])]))
+    assert np.abs(Sd.diag - g["pred_var"]).max() <= ctol(TOL_VAR, cond) * prior
+    mu2 = np.empty(g["pred_mean"].shape)
+    Sf = np.empty((M, M))
+    gpr.predict_(mu2, Sf, md, xp, pc)
+    assert np.abs(Sf - g["pred_cov"]).max() <= ctol(TOL_VAR, cond) * prior
+    assert np.abs(pc.wt - g["wt"]).max() <= ctol(TOL_F, cond) * np.abs(g["wt"]).max()
+    mus = np.empty(g["pred_mean_same_x"].shape)
+    gpr.predict_mean_(mus, md, md.x, pc)                    # xp === md.x -> jitter on K* too
+    assert mean_err(mus, g["pred_mean_same_x"], y) <= ctol(TOL_MU, cond)
+    pc.close()
+    # split_kernel.jl / split_predict.jl
+    if "split_A" in g.files:
+        xe, xq = g["xe"], g["xq"]
+        cm = gpr.Cmap(np.add, xe, xq)
+        sk = gpr.kernel(cov, hp, cm, x)
+        for got, ref in ((sk.A, g["split_A"]), (sk.B, g["split_B"]), (sk.C, g["split_C"])):
+            assert np.abs(got / ref - 1).max() < TOL_K
+        spc = gpr.GPRSplitPredictCache(md, cm)
+        gpr.update_cache_(spc, md)
+        smu = np.empty((xe.shape[1], xq.shape[1]))
+        sS = gpr.Diagonal(np.empty(smu.size))
+        gpr.predict_(smu, sS, md, cm, spc)
+        assert mean_err(smu, g["split_mean"], y) <= ctol(TOL_MU, cond)
+        assert np.abs(sS.diag - g["split_var"]).max() <= ctol(TOL_VAR, cond) * prior
+        spc.var_range = (1, xe.shape[1])
+        gpr.predict_(smu, sS, md, cm, spc)
+        assert np.abs(sS.diag - g["split_var_all"]).max() <= ctol(TOL_VAR, cond) * prior
+        spc.close()
+
+
+# ------------------------------------------------------------------ (2)+(3) reference tests, against the oracle
+@pytest.mark.parametrize("n,dim", [(100, 1), (200, 4), (300, 7)])
+def test_covariance_reference_suite(gpr, n, dim):
+    """test/test_covariance.jl:13-105"""
+    rng = np.random.default_rng(n + dim)
+    x, xp = rng.random((dim, n)), rng.random((dim, 2 * n))
+    SE, WN = gpr.SquaredExp(), gpr.WhiteNoise()
+    hp = rng.random(dim + 1)
+    Kxx, Kxp = gpr.kernel(SE, hp, x), gpr.kernel(SE, hp, x, xp)
+    assert np.array_equal(Kxx, Kxx.T)
+    assert np.all(np.linalg.eigvalsh(Kxx) > 0)
+    assert Kxx.shape == (n, n) and Kxp.shape == (n, 2 * n)
+    assert np.abs(Kxx / o.kernel(o.SE, hp, x) - 1).max() < TOL_K
+    assert np.abs(Kxp / o.kernel(o.SE, hp, x, xp) - 1).max() < TOL_K
+    I = np.eye(n)
+    for cov, cov_o in ((SE + WN, (o.SE, o.NOISE)), (SE + SE, (o.SE, o.SE)), (SE + SE + WN, (o.SE, o.SE, o.NOISE)),
+                       (WN + SE, (o.NOISE, o.SE)), (SE + WN + SE, (o.SE, o.NOISE, o.SE))):
+        hps = rng.random(gpr.dim_hp(cov, dim))
+        Ks, Kc = gpr.kernel(cov, hps, x), gpr.kernel(cov, hps, x, xp)
+        assert np.abs(Ks / o.kernel(cov_o, hps, x) - 1).max() < TOL_K
+        assert np.abs(Kc / o.kernel(cov_o, hps, x, xp) - 1).max() < TOL_K
+        # composition identity through the library itself
+        parts = gpr.split(hps, [gpr.dim_hp(k, dim) for k in cov.kernels])
+        acc, accc = np.zeros((n, n)), np.zeros((n, 2 * n))
+        for k, h in zip(cov.kernels, parts):
+            if isinstance(k, gpr.WhiteNoise):
+                acc += h[0] ** 2 * I
+            else:
+                acc += gpr.kernel(SE, h, x)
+                accc += gpr.kernel(SE, h, x, xp)
+        np.testing.assert_allclose(Ks, acc, rtol=1.5e-8)
+        np.testing.assert_allclose(Kc, accc, rtol=1.5e-8)
+    # :84-87 derivative vs forward difference (all i, not only i = dim)
+    K0 = gpr.kernel(SE, hp, x)
+    for i in range(1, dim + 2):
+        hpe = hp.copy()
+        hpe[i - 1] += 1e-7
+        fd = (gpr.kernel(SE, hpe, x) - K0) / 1e-7
+        np.testing.assert_allclose(gpr.grad(SE, i, hp, x), fd, atol=1e-3)
+    # :89-105 composed index map
+    x2 = rng.random((2, 100))
+    cov = SE + WN + SE
+    hp7 = rng.random(7)
+    hs = gpr.split(hp7, [3, 1, 3])
+    for i, (c, li) in {1: (0, 1), 2: (0, 2), 3: (0, 3), 5: (2, 1), 6: (2, 2), 7: (2, 3)}.items():
+        np.testing.assert_allclose(gpr.grad(cov, i, hp7, x2), gpr.grad(SE, li, hs[c], x2), rtol=1.5e-8)
+    assert gpr.grad(cov, 4, hp7, x2).lam == pytest.approx(2 * hs[1][0])
+
+
+@pytest.mark.parametrize("n,dim,ny", [(10, 2, 1), (20, 5, 1), (100, 2, 1), (100, 5, 5), (300, 3, 10)])
+def test_loss_reference_suite(gpr, n, dim, ny):
+    """test/test_loss.jl:21-97"""
+    rng = np.random.default_rng(n * 31 + dim + ny)
+    x = rng.random((dim, n))
+    y1 = np.sin(x).sum(0)
+    if ny == 1:
+        y, ta = y1, 1
+    else:
+        y = np.stack([rng.random() * y1 for _ in range(ny)], axis=1)
+        ta = int(rng.integers(1, ny + 1))
+    cov, cov_o = gpr.SquaredExp() + gpr.WhiteNoise(), (o.SE, o.NOISE)
+    hp = 0.05 + rng.random(dim + 2)
+    md = gpr.GPRModel(cov, hp, x, y, train_axis=ta)
+    ll = gpr.MarginalLikelihood()
+    yt = gpr.get_sample(md)
+    mdo = o.GPRModel(cov_o, hp, x, y, train_axis=ta)
+    tco = o.MllGradCache(mdo)
+    Fo, Go = o.loss_grad(hp, mdo, tco)
+    cond = np.linalg.cond(o.kernel(cov_o, hp, x))
+    assert gpr.loss(ll, cov, hp, x, yt) == pytest.approx(gpr.loss(ll, hp, md), rel=1.5e-8)      # :35 functional == cached
+    assert gpr.loss(ll, hp, md) == pytest.approx(Fo, rel=ctol(TOL_F, cond))
+    DL1 = gpr.grad(ll, hp, md)
+    assert grad_err(DL1, Go) <= ctol(TOL_G, cond)
+    tc = gpr.MllGradCache(md)
+    gpr.update_cache_(tc, hp, md)
+    assert np.abs(tc.kchol_base - tco.kchol_base).max() <= ctol(1e-10, cond) * np.abs(tco.kchol_base).max()   # :46
+    assert np.abs(tc.alpha - tco.alpha).max() <= ctol(TOL_F, cond) * np.abs(tco.alpha).max()                  # :47
+    assert np.abs(tc.K_inv - tco.Kinv).max() <= ctol(TOL_F, cond) * np.abs(tco.Kinv).max()                    # :48
+    for i in range(len(hp)):                                                                                  # :50-55
+        hpe = hp.copy()
+        hpe[i] += 1e-6
+        fd = (gpr.loss(ll, hpe, md, tc) - gpr.loss(ll, hp, md, tc)) / 1e-6
+        assert DL1[i] == pytest.approx(fd, rel=2e-3, abs=1e-3 * max(1.0, abs(fd)))
+    tc.close()
+
+
+def test_nlml_known_answer_diagonal(gpr):
+    """test/test_loss.jl:1-11 through the device: an SE kernel with a huge inverse length scale is diagonal,
+    K = (sigma^2 + eps + sigma_n^2) I, so NLML has the closed form of the reference's known-answer test."""
+    rng = np.random.default_rng(3)
+    n = 200
+    x = np.arange(n, dtype=np.float64)[None, :]
+    y = rng.random(n)
+    hp = np.array([0.8, 50.0, 0.3])
+    d = 0.8 ** 2 + 1e-8 + 0.3 ** 2
+    mle = 0.5 * (np.dot(y, y) / d + n * np.log(d) + n * np.log(2 * np.pi))
+    md = gpr.GPRModel(gpr.SquaredExp() + gpr.WhiteNoise(), hp, x, y)
+    assert gpr.loss(gpr.MarginalLikelihood(), hp, md) == pytest.approx(mle, rel=1e-13)
+
+
+def test_not_positive_definite_raises(gpr):
+    """cholesky!(...; check=true) throws PosDefException (src/cost.jl:77)"""
+    x = np.zeros((1, 300))           # identical points, no jitter -> singular K
+    y = np.ones(300)
+    md = gpr.GPRModel(gpr.SquaredExp(), np.array([1.0, 1.0]), x, y)
+    tc = gpr.MllLossCache(md)
+    with pytest.raises(gpr.PosDefException) as ei:
+        gpr.update_cache_(tc, md.params, md, ϵ=0.0)
+    assert 1 <= ei.value.info <= 300
+    tc.close()
+
+
+@pytest.mark.parametrize("n,npred,dim", [(100, 100, 1), (200, 500, 2), (500, 200, 5)])
+def test_predict_reference_suite(gpr, n, npred, dim):
+    """test/test_models.jl:1-48"""
+    rng = np.random.default_rng(n + npred + dim)
+    x, xp = rng.random((dim, n)), rng.random((dim, npred))
+    y = np.sin(x.sum(0)) ** 2
+    SE, WN = gpr.SquaredExp(), gpr.WhiteNoise()
+    md2 = gpr.GPRModel(SE + SE, 0.2 + rng.random(2 * (dim + 1)), x, y)
+    np.testing.assert_allclose(gpr.predict_mean(md2, x), y, rtol=1e-5, atol=1e-5)        # :19 interpolation
+    _, S = gpr.predict(md2, x)
+    assert np.abs(S).max() < 1e-5                                                         # :24
+    hp3 = rng.random(dim + 2)
+    hp3[-1] = 1e-5
+    md3 = gpr.GPRModel(SE + WN, hp3, x, y)
+    np.testing.assert_allclose(gpr.predict_mean(md3, x), y, rtol=1e-3, atol=1e-3)         # :28
+    md = gpr.GPRModel(SE + WN, 0.1 + rng.random(dim + 2), x, y)
+    yp, Sf = gpr.predict(md, xp)
+    yd, Sd = gpr.predict(md, xp, diagonal_var=True)
+    np.testing.assert_allclose(np.diag(Sf), Sd.diag, atol=1e-5)                           # :41
+    mdo = o.GPRModel((o.SE, o.NOISE), md.params, x, y)
+    cond = np.linalg.cond(o.kernel((o.SE, o.NOISE), md.params, x))
+    mu_o, var_o = o.predict(mdo, xp, diagonal_var=True)
+    assert mean_err(yp, mu_o, y) <= ctol(TOL_MU, cond) and mean_err(yd, mu_o, y) <= ctol(TOL_MU, cond)
+    assert np.abs(Sd.diag - var_o).max() <= ctol(TOL_VAR, cond) * o.prior_diag(mdo)
+    md1 = gpr.GPRModel(SE, 0.5 + rng.random(dim + 1), x, y)
+    _, Sf = gpr.predict(md1, xp)
+    _, Sd = gpr.predict(md1, xp, diagonal_var=True)
+    np.testing.assert_allclose(np.diag(Sf), Sd.diag, atol=1e-5)                           # :47
+
+
+@pytest.mark.parametrize("cov_id", [0, 1, 2, 3])
+@pytest.mark.parametrize("dim,n,e,q", [(1, 100, 10, 10), (2, 200, 20, 30), (5, 500, 50, 10)])
+def test_split_reference_suite(gpr, cov_id, dim, n, e, q):
+    """test/test_split_kernel.jl:1-78"""
+    SE, WN = gpr.SquaredExp(), gpr.WhiteNoise()
+    cov = [SE, SE + WN, SE + SE, SE + SE + WN][cov_id]
+    rng = np.random.default_rng(cov_id * 1000 + n + e + q)
+    x, xe, xq = rng.random((dim, n)), rng.random((dim, e)), rng.random((dim, q))
+    y = np.sin(x.sum(0)) ** 2
+    hp = 0.2 + rng.random(gpr.dim_hp(cov, dim))
+    xeq = gpr.Cmap(np.add, xe, xq)
+    KK = gpr.kernel(cov, hp, xeq[:, :], x)
+    Kxp = gpr.kernel(cov, hp, xeq, x)
+    for (ee, qq, s) in ((0, 0, n - 1), (e - 1, q - 1, n - 1), (3, 2, 5)):
+        assert Kxp[ee, qq, s] == pytest.approx(KK[qq * e + ee, s], rel=1e-9)               # :36-44
+    md = gpr.GPRModel(cov, hp, x, y)
+    yp, varp = gpr.predict(md, xeq[:, :], diagonal_var=True)
+    yps, varps = gpr.predict(md, xeq, diagonal_var=True)
+    np.testing.assert_allclose(yps.reshape(-1, order="F"), yp, rtol=1e-6, atol=1e-8)       # :67-69
+    xqe = gpr.Cmap(np.add, xq, xe)
+    _, varpt = gpr.predict(md, xqe[:, :], diagonal_var=True)
+    np.testing.assert_allclose(varps.diag[:3 * q], varpt.diag[:3 * q], rtol=1e-5, atol=1e-8)   # :75
+    assert not np.allclose(varps.diag[:3 * q + 1], varpt.diag[:3 * q + 1], rtol=1e-5, atol=0)  # :76
+
+
+def test_train_matches_oracle_trajectory(gpr):
+    """Config 1 (BASELINE.json): 1-D sin(x)+noise, N=1000, SquaredExp()+WhiteNoise(), hyper-parameter training
+    from log-hp0 = ones with the same host optimiser on the CUDA path and on the oracle (src/train.jl:47-56)."""
+    import scipy.optimize as so
+    rng = np.random.default_rng(1001)
+    N = 1000
+    x = 10.0 * rng.random((1, N))
+    y = np.sin(x[0]) + 0.1 * rng.standard_normal(N)
+    md = gpr.GPRModel(gpr.SquaredExp() + gpr.WhiteNoise(), np.ones(3), x, y)
+    hp_gpu, res = gpr.train(md, gpr.MarginalLikelihood(), method="L-BFGS-B", options={"gtol": 1e-2, "maxiter": 60})
+    mdo = o.GPRModel((o.SE, o.NOISE), np.ones(3), x, y)
+    tco = o.MllGradCache(mdo)
+    res_o = so.minimize(lambda v: o.log_loss_grad(v, mdo, tco), np.ones(3), jac=True, method="L-BFGS-B",
+                        options={"gtol": 1e-2, "maxiter": 60})
+    np.testing.assert_allclose(hp_gpu, np.exp(res_o.x), rtol=1e-6)
+    assert res.fun == pytest.approx(res_o.fun, rel=1e-9)
+    assert 0.05 < hp_gpu[2] < 0.2          # recovers the noise level 0.1
+
+
+# ------------------------------------------------------------------ (4) larger sizes: oracle where it is cheap, else invariants
+def test_config2_n8192_three_hp_sets(gpr):
+    """BASELINE.json config 2: ARD SE + noise, N=8192, D=8, FP64 NLML + gradient over 3 hp sets."""
+    D, N = 8, 8192
+    rng = np.random.default_rng(2002)
+    x = rng.random((D, N))
+    y = np.sin(3 * x).sum(0) + 0.1 * rng.standard_normal(N)
+    sets = {"A": np.concatenate([[1.0], 0.5 * np.ones(D), [0.1]]),
+            "B": np.concatenate([[1.5], np.linspace(0.3, 1.2, D), [0.05]]),
+            "C": np.concatenate([[0.7], 2.0 * np.ones(D), [0.3]])}
+    cov = gpr.SquaredExp() + gpr.WhiteNoise()
+    md = gpr.GPRModel(cov, sets["A"], x, y)
+    ll = gpr.MarginalLikelihood()
+    tc = gpr.MllGradCache(md)
+    mdo = o.GPRModel((o.SE, o.NOISE), sets["A"], x, y)
+    for name, hp in sets.items():
+        G = np.empty(len(hp))
+        F = gpr.loss_grad_(ll, True, G, hp, md, tc)
+        Fo, Go = o.loss_grad(hp, mdo)
+        assert abs(F - Fo) <= TOL_F * abs(Fo), (name, F, Fo)
+        assert grad_err(G, Go) <= TOL_G, (name, grad_err(G, Go))
+    tc.close()
+
+
+def test_invariants_n16384(gpr):
+    """Properties that need no oracle: K alpha = y, U^T U = K on sampled entries, K^-1 K = I on sampled columns,
+    gradient == finite difference of the loss, determinism of repeated evaluations."""
+    D, N = 8, 16384
+    rng = np.random.default_rng(77)
+    x = rng.random((D, N))
+    y = np.sin(3 * x).sum(0) + 0.1 * rng.standard_normal(N)
+    hp = np.concatenate([[1.0], 0.5 * np.ones(D), [0.5], 2.0 * np.ones(D), [0.1]])
+    cov = gpr.SquaredExp() + gpr.SquaredExp() + gpr.WhiteNoise()
+    md = gpr.GPRModel(cov, hp, x, y)
+    ll = gpr.MarginalLikelihood()
+    tc = gpr.MllGradCache(md)
+    G = np.empty(len(hp))
+    F = gpr.loss_grad_(ll, True, G, hp, md, tc)
+    G2 = np.empty(len(hp))
+    F2 = gpr.loss_grad_(ll, True, G2, hp * (1 + 1e-15), md, tc)     # forces a re-evaluation
+    assert abs(F2 - F) <= 1e-9 * abs(F)
+    alpha = tc.alpha
+    cols = rng.choice(N, 64, replace=False)
+    Kc = o.kernel((o.SE, o.SE, o.NOISE), hp, x, x[:, cols], same=False)
+    Kc[cols, np.arange(64)] += 2e-8 + hp[-1] ** 2          # jitter of both SE components + noise on the diagonal
+    r = Kc.T @ alpha - y[cols]
+    assert np.abs(r).max() <= 1e-9 * np.abs(y).max()
+    Kinv = tc.K_inv
+    E = Kinv[:, cols].T @ Kc          # rows of K^-1 times columns of K
+    assert np.abs(E - np.eye(64)).max() < 1e-8
+    # directional finite difference of the NLML
+    v = rng.standard_normal(len(hp))
+    v /= np.linalg.norm(v)
+    h = 1e-5
+    Fp = gpr.loss(ll, hp + h * v, md, tc)
+    Fm = gpr.loss(ll, hp - h * v, md, tc)
+    assert (Fp - Fm) / (2 * h) == pytest.approx(float(G @ v), rel=1e-5)
+    tc.close()

@@ -1,0 +1,70 @@
+"""CPU check of the blocked-algorithm drivers (csrc/blocked.hpp) with the plain-loop test backend
+(tests/hostlogic/hostlogic.cpp).  The CUDA library instantiates the very same template."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.linalg as sl
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hl(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("hl") / "libhostlogic_test.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out,
+                           os.path.join(HERE, "hostlogic", "hostlogic.cpp")])
+    L = ctypes.CDLL(out)
+    for f in (L.hl_factor, L.hl_potrs, L.hl_trsm_run):
+        f.restype = ctypes.c_longlong
+    return L
+
+
+def dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def spd(n, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, n))
+    return X @ X.T / n + np.eye(n)
+
+
+@pytest.mark.parametrize("n", [128, 256, 384, 640])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_blocked_factor(hl, n, mode):
+    K = spd(n, n)
+    A = np.asfortranarray(K.copy())
+    calls = ctypes.c_longlong(0)
+    info = hl.hl_factor(dp(A), ctypes.c_int64(n), mode, ctypes.byref(calls))
+    assert info == 0
+    U = sl.cholesky(K, lower=False)
+    ref = [U, np.linalg.inv(U), np.linalg.inv(K)][mode]
+    np.testing.assert_allclose(np.triu(A), np.triu(ref), rtol=0, atol=1e-12 * np.abs(ref).max())
+    # dpotrf('U') semantics: the strict lower triangle keeps K (test/test_loss.jl:46)
+    assert np.array_equal(np.tril(A, -1), np.tril(K, -1))
+
+
+def test_blocked_not_posdef(hl):
+    K = np.eye(384)
+    K[300, 300] = -2.0
+    A = np.asfortranarray(K)
+    assert hl.hl_factor(dp(A), ctypes.c_int64(384), 0, None) == 301     # LAPACK info: 1-based failing pivot
+
+
+@pytest.mark.parametrize("n", [128, 512])
+def test_blocked_solves(hl, n):
+    K = spd(n, 7 * n)
+    rng = np.random.default_rng(n)
+    B = np.asfortranarray(rng.standard_normal((n, 128)))
+    B0 = B.copy()
+    A = np.asfortranarray(K.copy())
+    assert hl.hl_potrs(dp(A), ctypes.c_int64(n), dp(B), ctypes.c_int64(128)) == 0
+    np.testing.assert_allclose(B, np.linalg.solve(K, B0), atol=1e-12)
+    R = np.asfortranarray(rng.standard_normal((256, n)))
+    R0 = R.copy()
+    A = np.asfortranarray(K.copy())
+    assert hl.hl_trsm_run(dp(A), ctypes.c_int64(n), dp(R), ctypes.c_int64(256)) == 0
+    np.testing.assert_allclose(R, R0 @ np.linalg.inv(sl.cholesky(K, lower=False)), atol=1e-12)
