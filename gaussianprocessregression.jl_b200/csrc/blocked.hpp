@@ -127,6 +127,30 @@ struct Blocked {
     lauum(W22, ld, n2, b0 + n1 / LEAF);
   }
 
+  // Vector right-hand side (the loss path, y is a vector): same recursions with matrix-vector
+  // primitives, memory bound (reads the triangle once per sweep).
+  //   be.gemv(tA, M, K, alpha, A, lda, x, y):  y(M) += alpha * op(A)(M x K) * x(K)
+  //   be.leaf_mv(tA, dinv_blk, v, s):          v(128) <- s * op(Dinv) * v
+  void trsv_LUT(const double* T, int64_t ldt, int64_t n, int64_t b0, double* v, double s) {
+    if (n == LEAF) { be.leaf_mv('T', dinv_blk(b0), v, s); return; }
+    const int64_t n1 = split(n), n2 = n - n1;
+    trsv_LUT(T, ldt, n1, b0, v, s);
+    be.gemv('T', n2, n1, -s, T + n1 * ldt, ldt, v, v + n1);
+    trsv_LUT(T + n1 + n1 * ldt, ldt, n2, b0 + n1 / LEAF, v + n1, s);
+  }
+  void trsv_LUN(const double* T, int64_t ldt, int64_t n, int64_t b0, double* v, double s) {
+    if (n == LEAF) { be.leaf_mv('N', dinv_blk(b0), v, s); return; }
+    const int64_t n1 = split(n), n2 = n - n1;
+    trsv_LUN(T + n1 + n1 * ldt, ldt, n2, b0 + n1 / LEAF, v + n1, s);
+    be.gemv('N', n1, n2, -s, T + n1 * ldt, ldt, v + n1, v);
+    trsv_LUN(T, ldt, n1, b0, v, s);
+  }
+  // v (n) <- (U^T U)^-1 v
+  void potrsv(const double* U, int64_t ld, int64_t n, double* v) {
+    trsv_LUT(U, ld, n, 0, v, 1.0);
+    trsv_LUN(U, ld, n, 0, v, 1.0);
+  }
+
   // B (n x m) <- (U^T U)^-1 B
   void potrs(const double* U, int64_t ld, int64_t n, double* B, int64_t ldb, int64_t m) {
     trsm_LUT(U, ld, n, 0, B, ldb, m, 1.0);

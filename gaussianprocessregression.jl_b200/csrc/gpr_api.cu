@@ -76,6 +76,17 @@ struct CudaBE {
     note(cudaGetLastError());
     ctx->launches++;
   }
+  void gemv(char tA, int64_t M, int64_t K, double alpha, const double* A, int64_t lda, const double* x, double* y) {
+    if (tA == 'T') gemv_t_kernel<<<(unsigned)((M + 7) / 8), 256, 0, ctx->stream>>>((int)M, (int)K, alpha, A, lda, x, y);
+    else gemv_n_kernel<<<(unsigned)((M + 63) / 64), 256, 0, ctx->stream>>>((int)M, (int)K, alpha, A, lda, x, y);
+    note(cudaGetLastError());
+    ctx->launches++;
+  }
+  void leaf_mv(char tA, const double* dinv, double* v, double s) {
+    leaf_mv_kernel<<<1, 256, LEAF_MV_SMEM_BYTES, ctx->stream>>>(dinv, v, s, tA == 'T' ? 1 : 0);
+    note(cudaGetLastError());
+    ctx->launches++;
+  }
   void copy_upper_128(double* dst, int64_t ldd, const double* src) {
     copy_upper_128_kernel<<<1, 256, 0, ctx->stream>>>(dst, ldd, src);
     note(cudaGetLastError());
@@ -88,6 +99,7 @@ int setup_kernel_attributes(gpr_ctx* ctx) {
   CK(cudaFuncSetAttribute(dgemm128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<false, true>()));
   CK(cudaFuncSetAttribute(dgemm128_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<false, false>()));
   CK(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(leaf_mv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_MV_SMEM_BYTES));
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_SPLIT_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_SPLIT_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -237,7 +249,8 @@ int factor_and_solve(gpr_model* m, const double* hp, double eps, int64_t* info) 
     int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 65535);
     pad_copy_kernel<<<blocks, threads, 0, ctx->stream>>>(m->d_wt, Np, Np, m->nyp, m->d_y, N, N, m->ny);
     ctx->launches++;
-    blk.potrs(m->d_U, Np, Np, m->d_wt, Np, m->nyp);
+    if (m->ny == 1) blk.potrsv(m->d_U, Np, Np, m->d_wt);        // vector y: memory-bound trsv sweeps
+    else blk.potrs(m->d_U, Np, Np, m->d_wt, Np, m->nyp);       // matrix y: GEMM-based trsm on the padded block
     const double* alpha = m->d_wt + (int64_t)(m->train_axis - 1) * Np;
     const double* ycol = m->d_y + (int64_t)(m->train_axis - 1) * N;
     logdet_dot_kernel<<<1, 1024, 0, ctx->stream>>>(m->d_U, Np, N, ycol, alpha, m->d_scal);
@@ -976,9 +989,12 @@ int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, d
   if (e == cudaSuccess) e = cudaMalloc(&dB, sizeof(double) * ldb * b_cols);
   if (e == cudaSuccess) e = cudaMalloc(&dC, sizeof(double) * ldc * N);
   if (e == cudaSuccess) e = cudaMalloc(&dC0, sizeof(double) * ldc * N);
-  if (e == cudaSuccess) e = cudaMemcpy(dA, A, sizeof(double) * lda * a_cols, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(dB, B, sizeof(double) * ldb * b_cols, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(dC0, C, sizeof(double) * ldc * N, cudaMemcpyHostToDevice);
+  // every copy goes through the library stream: a pageable cudaMemcpy on the legacy stream may still be
+  // in flight when work on a non-blocking stream starts
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dA, A, sizeof(double) * lda * a_cols, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dB, B, sizeof(double) * ldb * b_cols, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dC0, C, sizeof(double) * ldc * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   float total = 0.f;
   if (e == cudaSuccess) {
     cudaEvent_t e0, e1;
@@ -995,7 +1011,8 @@ int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, d
       if (r > 0 || reps == 1) total += t;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (e == cudaSuccess) e = cudaMemcpy(C, dC, sizeof(double) * ldc * N, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(C, dC, sizeof(double) * ldc * N, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   }
   if (ms) *ms = total / (float)(reps > 1 ? reps - 1 : 1);
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dC0);
@@ -1021,10 +1038,11 @@ int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, 
       pad.assign((size_t)Np * Np, 0.0);
       for (int64_t j = 0; j < N; ++j) memcpy(&pad[(size_t)j * Np], A + j * N, sizeof(double) * N);
       for (int64_t j = N; j < Np; ++j) pad[(size_t)j * Np + j] = 1.0;
-      e = cudaMemcpy(dA, pad.data(), sizeof(double) * Np * Np, cudaMemcpyHostToDevice);
+      e = cudaMemcpyAsync(dA, pad.data(), sizeof(double) * Np * Np, cudaMemcpyHostToDevice, ctx->stream);
     } else {
-      e = cudaMemcpy(dA, A, sizeof(double) * Np * Np, cudaMemcpyHostToDevice);
+      e = cudaMemcpyAsync(dA, A, sizeof(double) * Np * Np, cudaMemcpyHostToDevice, ctx->stream);
     }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_info, 0, sizeof(long long), ctx->stream);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1040,8 +1058,10 @@ int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, 
     cudaEventElapsedTime(&t, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     rc = check_pending(ctx, "gpr_dbg_factor");
-    if (e == cudaSuccess && !rc)
-      e = cudaMemcpy2D(A, sizeof(double) * N, dA, sizeof(double) * Np, sizeof(double) * N, N, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && !rc) {
+      e = cudaMemcpy2DAsync(A, sizeof(double) * N, dA, sizeof(double) * Np, sizeof(double) * N, N, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
   }
   cudaFree(dA); cudaFree(dinv);
   if (info) *info = h_info;

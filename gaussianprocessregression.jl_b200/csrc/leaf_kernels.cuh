@@ -13,10 +13,16 @@
 namespace gpr {
 
 constexpr int LEAF_N = 128;
-constexpr int LEAF_LDS = 129;                                  // padded smem leading dimension
+constexpr int LEAF_LDS = 129;                                  // padded smem leading dimension of the factor
 constexpr int LEAF_THREADS = 256;
-constexpr int LEAF_PACKED = LEAF_N * (LEAF_N + 1) / 2;
-constexpr size_t LEAF_SMEM_BYTES = (size_t)(LEAF_N * LEAF_LDS + LEAF_PACKED) * sizeof(double);
+constexpr int LEAF_NB = 32;                                    // inner block size
+constexpr int LEAF_WLD = 33;                                   // padded leading dimension of a 32x32 inverse block
+constexpr int LEAF_WBLK = LEAF_NB * LEAF_WLD;                  // doubles per inverse block
+constexpr int LEAF_NWBLK = 10;                                 // upper 4x4 block triangle
+constexpr size_t LEAF_SMEM_BYTES =
+    (size_t)(LEAF_N * LEAF_LDS + LEAF_NWBLK * LEAF_WBLK + 2 * LEAF_NB + LEAF_N + 8) * sizeof(double);
+
+__device__ __forceinline__ int leaf_wblk(int I, int J) { return (J * (J + 1) / 2 + I) * LEAF_WBLK; }   // I <= J
 
 // A: 128x128 block (column major, lda) on the diagonal of the global matrix at
 // global row/col offset goff.  On exit the upper triangle of the block holds U
@@ -24,78 +30,328 @@ constexpr size_t LEAF_SMEM_BYTES = (size_t)(LEAF_N * LEAF_LDS + LEAF_PACKED) * s
 // the reference's dpotrf('U') also leaves in place: test/test_loss.jl:46).
 // dinv: 128x128 (ld 128), receives inv(U) with explicit zeros below the diagonal.
 // info: first failing pivot (1-based global index), LAPACK style; 0 = ok.
+//
+// Blocked with NB = 32 inside one CTA:
+//   per block step J: (1) warp 0 factors the 32x32 diagonal block with one column per lane in registers
+//   (pivot broadcast by shuffle, scaled pivot row exchanged through a 2 x 32 double buffer, one
+//   __syncwarp per pivot), (2) forward substitution of the 32-row panel, one column per thread,
+//   (3) rank-32 update of the trailing upper triangle.  The inverse is formed block-wise: the four
+//   diagonal 32x32 inverses by four warps (branch-free back substitution in registers), then the six
+//   off-diagonal blocks in three rounds of small block products.
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 potrf_leaf_kernel(double* __restrict__ A, long long lda, double* __restrict__ dinv, long long* info, long long goff) {
   extern __shared__ __align__(16) double leaf_smem[];
-  double* S = leaf_smem;                          // S(r,c) = S[c*LEAF_LDS + r]
-  double* Wp = leaf_smem + LEAF_N * LEAF_LDS;     // packed upper inverse: W(i,j) = Wp[j*(j+1)/2 + i]
-  const int tid = threadIdx.x;
+  double* S = leaf_smem;                                   // S(r,c) = S[c*LEAF_LDS + r]
+  double* W = S + LEAF_N * LEAF_LDS;                        // 10 inverse blocks, block (I,J) at leaf_wblk(I,J), (r,c) at [c*33 + r]
+  double* rowbuf = W + LEAF_NWBLK * LEAF_WBLK;              // 2 x 32
+  double* rinvs = rowbuf + 2 * LEAF_NB;                     // 128: 1 / U_kk
+  int* flag = reinterpret_cast<int*>(rinvs + LEAF_N);       // failure flag
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int idx = tid; idx < LEAF_N * LEAF_N; idx += LEAF_THREADS) {
-    const int r = idx & (LEAF_N - 1), c = idx >> 7;
-    S[c * LEAF_LDS + r] = A[r + (long long)c * lda];
+  if (tid == 0) *flag = 0;
+  // load the block: 64 elements per thread, 8 independent loads in flight
+#pragma unroll 1
+  for (int q0 = 0; q0 < 64; q0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = tid + LEAF_THREADS * (q0 + q);
+      v[q] = A[(idx & 127) + (long long)(idx >> 7) * lda];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = tid + LEAF_THREADS * (q0 + q);
+      S[(idx >> 7) * LEAF_LDS + (idx & 127)] = v[q];
+    }
   }
   __syncthreads();
 
-  // right-looking U^T U factorization of the upper triangle
-  const int j = tid & (LEAF_N - 1);
-  const int half = tid >> 7;
-  bool failed = false;
-  for (int k = 0; k < LEAF_N; ++k) {
-    const double piv = S[k * LEAF_LDS + k];
-    if (!(piv > 0.0)) {   // also catches NaN
-      if (tid == 0 && *info == 0) *info = goff + k + 1;
-      failed = true;
-      break;
-    }
-    const double d = sqrt(piv);
-    const double inv = 1.0 / d;
-    __syncthreads();   // everyone has read the pivot
-    if (half == 0) {
-      if (j > k) S[j * LEAF_LDS + k] *= inv;
-      else if (j == k) S[k * LEAF_LDS + k] = d;
+#pragma unroll 1
+  for (int J = 0; J < 4; ++J) {
+    const int o = J * LEAF_NB;
+    // ---- (1) diagonal block, warp 0: lane j owns column j (rows 0..j used)
+    if (warp == 0) {
+      double a[LEAF_NB];
+#pragma unroll
+      for (int i = 0; i < LEAF_NB; ++i) a[i] = S[(o + lane) * LEAF_LDS + o + i];
+      bool bad = false;
+#pragma unroll
+      for (int k = 0; k < LEAF_NB; ++k) {
+        const double piv = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(piv > 0.0)) {          // uniform across the warp; also catches NaN
+          if (lane == 0) { if (*info == 0) *info = goff + o + k + 1; *flag = 1; }
+          bad = true;
+          break;
+        }
+        const double rinv = rsqrt(piv);
+        if (lane == k) { a[k] = piv * rinv; rinvs[o + k] = rinv; }
+        else if (lane > k) a[k] *= rinv;                     // u_kj, row k of U in column j
+        double* buf = rowbuf + (k & 1) * LEAF_NB;
+        if (lane > k) buf[lane] = a[k];
+        __syncwarp();
+        if (lane > k) {
+          const double ukj = a[k];
+#pragma unroll
+          for (int i = k + 1; i < LEAF_NB; ++i)
+            if (i <= lane) a[i] -= buf[i] * ukj;             // a_ij -= u_ki u_kj
+        }
+      }
+      if (!bad) {
+#pragma unroll
+        for (int i = 0; i < LEAF_NB; ++i)
+          if (i <= lane) S[(o + lane) * LEAF_LDS + o + i] = a[i];
+      }
     }
     __syncthreads();
-    if (j > k) {
-      const double ukj = S[j * LEAF_LDS + k];
-      for (int i = k + 1 + half; i <= j; i += 2) S[j * LEAF_LDS + i] -= S[i * LEAF_LDS + k] * ukj;
+    if (*flag) break;
+    // ---- (2) panel: U(o.., c) = U_JJ^-T A(o.., c), one column per thread
+    const int rem = LEAF_N - o - LEAF_NB;
+    if (tid < rem) {
+      const int c = o + LEAF_NB + tid;
+      double b[LEAF_NB];
+#pragma unroll
+      for (int r = 0; r < LEAF_NB; ++r) b[r] = S[c * LEAF_LDS + o + r];
+#pragma unroll
+      for (int k = 0; k < LEAF_NB; ++k) {
+        const double xk = b[k] * rinvs[o + k];
+        b[k] = xk;
+#pragma unroll
+        for (int r = k + 1; r < LEAF_NB; ++r) b[r] -= S[(o + r) * LEAF_LDS + o + k] * xk;   // U(k,r)
+      }
+#pragma unroll
+      for (int r = 0; r < LEAF_NB; ++r) S[c * LEAF_LDS + o + r] = b[r];
+    }
+    __syncthreads();
+    // ---- (3) trailing update of the upper triangle: S(i,c) -= sum_k U(o+k,i) U(o+k,c)
+    {
+      const int c = tid & 127, part = tid >> 7;
+      if (c >= o + LEAF_NB) {
+        double u[LEAF_NB];
+#pragma unroll
+        for (int k = 0; k < LEAF_NB; ++k) u[k] = S[c * LEAF_LDS + o + k];
+        for (int i = o + LEAF_NB + part; i <= c; i += 2) {
+          const double* ui = S + i * LEAF_LDS + o;
+          double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+          for (int k = 0; k < LEAF_NB; k += 4) {
+            d0 += ui[k] * u[k]; d1 += ui[k + 1] * u[k + 1]; d2 += ui[k + 2] * u[k + 2]; d3 += ui[k + 3] * u[k + 3];
+          }
+          S[c * LEAF_LDS + i] -= (d0 + d1) + (d2 + d3);
+        }
+      }
     }
     __syncthreads();
   }
-  __syncthreads();
+  const bool failed = (*flag != 0);
 
   // write U (upper part only)
-  for (int idx = tid; idx < LEAF_N * LEAF_N; idx += LEAF_THREADS) {
-    const int r = idx & (LEAF_N - 1), c = idx >> 7;
-    if (r <= c) A[r + (long long)c * lda] = S[c * LEAF_LDS + r];
-  }
-
-  // inverse of the upper factor, column j owned by thread j (row sweep from the bottom)
-  if (!failed && tid < LEAF_N) {
-    const int cj = tid;
-    double* w = Wp + cj * (cj + 1) / 2;
-    for (int i = LEAF_N - 1; i >= 0; --i) {   // same i in every lane: U(i,k) reads are broadcasts
-      if (i > cj) continue;
-      double s0 = (i == cj) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int k = i + 1;
-      for (; k + 3 <= cj; k += 4) {
-        s0 -= S[k * LEAF_LDS + i] * w[k];
-        s1 -= S[(k + 1) * LEAF_LDS + i] * w[k + 1];
-        s2 -= S[(k + 2) * LEAF_LDS + i] * w[k + 2];
-        s3 -= S[(k + 3) * LEAF_LDS + i] * w[k + 3];
-      }
-      for (; k <= cj; ++k) s0 -= S[k * LEAF_LDS + i] * w[k];
-      w[i] = ((s0 + s1) + (s2 + s3)) / S[i * LEAF_LDS + i];
+  if (!failed) {
+    for (int idx = tid; idx < LEAF_N * LEAF_N; idx += LEAF_THREADS) {
+      const int r = idx & (LEAF_N - 1), c = idx >> 7;
+      if (r <= c) A[r + (long long)c * lda] = S[c * LEAF_LDS + r];
     }
   }
-  __syncthreads();
+
+  if (!failed) {
+    // ---- inverse, diagonal blocks: warp J, lane j -> column j of inv(U_JJ); rows k > j come out as exact zeros
+    if (warp < 4) {
+      const int o = warp * LEAF_NB;
+      double sacc[LEAF_NB];
+#pragma unroll
+      for (int i = 0; i < LEAF_NB; ++i) sacc[i] = (i == lane) ? 1.0 : 0.0;
+      double* wd = W + leaf_wblk(warp, warp) + lane * LEAF_WLD;
+#pragma unroll
+      for (int k = LEAF_NB - 1; k >= 0; --k) {
+        const double wk = sacc[k] * rinvs[o + k];
+        wd[k] = wk;
+#pragma unroll
+        for (int i = 0; i < k; ++i) sacc[i] -= S[(o + k) * LEAF_LDS + o + i] * wk;   // U(i,k)
+      }
+    }
+    __syncthreads();
+    // ---- off-diagonal blocks, three rounds: W_IJ = W_II * ( - sum_{K=I+1..J} U_IK W_KJ )
+    const int r = lane;              // row inside the block
+    const int cbase = warp;          // columns cbase + 8*m
+#pragma unroll 1
+    for (int round = 1; round <= 3; ++round) {
+      const int npairs = 4 - round;  // (I, I+round), I = 0..npairs-1
+      double acc[3][4];
+      // phase A: T = - sum_K U_IK W_KJ  -> written to the (I,J) block as a temporary
+#pragma unroll
+      for (int pidx = 0; pidx < 3; ++pidx) {
+        if (pidx < npairs) {
+          const int I = pidx, Jb = pidx + round;
+          double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+          for (int Kb = I + 1; Kb <= Jb; ++Kb) {
+            const double* Urow = S + (Kb * LEAF_NB) * LEAF_LDS + I * LEAF_NB + r;      // U_IK(r, kk) = Urow[kk*LDS]
+            const double* Wk = W + leaf_wblk(Kb, Jb);                                   // W_KJ(kk, c) = Wk[c*33 + kk]
+#pragma unroll 8
+            for (int kk = 0; kk < LEAF_NB; ++kk) {
+              const double uv = Urow[kk * LEAF_LDS];
+              t0 -= uv * Wk[(cbase) * LEAF_WLD + kk];
+              t1 -= uv * Wk[(cbase + 8) * LEAF_WLD + kk];
+              t2 -= uv * Wk[(cbase + 16) * LEAF_WLD + kk];
+              t3 -= uv * Wk[(cbase + 24) * LEAF_WLD + kk];
+            }
+          }
+          acc[pidx][0] = t0; acc[pidx][1] = t1; acc[pidx][2] = t2; acc[pidx][3] = t3;
+        }
+      }
+#pragma unroll
+      for (int pidx = 0; pidx < 3; ++pidx) {
+        if (pidx < npairs) {
+          double* Tb = W + leaf_wblk(pidx, pidx + round);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) Tb[(cbase + 8 * m) * LEAF_WLD + r] = acc[pidx][m];
+        }
+      }
+      __syncthreads();
+      // phase B: W_IJ = W_II * T
+#pragma unroll
+      for (int pidx = 0; pidx < 3; ++pidx) {
+        if (pidx < npairs) {
+          const int I = pidx, Jb = pidx + round;
+          const double* Wii = W + leaf_wblk(I, I);          // W_II(r, kk) = Wii[kk*33 + r]
+          const double* Tb = W + leaf_wblk(I, Jb);          // T(kk, c)    = Tb[c*33 + kk]
+          double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll 8
+          for (int kk = 0; kk < LEAF_NB; ++kk) {
+            const double wv = Wii[kk * LEAF_WLD + r];
+            t0 += wv * Tb[(cbase) * LEAF_WLD + kk];
+            t1 += wv * Tb[(cbase + 8) * LEAF_WLD + kk];
+            t2 += wv * Tb[(cbase + 16) * LEAF_WLD + kk];
+            t3 += wv * Tb[(cbase + 24) * LEAF_WLD + kk];
+          }
+          acc[pidx][0] = t0; acc[pidx][1] = t1; acc[pidx][2] = t2; acc[pidx][3] = t3;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int pidx = 0; pidx < 3; ++pidx) {
+        if (pidx < npairs) {
+          double* Tb = W + leaf_wblk(pidx, pidx + round);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) Tb[(cbase + 8 * m) * LEAF_WLD + r] = acc[pidx][m];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // dinv (ld 128): inverse in the upper block triangle, explicit zeros elsewhere
   for (int idx = tid; idx < LEAF_N * LEAF_N; idx += LEAF_THREADS) {
-    const int r = idx & (LEAF_N - 1), c = idx >> 7;
+    const int rr = idx & (LEAF_N - 1), cc = idx >> 7;
     double v = 0.0;
-    if (!failed && r <= c) v = Wp[c * (c + 1) / 2 + r];
+    if (!failed && (rr >> 5) <= (cc >> 5)) v = W[leaf_wblk(rr >> 5, cc >> 5) + (cc & 31) * LEAF_WLD + (rr & 31)];
     dinv[idx] = v;
   }
 }
+
+// ---------------------------------------------------------------------------
+// Vector solves (alpha = K^-1 y when y is a vector: ldiv!(alpha, kchol, y), src/cost.jl:79,89,106).
+// Memory-bound matrix-vector kernels over blocks of the factor; every reduction has a fixed order.
+// ---------------------------------------------------------------------------
+// y(M) += alpha * A^T x,  op(A)[m,k] = A[k + m*lda]  (k contiguous): one warp per output element.
+__global__ void __launch_bounds__(256) gemv_t_kernel(int M, int K, double alpha, const double* __restrict__ A,
+                                                     long long lda, const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  const double* col = A + (long long)m * lda;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int k = 2 * lane;
+  for (; k + 192 < K; k += 256) {
+    const double2 a0 = *reinterpret_cast<const double2*>(col + k), a1 = *reinterpret_cast<const double2*>(col + k + 64);
+    const double2 a2 = *reinterpret_cast<const double2*>(col + k + 128), a3 = *reinterpret_cast<const double2*>(col + k + 192);
+    const double2 x0 = *reinterpret_cast<const double2*>(x + k), x1 = *reinterpret_cast<const double2*>(x + k + 64);
+    const double2 x2 = *reinterpret_cast<const double2*>(x + k + 128), x3 = *reinterpret_cast<const double2*>(x + k + 192);
+    s0 += a0.x * x0.x + a0.y * x0.y; s1 += a1.x * x1.x + a1.y * x1.y;
+    s2 += a2.x * x2.x + a2.y * x2.y; s3 += a3.x * x3.x + a3.y * x3.y;
+  }
+  for (; k < K; k += 64) {
+    const double2 a0 = *reinterpret_cast<const double2*>(col + k);
+    const double2 x0 = *reinterpret_cast<const double2*>(x + k);
+    s0 += a0.x * x0.x + a0.y * x0.y;
+  }
+  double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) y[m] += alpha * s;
+}
+
+// y(M) += alpha * A x,  op(A)[m,k] = A[m + k*lda]  (m contiguous): a CTA owns 64 rows, its 8 warps split k.
+__global__ void __launch_bounds__(256) gemv_n_kernel(int M, int K, double alpha, const double* __restrict__ A,
+                                                     long long lda, const double* __restrict__ x, double* __restrict__ y) {
+  __shared__ double red[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * 64 + 2 * lane;
+  double sx0 = 0.0, sy0 = 0.0, sx1 = 0.0, sy1 = 0.0;
+  if (m0 < M) {
+    const double* p = A + m0;
+    int k = warp;
+    for (; k + 24 < K; k += 32) {
+      const double2 a0 = *reinterpret_cast<const double2*>(p + (long long)k * lda);
+      const double2 a1 = *reinterpret_cast<const double2*>(p + (long long)(k + 8) * lda);
+      const double2 a2 = *reinterpret_cast<const double2*>(p + (long long)(k + 16) * lda);
+      const double2 a3 = *reinterpret_cast<const double2*>(p + (long long)(k + 24) * lda);
+      const double x0 = x[k], x1 = x[k + 8], x2 = x[k + 16], x3 = x[k + 24];
+      sx0 += a0.x * x0; sy0 += a0.y * x0; sx1 += a1.x * x1; sy1 += a1.y * x1;
+      sx0 += a2.x * x2; sy0 += a2.y * x2; sx1 += a3.x * x3; sy1 += a3.y * x3;
+    }
+    for (; k < K; k += 8) {
+      const double2 a0 = *reinterpret_cast<const double2*>(p + (long long)k * lda);
+      const double x0 = x[k];
+      sx0 += a0.x * x0; sy0 += a0.y * x0;
+    }
+  }
+  red[warp][2 * lane] = sx0 + sx1;
+  red[warp][2 * lane + 1] = sy0 + sy1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int m = blockIdx.x * 64 + threadIdx.x;
+    if (m < M) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+      y[m] += alpha * s;
+    }
+  }
+}
+
+// v(128) <- s * op(Dinv) v with Dinv a 128x128 block (ld 128); trans != 0: op = transpose.  One CTA.
+__global__ void __launch_bounds__(256, 1) leaf_mv_kernel(const double* __restrict__ dinv, double* __restrict__ v,
+                                                         double s, int trans) {
+  extern __shared__ __align__(16) double mv_smem[];
+  double* S = mv_smem;                       // S(r,c) = S[c*129 + r]
+  double* vs = S + LEAF_N * LEAF_LDS;        // 128
+  double* part = vs + LEAF_N;                // 256
+  const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int q0 = 0; q0 < 64; q0 += 8) {
+    double t[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t[q] = dinv[tid + LEAF_THREADS * (q0 + q)];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int idx = tid + LEAF_THREADS * (q0 + q);
+      S[(idx >> 7) * LEAF_LDS + (idx & 127)] = t[q];
+    }
+  }
+  if (tid < LEAF_N) vs[tid] = v[tid];
+  __syncthreads();
+  const int m = tid & 127, half = tid >> 7;
+  double a0 = 0.0, a1 = 0.0;
+  if (trans) {
+#pragma unroll 8
+    for (int k = half * 64; k < half * 64 + 64; k += 2) { a0 += S[m * LEAF_LDS + k] * vs[k]; a1 += S[m * LEAF_LDS + k + 1] * vs[k + 1]; }
+  } else {
+#pragma unroll 8
+    for (int k = half * 64; k < half * 64 + 64; k += 2) { a0 += S[k * LEAF_LDS + m] * vs[k]; a1 += S[(k + 1) * LEAF_LDS + m] * vs[k + 1]; }
+  }
+  part[tid] = a0 + a1;
+  __syncthreads();
+  if (tid < LEAF_N) v[tid] = s * (part[tid] + part[tid + 128]);
+}
+constexpr size_t LEAF_MV_SMEM_BYTES = (size_t)(LEAF_N * LEAF_LDS + LEAF_N + 256) * sizeof(double);
 
 // dst (128x128 block of a column-major matrix, ldd): upper part <- src (ld 128)
 __global__ void copy_upper_128_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src) {

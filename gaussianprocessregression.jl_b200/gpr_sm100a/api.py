@@ -106,9 +106,9 @@ class UniformScaling:
 
 def kernel(cov, hp, x, xp=None, dist=None, ϵ=1e-8, ctx=None):
     """kernel(K, hp, x[, xp]; ϵ)  (src/covariance.jl:29-47, src/compose_covar.jl:35-45).
-    `xp` may be a `Cmap`, which returns a `SplitKernel` (src/split_kernel.jl:125-135)."""
-    if isinstance(xp, Cmap):
-        return _split_kernel(cov, hp, xp, x, ctx)
+    kernel(cov, hp, xp::Cmap, x) returns a `SplitKernel` (src/split_kernel.jl:125-135)."""
+    if isinstance(x, Cmap):
+        return _split_kernel(cov, hp, x, xp, ctx)
     x = np.asarray(x)
     if isinstance(cov, WhiteNoise):
         if xp is None:

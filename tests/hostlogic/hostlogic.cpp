@@ -58,6 +58,23 @@ struct CpuBE {
       }
     }
   }
+  void gemv(char tA, int64_t M, int64_t K, double alpha, const double* A, int64_t lda, const double* x, double* y) {
+    for (int64_t m = 0; m < M; ++m) {
+      double s = 0.0;
+      for (int64_t k = 0; k < K; ++k) s += ((tA == 'T') ? A[k + m * lda] : A[m + k * lda]) * x[k];
+      y[m] += alpha * s;
+    }
+  }
+  void leaf_mv(char tA, const double* dinv, double* v, double s) {
+    const int n = gpr::LEAF;
+    double tmp[gpr::LEAF];
+    for (int m = 0; m < n; ++m) {
+      double acc = 0.0;
+      for (int k = 0; k < n; ++k) acc += ((tA == 'T') ? dinv[k + m * n] : dinv[m + k * n]) * v[k];
+      tmp[m] = s * acc;
+    }
+    for (int m = 0; m < n; ++m) v[m] = tmp[m];
+  }
   void copy_upper_128(double* dst, int64_t ldd, const double* src) {
     for (int c = 0; c < gpr::LEAF; ++c)
       for (int r = 0; r <= c; ++r) dst[r + c * ldd] = src[r + c * gpr::LEAF];
@@ -87,6 +104,16 @@ long long hl_potrs(double* A, int64_t n, double* B, int64_t m) {
   gpr::Blocked<CpuBE> blk(be, dinv.data());
   blk.potrf(A, n, n, 0);
   blk.potrs(A, n, n, B, n, m);
+  return be.info;
+}
+
+// potrf(A) then v (n) <- A^-1 v through the vector (trsv) recursions
+long long hl_potrsv(double* A, int64_t n, double* v) {
+  CpuBE be;
+  std::vector<double> dinv((size_t)n * 128);
+  gpr::Blocked<CpuBE> blk(be, dinv.data());
+  blk.potrf(A, n, n, 0);
+  blk.potrsv(A, n, n, v);
   return be.info;
 }
 

@@ -17,7 +17,7 @@ def hl(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out,
                            os.path.join(HERE, "hostlogic", "hostlogic.cpp")])
     L = ctypes.CDLL(out)
-    for f in (L.hl_factor, L.hl_potrs, L.hl_trsm_run):
+    for f in (L.hl_factor, L.hl_potrs, L.hl_trsm_run, L.hl_potrsv):
         f.restype = ctypes.c_longlong
     return L
 
@@ -63,6 +63,11 @@ def test_blocked_solves(hl, n):
     A = np.asfortranarray(K.copy())
     assert hl.hl_potrs(dp(A), ctypes.c_int64(n), dp(B), ctypes.c_int64(128)) == 0
     np.testing.assert_allclose(B, np.linalg.solve(K, B0), atol=1e-12)
+    v = rng.standard_normal(n)
+    v0 = v.copy()
+    A = np.asfortranarray(K.copy())
+    assert hl.hl_potrsv(dp(A), ctypes.c_int64(n), dp(v)) == 0
+    np.testing.assert_allclose(v, np.linalg.solve(K, v0), atol=1e-12)
     R = np.asfortranarray(rng.standard_normal((256, n)))
     R0 = R.copy()
     A = np.asfortranarray(K.copy())

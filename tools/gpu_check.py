@@ -51,6 +51,13 @@ def sec_gemm():
         eu = relerr(np.triu(C), np.triu(ref))
         el = float(np.abs(np.tril(C, -1) - np.tril(C0, -1)).max())
         print(f"gemm {tA}{tB} upper-only: upper relerr {eu:.2e}, lower untouched diff {el:.2e}", "OK" if eu < 1e-13 and el == 0 else "BAD")
+        if not (eu < 1e-13 and el == 0):
+            badu = np.argwhere(np.abs(np.triu(C) - np.triu(ref)) > 1e-10)
+            badl = np.argwhere(np.abs(np.tril(C, -1) - np.tril(C0, -1)) > 0)
+            print("   bad upper:", len(badu), badu[:6].tolist(), " bad lower:", len(badl), badl[:6].tolist())
+            if len(badu):
+                i, j = badu[0]
+                print("   C, ref, C0, full-update at first bad upper:", C[i, j], ref[i, j], C0[i, j])
 
 
 def sec_gemm_perf():
