@@ -1,0 +1,149 @@
+# GPRsm100a.jl -- Julia glue binding libgpr_sm100a.so (include/gpr_sm100a.h) into
+# srinix007/GaussianProcessRegression.jl.  SOURCE ONLY: no `julia` binary exists in the build image, so this
+# file has never been executed; the executed binding of the same C ABI is the ctypes layer
+# gaussianprocessregression.jl_b200/gpr_sm100a/_ffi.py, which mirrors it call for call.
+#
+# Seam (SURVEY.md 8b): the reference's callers (train, update_sample!, cv_step!, predict*) only ever touch the
+# non-allocating, cache-based API.  New cache types hold an opaque model handle; the methods below overload
+#     update_cache!(tc, hp, md)                 src/cost.jl:74-111
+#     loss(::MarginalLikelihood, md, tc)        src/cost.jl:113-117
+#     grad!(dL, ::MarginalLikelihood, md, tc)   src/cost.jl:119-127
+#     loss_grad! / log_loss_grad!               src/cost.jl:50-70   (one fused ccall)
+#     update_cache!(pc, md)                     src/predict.jl:29-34
+#     predict_mean! / predict!                  src/predict.jl:36-71, src/split_predict.jl:5-53
+# and `loss_cache / grad_cache / loss_grad_cache / predict_cache` route a wrapped model to them, so
+# `train(SM100(md), MarginalLikelihood(); method = ...)` and `predict(SM100(md), xp)` run unchanged.
+module GPRsm100a
+
+using GaussianProcessRegression
+using LinearAlgebra
+import GaussianProcessRegression: update_cache!, loss, grad!, loss_grad!, log_loss_grad!, loss_cache, grad_cache,
+    loss_grad_cache, predict_cache, predict_mean!, predict!, AbstractGPRModel, AbstractLossCache, AbstractGradCache,
+    AbstractPredictCache, MarginalLikelihood, SquaredExp, WhiteNoise, ComposedKernel, GPRModel, Cmap, get_sample, islog
+
+const LIB = get(ENV, "GPR_SM100A_LIB", "libgpr_sm100a")
+const GPR_KERN_SE, GPR_KERN_NOISE = Cint(1), Cint(2)
+const GPR_FETCH_U, GPR_FETCH_ALPHA, GPR_FETCH_KINV, GPR_FETCH_WT = Cint(0), Cint(1), Cint(2), Cint(3)
+
+mutable struct Ctx
+    h::Ptr{Cvoid}
+    function Ctx(device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:gpr_ctx_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r)
+        rc == 0 || error("gpr_ctx_create: ", unsafe_string(ccall((:gpr_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+        c = new(r[])
+        finalizer(x -> ccall((:gpr_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c)
+    end
+end
+const DEFAULT_CTX = Ref{Union{Nothing,Ctx}}(nothing)
+ctx() = (DEFAULT_CTX[] === nothing && (DEFAULT_CTX[] = Ctx(0)); DEFAULT_CTX[])
+
+function check(c::Ctx, rc::Cint, info::Int64 = 0)
+    rc == 0 && return nothing
+    rc == 1 && throw(PosDefException(info))          # cholesky!(...; check = true), src/cost.jl:77
+    error("libgpr_sm100a: ", unsafe_string(ccall((:gpr_last_error, LIB), Cstring, (Ptr{Cvoid},), c.h)))
+end
+
+comp_types(::SquaredExp) = Cint[GPR_KERN_SE]
+comp_types(K::ComposedKernel) = Cint[k isa WhiteNoise ? GPR_KERN_NOISE : GPR_KERN_SE for k in K.kernels]
+
+"Wrapper that routes a GPRModel to the sm_100a caches (everything else is forwarded)."
+struct SM100{M<:GPRModel} <: AbstractGPRModel{Any,Float64,Vector{Float64},Matrix{Float64}}
+    md::M
+end
+Base.getproperty(s::SM100, f::Symbol) = f === :md ? getfield(s, :md) : getproperty(getfield(s, :md), f)
+GaussianProcessRegression.get_sample(s::SM100) = get_sample(s.md)
+GaussianProcessRegression.islog(c::MarginalLikelihood, s::SM100) = islog(c, s.md)
+
+mutable struct Handle
+    c::Ctx
+    h::Ptr{Cvoid}
+end
+function Handle(md)
+    c = ctx()
+    t = comp_types(md.covar)
+    y = md.y isa Vector ? reshape(md.y, :, 1) : md.y
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:gpr_model_create, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cint}, Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Ref{Ptr{Cvoid}}),
+        c.h, t, length(t), size(md.x, 1), size(md.x, 2), md.x, y, size(y, 2), md.train_axis, r)
+    check(c, rc)
+    h = Handle(c, r[])
+    finalizer(x -> ccall((:gpr_model_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), h)
+end
+
+struct SM100LossCache <: AbstractLossCache;    hp::Vector{Float64}; h::Handle; end
+struct SM100GradCache <: AbstractGradCache;    hp::Vector{Float64}; h::Handle; end
+struct SM100PredictCache <: AbstractPredictCache; h::Handle; end
+struct SM100SplitPredictCache <: AbstractPredictCache; h::Handle; var_range::UnitRange{Int64}; end
+SM100LossCache(md::SM100) = SM100LossCache(copy(md.params), Handle(md))
+SM100GradCache(md::SM100) = SM100GradCache(copy(md.params), Handle(md))
+
+# trait functions (src/cost.jl:10-12, src/predict.jl:1, src/split_predict.jl:1) dispatch on the wrapped model
+# through the cache constructors: loss_cache(cost)(md) in src/train.jl:16,38,49,60,74 calls SM100*Cache(md::SM100)
+GaussianProcessRegression.MllLossCache(md::SM100) = SM100LossCache(md)
+GaussianProcessRegression.MllGradCache(md::SM100) = SM100GradCache(md)
+predict_cache(::SM100, ::AbstractArray) = (md, xp) -> SM100PredictCache(Handle(md))
+predict_cache(::SM100, ::Cmap) = (md, xp) -> SM100SplitPredictCache(Handle(md), 1:3)
+
+function _update!(h::Handle, hp, want_inverse::Bool; ϵ = 1e-8)
+    info = Ref{Int64}(0)
+    rc = ccall((:gpr_update_cache, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cdouble, Cint, Ref{Int64}),
+        h.h, hp, length(hp), ϵ, want_inverse, info)
+    check(h.c, rc, info[])
+end
+update_cache!(tc::SM100LossCache, hp, md) = (tc.hp .= hp; _update!(tc.h, tc.hp, false))
+update_cache!(tc::SM100GradCache, hp, md) = (tc.hp .= hp; _update!(tc.h, tc.hp, true))
+update_cache!(pc::Union{SM100PredictCache,SM100SplitPredictCache}, md) = _update!(pc.h, md.params, false)
+
+function loss(::MarginalLikelihood, md::SM100, tc::Union{SM100LossCache,SM100GradCache})
+    F = Ref{Float64}(0.0)
+    check(tc.h.c, ccall((:gpr_loss, LIB), Cint, (Ptr{Cvoid}, Ref{Float64}), tc.h.h, F))
+    return F[]
+end
+function grad!(∇L, ::MarginalLikelihood, md::SM100, tc::SM100GradCache)
+    check(tc.h.c, ccall((:gpr_grad, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), tc.h.h, 0, ∇L))
+    return nothing
+end
+# fused single-call forms of src/cost.jl:50-70 (Optim only_fg! contract: F / G may be `nothing`)
+function _fg!(F, G, v, tc::SM100GradCache, logscale::Bool)
+    f = Ref{Float64}(0.0); info = Ref{Int64}(0)
+    rc = ccall((:gpr_nlml_grad, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cdouble, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
+        tc.h.h, v, length(v), logscale, 1e-8, F === nothing ? C_NULL : f, G === nothing ? C_NULL : G, info)
+    check(tc.h.c, rc, info[])
+    F === nothing ? nothing : f[]
+end
+loss_grad!(::MarginalLikelihood, F, G, hp, md::SM100, tc::SM100GradCache) = _fg!(F, G, hp, tc, false)
+log_loss_grad!(::MarginalLikelihood, F, G, log_hp, md::SM100, tc::SM100GradCache) = _fg!(F, G, log_hp, tc, true)
+
+"tc.kchol_base / tc.α / tc.K⁻¹ of the reference caches (test/test_loss.jl:46-48)"
+function fetch(h::Handle, which::Cint, dims...)
+    out = Array{Float64}(undef, dims...)
+    check(h.c, ccall((:gpr_fetch, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.h, which, out))
+    out
+end
+
+function predict_mean!(μₚ, md::SM100, xp::AbstractMatrix, pc::SM100PredictCache)
+    rc = ccall((:gpr_predict, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        pc.h.h, xp, size(xp, 2), xp === md.x, μₚ, C_NULL, C_NULL)
+    check(pc.h.c, rc)
+end
+function predict!(μₚ, Σₚ::Diagonal, md::SM100, xp::AbstractMatrix, pc::SM100PredictCache)
+    rc = ccall((:gpr_predict, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        pc.h.h, xp, size(xp, 2), xp === md.x, μₚ, Σₚ.diag, C_NULL)
+    check(pc.h.c, rc)
+end
+function predict!(μₚ, Σₚ::AbstractMatrix, md::SM100, xp::AbstractMatrix, pc::SM100PredictCache)
+    rc = ccall((:gpr_predict, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        pc.h.h, xp, size(xp, 2), xp === md.x, μₚ, C_NULL, Σₚ)
+    check(pc.h.c, rc)
+end
+function predict!(μₚ, Σₚ::Diagonal, md::SM100, xeq::Cmap, pc::SM100SplitPredictCache)
+    rc = ccall((:gpr_split_predict, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
+        pc.h.h, xeq.xe, size(xeq.xe, 2), xeq.xq, size(xeq.xq, 2), first(pc.var_range), last(pc.var_range), μₚ, Σₚ.diag)
+    check(pc.h.c, rc)
+end
+
+end # module
