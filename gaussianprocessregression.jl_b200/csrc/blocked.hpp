@@ -2,10 +2,15 @@
 // column-major factor.  Everything is expressed through three primitives of a
 // backend BE:
 //
-//   be.gemm(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, flags)
+//   be.gemm(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, flags, batch, sA, sB, sC)
+//        strided batch: member z uses A + z*sA, B + z*sB, C + z*sC
+//        flags: BLK_UPPER_ONLY (C diagonal-anchored, only row <= col computed/stored),
+//               BLK_K_FROM_N   (tile column block J contracts over k >= 128*J only: the triangular product W W^T)
 //   be.potrf_leaf(A, lda, Dinv_blk, global_row_offset)   128x128 diagonal block:
 //        A(upper) <- chol(A) (U^T U = A) and Dinv_blk <- inv(U) (full 128x128, zeros below the diagonal)
-//   be.copy_upper_128(dst, ldd, src128)                  dst(upper part of a 128 block) <- src (ld 128)
+//   be.copy_dinv_128(dst, ldd, src128, batch, stride, dstride, full)
+//        dst (128 block; member z at dst + z*stride) <- Dinv block (src + z*dstride); upper part only, or the
+//        full block incl. the explicit zeros below the diagonal when full
 //
 // The product (libgpr_sm100a.so) instantiates this with the CUDA backend
 // (DMMA GEMM + leaf kernels, gpr_api.cu).  tests/hostlogic instantiates it
@@ -30,6 +35,7 @@ namespace gpr {
 
 constexpr int LEAF = 128;
 constexpr int BLK_UPPER_ONLY = 1;   // == GEMM_UPPER_ONLY
+constexpr int BLK_K_FROM_N = 2;     // == GEMM_K_FROM_N
 
 template <class BE>
 struct Blocked {
@@ -42,87 +48,124 @@ struct Blocked {
   static int64_t split(int64_t n) { return ((n / LEAF) / 2) * LEAF; }
 
   // A(upper) <- U with U^T U = A.  A: n x n at the diagonal, global block b0.
-  void potrf(double* A, int64_t ld, int64_t n, int64_t b0) {
-    if (n == LEAF) { be.potrf_leaf(A, ld, dinv_blk(b0), b0 * LEAF); return; }
+  // Right-looking recursion that carries the whole row panel to the right of the block ("mr" further
+  // columns of the same rows): factor the block, apply U^-T to the panel, update everything below/right.
+  // Every launch is as wide as the remaining matrix, so only the last few block columns produce
+  // launches with fewer tiles than SMs.
+  void potrf(double* A, int64_t ld, int64_t n, int64_t b0) { potrf_panel(A, ld, n, 0, b0); }
+
+  void potrf_panel(double* A, int64_t ld, int64_t n, int64_t mr, int64_t b0) {
+    if (n == LEAF) {
+      be.potrf_leaf(A, ld, dinv_blk(b0), b0 * LEAF);
+      if (mr > 0) {
+        double* P = A + (int64_t)LEAF * ld;   // row panel right of the block: 128 x mr
+        be.gemm('T', 'N', LEAF, mr, LEAF, 1.0, dinv_blk(b0), LEAF, P, ld, 0.0, P, ld, 0, 1, 0, 0, 0);
+      }
+      return;
+    }
     const int64_t n1 = split(n), n2 = n - n1;
-    double* A12 = A + n1 * ld;
-    double* A22 = A + n1 + n1 * ld;
-    potrf(A, ld, n1, b0);
-    trsm_LUT(A, ld, n1, b0, A12, ld, n2, 1.0);
-    be.gemm('T', 'N', n2, n2, n1, -1.0, A12, ld, A12, ld, 1.0, A22, ld, BLK_UPPER_ONLY);
-    potrf(A22, ld, n2, b0 + n1 / LEAF);
+    double* A12 = A + n1 * ld;           // n1 x (n2 + mr): rest of the row panel
+    double* A22 = A + n1 + n1 * ld;      // (n2) x (n2 + mr), diagonal anchored
+    potrf_panel(A, ld, n1, n2 + mr, b0);
+    be.gemm('T', 'N', n2, n2 + mr, n1, -1.0, A12, ld, A12, ld, 1.0, A22, ld, BLK_UPPER_ONLY, 1, 0, 0, 0);
+    potrf_panel(A22, ld, n2, mr, b0 + n1 / LEAF);
   }
 
   // B (n x m) <- s * T^-T B,   T upper n x n, s = +-1
-  void trsm_LUT(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m, double s) {
-    if (n == LEAF) { be.gemm('T', 'N', LEAF, m, LEAF, s, dinv_blk(b0), LEAF, B, ldb, 0.0, B, ldb, 0); return; }
+  // Strided batch (all trsm/trmm drivers): `bt` independent problems, member z uses T + z*sT, B + z*sB and the
+  // Dinv blocks shifted by z*sD doubles.
+  void trsm_LUT(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m, double s,
+                int64_t bt = 1, int64_t sT = 0, int64_t sB = 0, int64_t sD = 0) {
+    if (n == LEAF) { be.gemm('T', 'N', LEAF, m, LEAF, s, dinv_blk(b0), LEAF, B, ldb, 0.0, B, ldb, 0, bt, sD, sB, sB); return; }
     const int64_t n1 = split(n), n2 = n - n1;
     const double* Tb = T + n1 * ldt;
     const double* Tc = T + n1 + n1 * ldt;
-    trsm_LUT(T, ldt, n1, b0, B, ldb, m, s);
-    be.gemm('T', 'N', n2, m, n1, -s, Tb, ldt, B, ldb, 1.0, B + n1, ldb, 0);
-    trsm_LUT(Tc, ldt, n2, b0 + n1 / LEAF, B + n1, ldb, m, s);
+    trsm_LUT(T, ldt, n1, b0, B, ldb, m, s, bt, sT, sB, sD);
+    be.gemm('T', 'N', n2, m, n1, -s, Tb, ldt, B, ldb, 1.0, B + n1, ldb, 0, bt, sT, sB, sB);
+    trsm_LUT(Tc, ldt, n2, b0 + n1 / LEAF, B + n1, ldb, m, s, bt, sT, sB, sD);
   }
 
   // B (n x m) <- s * T^-1 B
-  void trsm_LUN(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m, double s) {
-    if (n == LEAF) { be.gemm('N', 'N', LEAF, m, LEAF, s, dinv_blk(b0), LEAF, B, ldb, 0.0, B, ldb, 0); return; }
+  void trsm_LUN(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m, double s,
+                int64_t bt = 1, int64_t sT = 0, int64_t sB = 0, int64_t sD = 0) {
+    if (n == LEAF) { be.gemm('N', 'N', LEAF, m, LEAF, s, dinv_blk(b0), LEAF, B, ldb, 0.0, B, ldb, 0, bt, sD, sB, sB); return; }
     const int64_t n1 = split(n), n2 = n - n1;
     const double* Tb = T + n1 * ldt;
     const double* Tc = T + n1 + n1 * ldt;
-    trsm_LUN(Tc, ldt, n2, b0 + n1 / LEAF, B + n1, ldb, m, s);
-    be.gemm('N', 'N', n1, m, n2, -s, Tb, ldt, B + n1, ldb, 1.0, B, ldb, 0);
-    trsm_LUN(T, ldt, n1, b0, B, ldb, m, s);
+    trsm_LUN(Tc, ldt, n2, b0 + n1 / LEAF, B + n1, ldb, m, s, bt, sT, sB, sD);
+    be.gemm('N', 'N', n1, m, n2, -s, Tb, ldt, B + n1, ldb, 1.0, B, ldb, 0, bt, sT, sB, sB);
+    trsm_LUN(T, ldt, n1, b0, B, ldb, m, s, bt, sT, sB, sD);
   }
 
   // B (m x n) <- s * B T^-1
-  void trsm_RUN(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m, double s) {
-    if (n == LEAF) { be.gemm('N', 'N', m, LEAF, LEAF, s, B, ldb, dinv_blk(b0), LEAF, 0.0, B, ldb, 0); return; }
+  void trsm_RUN(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m, double s,
+                int64_t bt = 1, int64_t sT = 0, int64_t sB = 0, int64_t sD = 0) {
+    if (n == LEAF) { be.gemm('N', 'N', m, LEAF, LEAF, s, B, ldb, dinv_blk(b0), LEAF, 0.0, B, ldb, 0, bt, sB, sD, sB); return; }
     const int64_t n1 = split(n), n2 = n - n1;
     const double* Tb = T + n1 * ldt;
     const double* Tc = T + n1 + n1 * ldt;
     double* B2 = B + n1 * ldb;
-    trsm_RUN(T, ldt, n1, b0, B, ldb, m, s);
-    be.gemm('N', 'N', m, n2, n1, -s, B, ldb, Tb, ldt, 1.0, B2, ldb, 0);
-    trsm_RUN(Tc, ldt, n2, b0 + n1 / LEAF, B2, ldb, m, s);
+    trsm_RUN(T, ldt, n1, b0, B, ldb, m, s, bt, sT, sB, sD);
+    be.gemm('N', 'N', m, n2, n1, -s, B, ldb, Tb, ldt, 1.0, B2, ldb, 0, bt, sB, sT, sB);
+    trsm_RUN(Tc, ldt, n2, b0 + n1 / LEAF, B2, ldb, m, s, bt, sT, sB, sD);
   }
 
   // B (m x n) <- B T^T,  T upper n x n whose diagonal 128-blocks are the Dinv blocks
   // (i.e. T is the already inverted factor W = U^-1).
   void trmm_RUT(const double* T, int64_t ldt, int64_t n, int64_t b0, double* B, int64_t ldb, int64_t m) {
-    if (n == LEAF) { be.gemm('N', 'T', m, LEAF, LEAF, 1.0, B, ldb, dinv_blk(b0), LEAF, 0.0, B, ldb, 0); return; }
+    if (n == LEAF) { be.gemm('N', 'T', m, LEAF, LEAF, 1.0, B, ldb, dinv_blk(b0), LEAF, 0.0, B, ldb, 0, 1, 0, 0, 0); return; }
     const int64_t n1 = split(n), n2 = n - n1;
     const double* Tb = T + n1 * ldt;
     const double* Tc = T + n1 + n1 * ldt;
     double* B2 = B + n1 * ldb;
     trmm_RUT(T, ldt, n1, b0, B, ldb, m);
-    be.gemm('N', 'T', m, n1, n2, 1.0, B2, ldb, Tb, ldt, 1.0, B, ldb, 0);
+    be.gemm('N', 'T', m, n1, n2, 1.0, B2, ldb, Tb, ldt, 1.0, B, ldb, 0, 1, 0, 0, 0);
     trmm_RUT(Tc, ldt, n2, b0 + n1 / LEAF, B2, ldb, m);
   }
 
   // W(upper) <- inv(U), in place.  Needs the Dinv blocks produced by potrf.
-  void trtri(double* W, int64_t ld, int64_t n, int64_t b0) {
-    if (n == LEAF) { be.copy_upper_128(W, ld, dinv_blk(b0)); return; }
+  // Level-synchronous: the two half-size inversions of a node are independent, so all nodes of one depth
+  // are processed as ONE strided batch (members `stride` doubles apart along the diagonal, Dinv blocks
+  // `dstride` apart).  Every launch then covers the whole matrix width regardless of depth.
+  // full_diag: write the diagonal 128-blocks of W with explicit zeros below the diagonal (needed by the
+  // out-of-place W W^T product; only legal when W is not the buffer whose strict lower triangle keeps K).
+  void trtri(double* W, int64_t ld, int64_t n, int64_t b0, bool full_diag = false) {
+    trtri_batched(W, ld, n, b0, 1, 0, 0, full_diag);
+  }
+  void trtri_batched(double* W, int64_t ld, int64_t n, int64_t b0, int64_t bt, int64_t stride, int64_t dstride,
+                     bool full_diag) {
+    if (n == LEAF) { be.copy_dinv_128(W, ld, dinv_blk(b0), bt, stride, dstride, full_diag); return; }
     const int64_t n1 = split(n), n2 = n - n1;
     double* W12 = W + n1 * ld;
     double* W22 = W + n1 + n1 * ld;
-    trsm_LUN(W, ld, n1, b0, W12, ld, n2, 1.0);                     // U11^-1 U12
-    trsm_RUN(W22, ld, n2, b0 + n1 / LEAF, W12, ld, n1, -1.0);      // -(.) U22^-1
-    trtri(W, ld, n1, b0);
-    trtri(W22, ld, n2, b0 + n1 / LEAF);
+    trsm_LUN(W, ld, n1, b0, W12, ld, n2, 1.0, bt, stride, stride, dstride);                    // U11^-1 U12
+    trsm_RUN(W22, ld, n2, b0 + n1 / LEAF, W12, ld, n1, -1.0, bt, stride, stride, dstride);     // -(.) U22^-1
+    if (n1 == n2 && (bt == 1 || stride == 2 * n1 * (ld + 1))) {
+      // children of all members are equally spaced: merge them into one batch of 2*bt
+      trtri_batched(W, ld, n1, b0, 2 * bt, n1 * (ld + 1), (n1 / LEAF) * (int64_t)(LEAF * LEAF), full_diag);
+    } else {
+      trtri_batched(W, ld, n1, b0, bt, stride, dstride, full_diag);
+      trtri_batched(W22, ld, n2, b0 + n1 / LEAF, bt, stride, dstride, full_diag);
+    }
+  }
+
+  // C(upper) <- W W^T out of place, W upper triangular with clean diagonal blocks (trtri(..., full_diag = true)):
+  // C_IJ = sum_{K >= J} W_IK W_JK^T, one fully parallel launch (no recursion, no small launches).
+  void lauum_oop(const double* W, int64_t ldw, int64_t n, double* C, int64_t ldc) {
+    be.gemm('N', 'T', n, n, n, 1.0, W, ldw, W, ldw, 0.0, C, ldc, BLK_UPPER_ONLY | BLK_K_FROM_N, 1, 0, 0, 0);
   }
 
   // W(upper) <- W W^T (upper part), in place, W = inv(U) as left by trtri.
   void lauum(double* W, int64_t ld, int64_t n, int64_t b0) {
     if (n == LEAF) {
-      be.gemm('N', 'T', LEAF, LEAF, LEAF, 1.0, dinv_blk(b0), LEAF, dinv_blk(b0), LEAF, 0.0, W, ld, BLK_UPPER_ONLY);
+      be.gemm('N', 'T', LEAF, LEAF, LEAF, 1.0, dinv_blk(b0), LEAF, dinv_blk(b0), LEAF, 0.0, W, ld, BLK_UPPER_ONLY, 1, 0, 0, 0);
       return;
     }
     const int64_t n1 = split(n), n2 = n - n1;
     double* W12 = W + n1 * ld;
     double* W22 = W + n1 + n1 * ld;
     lauum(W, ld, n1, b0);
-    be.gemm('N', 'T', n1, n1, n2, 1.0, W12, ld, W12, ld, 1.0, W, ld, BLK_UPPER_ONLY);
+    be.gemm('N', 'T', n1, n1, n2, 1.0, W12, ld, W12, ld, 1.0, W, ld, BLK_UPPER_ONLY, 1, 0, 0, 0);
     trmm_RUT(W22, ld, n2, b0 + n1 / LEAF, W12, ld, n1);
     lauum(W22, ld, n2, b0 + n1 / LEAF);
   }

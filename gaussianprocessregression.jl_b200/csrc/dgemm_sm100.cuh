@@ -42,6 +42,7 @@ constexpr int GEMM_LDM = 130;   // m-contiguous smem row stride (doubles)
 
 enum GemmFlags : int {
   GEMM_UPPER_ONLY = 1,   // C is a diagonal-anchored symmetric block: only tiles/elements with row <= col are computed/stored
+  GEMM_K_FROM_N = 2,     // tile column block J contracts over k >= 128*J only (triangular product W W^T, W upper)
 };
 
 struct GemmParams {
@@ -51,6 +52,7 @@ struct GemmParams {
   const double* B; long long ldb;
   double* C; long long ldc;
   int flags;
+  long long sA, sB, sC;   // strided batch (blockIdx.z)
 };
 
 template <bool KC> struct GemmTile {
@@ -117,8 +119,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
   const int wm = warp & 1, wn = warp >> 1;
 
   const long long m0 = (long long)tile_m * GEMM_BM, n0 = (long long)tile_n * GEMM_BN;
-  const double* Ap = A_KC ? (p.A + m0 * p.lda) : (p.A + m0);
-  const double* Bp = B_KC ? (p.B + n0 * p.ldb) : (p.B + n0);
+  const long long bz = blockIdx.z;
+  const double* Ap = p.A + bz * p.sA + (A_KC ? m0 * p.lda : m0);
+  const double* Bp = p.B + bz * p.sB + (B_KC ? n0 * p.ldb : n0);
+  const int kt0 = (p.flags & GEMM_K_FROM_N) ? tile_n * (GEMM_BN / GEMM_BK) : 0;   // first k-tile of this tile
 
   double acc[8][4][2];
 #pragma unroll
@@ -126,12 +130,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const int KT = p.K / GEMM_BK;
+  const int KT = p.K / GEMM_BK - kt0;
 
   // Pull the C tile towards L2 while the main loop runs (the epilogue reads it when beta != 0):
   // 128 columns x 1 KiB = 8 lines per column, 4 prefetches per thread.
   if (p.beta != 0.0) {
-    const double* cpre = p.C + m0 + (n0 + (tid >> 1)) * p.ldc + (tid & 1) * 64;
+    const double* cpre = p.C + bz * p.sC + m0 + (n0 + (tid >> 1)) * p.ldc + (tid & 1) * 64;
 #pragma unroll
     for (int q = 0; q < 4; ++q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(cpre + q * 16));
   }
@@ -140,8 +144,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
 #pragma unroll
   for (int s = 0; s < GEMM_STAGES - 1; ++s) {
     if (s < KT) {
-      gemm_load_tile<A_KC>(gemm_smem + s * (SA + SB), Ap, p.lda, s, tid);
-      gemm_load_tile<B_KC>(gemm_smem + s * (SA + SB) + SA, Bp, p.ldb, s, tid);
+      gemm_load_tile<A_KC>(gemm_smem + s * (SA + SB), Ap, p.lda, kt0 + s, tid);
+      gemm_load_tile<B_KC>(gemm_smem + s * (SA + SB) + SA, Bp, p.ldb, kt0 + s, tid);
     }
     cp_async_commit();
   }
@@ -153,8 +157,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
       int nk = kt + GEMM_STAGES - 1;
       if (nk < KT) {
         int s = nk % GEMM_STAGES;
-        gemm_load_tile<A_KC>(gemm_smem + s * (SA + SB), Ap, p.lda, nk, tid);
-        gemm_load_tile<B_KC>(gemm_smem + s * (SA + SB) + SA, Bp, p.ldb, nk, tid);
+        gemm_load_tile<A_KC>(gemm_smem + s * (SA + SB), Ap, p.lda, kt0 + nk, tid);
+        gemm_load_tile<B_KC>(gemm_smem + s * (SA + SB) + SA, Bp, p.ldb, kt0 + nk, tid);
       }
       cp_async_commit();
     }
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
   // hoisted by the compiler, which would serialise 64 DRAM round trips).
   const bool diag_tile = (p.flags & GEMM_UPPER_ONLY) && (tile_m == tile_n);
   const double alpha = p.alpha, beta = p.beta;
-  double* Cp = p.C + m0 + n0 * p.ldc;
+  double* Cp = p.C + bz * p.sC + m0 + n0 * p.ldc;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     double old[8][2];
@@ -278,20 +282,16 @@ template <bool A_KC, bool B_KC> constexpr size_t gemm_smem_bytes() {
 }
 
 // transA/transB: 'N' or 'T' (BLAS meaning, column major).  Supported: TN, NN, NT.
+// (the dynamic shared memory attribute of the three instantiations is set once per context: gpr_api.cu)
 inline cudaError_t launch_dgemm128(cudaStream_t st, char transA, char transB, int M, int N, int K, double alpha,
                                    const double* A, long long lda, const double* B, long long ldb, double beta,
-                                   double* C, long long ldc, int flags) {
-  if (M <= 0 || N <= 0) return cudaSuccess;
-  if ((M % GEMM_BM) || (N % GEMM_BN) || (K % GEMM_BK) || K <= 0) return cudaErrorInvalidValue;
-  GemmParams p{M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, flags};
-  dim3 grid(M / GEMM_BM, N / GEMM_BN), block(GEMM_THREADS);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(dgemm128_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<true, true>());
-    cudaFuncSetAttribute(dgemm128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<false, true>());
-    cudaFuncSetAttribute(dgemm128_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<false, false>());
-    attr_done = true;
-  }
+                                   double* C, long long ldc, int flags, int batch = 1, long long sA = 0,
+                                   long long sB = 0, long long sC = 0) {
+  if (M <= 0 || N <= 0 || batch <= 0) return cudaSuccess;
+  if ((M % GEMM_BM) || (N % GEMM_BN) || (K % GEMM_BK) || K <= 0 || batch > 65535) return cudaErrorInvalidValue;
+  if ((flags & GEMM_K_FROM_N) && K < N) return cudaErrorInvalidValue;
+  GemmParams p{M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, flags, sA, sB, sC};
+  dim3 grid(M / GEMM_BM, N / GEMM_BN, batch), block(GEMM_THREADS);
   const bool aT = (transA == 'T' || transA == 't'), bT = (transB == 'T' || transB == 't');
   if (aT && !bT)
     dgemm128_kernel<true, true><<<grid, block, gemm_smem_bytes<true, true>(), st>>>(p);

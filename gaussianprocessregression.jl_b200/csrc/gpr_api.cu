@@ -40,6 +40,7 @@ struct gpr_ctx {
   std::string err;
   int sm_count = 0;
   int64_t predict_tile = 8192;
+  int inplace_lauum = 0;   // option "inplace_lauum": force the recursive in-place W W^T (saves one N x N buffer)
   long long launches = 0;
   long long* d_info = nullptr;
   cudaError_t pending = cudaSuccess;   // first launch error seen by the backend
@@ -67,9 +68,15 @@ struct CudaBE {
   gpr_ctx* ctx;
   void note(cudaError_t e) { if (e != cudaSuccess && ctx->pending == cudaSuccess) ctx->pending = e; }
   void gemm(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
-            const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags) {
-    note(launch_dgemm128(ctx->stream, tA, tB, (int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, flags));
-    ctx->launches++;
+            const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int64_t batch = 1,
+            int64_t sA = 0, int64_t sB = 0, int64_t sC = 0) {
+    // grid.z is limited to 65535: split very large batches
+    for (int64_t z0 = 0; z0 < batch; z0 += 32768) {
+      const int64_t nb = std::min<int64_t>(32768, batch - z0);
+      note(launch_dgemm128(ctx->stream, tA, tB, (int)M, (int)N, (int)K, alpha, A + z0 * sA, lda, B + z0 * sB, ldb, beta,
+                           C + z0 * sC, ldc, flags, (int)nb, sA, sB, sC));
+      ctx->launches++;
+    }
   }
   void potrf_leaf(double* A, int64_t lda, double* dinv, int64_t goff) {
     potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, ctx->stream>>>(A, lda, dinv, ctx->d_info, goff);
@@ -87,8 +94,9 @@ struct CudaBE {
     note(cudaGetLastError());
     ctx->launches++;
   }
-  void copy_upper_128(double* dst, int64_t ldd, const double* src) {
-    copy_upper_128_kernel<<<1, 256, 0, ctx->stream>>>(dst, ldd, src);
+  void copy_dinv_128(double* dst, int64_t ldd, const double* src, int64_t batch, int64_t stride, int64_t dstride,
+                     bool full) {
+    copy_dinv_128_kernel<<<(unsigned)batch, 256, 0, ctx->stream>>>(dst, ldd, src, stride, dstride, full ? 1 : 0);
     note(cudaGetLastError());
     ctx->launches++;
   }
@@ -160,6 +168,7 @@ struct gpr_model {
   double* d_hp = nullptr;     // P
   double* d_U = nullptr;      // Np x Np: upper = U, strict lower = K
   double* d_Kinv = nullptr;   // Np x Np upper = K^-1 (may alias d_U when memory is short)
+  double* d_W = nullptr;      // Np x Np upper = U^-1 (out-of-place inverse path; optional)
   double* d_dinv = nullptr;   // Np/128 blocks of 128x128
   double* d_wt = nullptr;     // Np x nyp : K^-1 y (all columns), zero padded
   double* d_scal = nullptr;   // [logdet, y.alpha]
@@ -278,25 +287,42 @@ int factor_and_solve(gpr_model* m, const double* hp, double eps, int64_t* info) 
 int form_inverse(gpr_model* m) {
   gpr_ctx* ctx = m->ctx;
   const int64_t Np = m->Np;
+  // Buffers: preferred = two extra N x N (W = U^-1 and K^-1 = W W^T out of place, one fully parallel launch);
+  // one extra = in-place trtri + recursive lauum on it; none = invert in place over U (destroys the factor).
   if (!m->d_Kinv) {
     cudaError_t e = cudaMalloc(&m->d_Kinv, sizeof(double) * Np * Np);
-    if (e != cudaSuccess) {   // not enough memory for a second N x N: invert in place (destroys U)
+    if (e != cudaSuccess) {
       cudaGetLastError();
       m->d_Kinv = m->d_U;
       m->kinv_alias = true;
+    } else if (!ctx->inplace_lauum) {
+      e = cudaMalloc(&m->d_W, sizeof(double) * Np * Np);
+      if (e != cudaSuccess) { cudaGetLastError(); m->d_W = nullptr; }
     }
   }
   CudaBE be{ctx};
   Blocked<CudaBE> blk(be, m->d_dinv);
-  {
-    Scope s(m->tm, GPR_T_TRTRI, ctx->stream);
-    if (!m->kinv_alias) CK(cudaMemcpyAsync(m->d_Kinv, m->d_U, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, ctx->stream));
-    else m->factor_destroyed = true;
-    blk.trtri(m->d_Kinv, Np, Np, 0);
-  }
-  {
-    Scope s(m->tm, GPR_T_LAUUM, ctx->stream);
-    blk.lauum(m->d_Kinv, Np, Np, 0);
+  if (m->d_W) {
+    {
+      Scope s(m->tm, GPR_T_TRTRI, ctx->stream);
+      CK(cudaMemcpyAsync(m->d_W, m->d_U, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, ctx->stream));
+      blk.trtri(m->d_W, Np, Np, 0, true);
+    }
+    {
+      Scope s(m->tm, GPR_T_LAUUM, ctx->stream);
+      blk.lauum_oop(m->d_W, Np, Np, m->d_Kinv, Np);
+    }
+  } else {
+    {
+      Scope s(m->tm, GPR_T_TRTRI, ctx->stream);
+      if (!m->kinv_alias) CK(cudaMemcpyAsync(m->d_Kinv, m->d_U, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, ctx->stream));
+      else m->factor_destroyed = true;
+      blk.trtri(m->d_Kinv, Np, Np, 0, false);
+    }
+    {
+      Scope s(m->tm, GPR_T_LAUUM, ctx->stream);
+      blk.lauum(m->d_Kinv, Np, Np, 0);
+    }
   }
   m->have_inverse = true;
   m->kinv_symmetric = false;
@@ -389,6 +415,7 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
     ctx->predict_tile = round_up(value, 128);
     return GPR_OK;
   }
+  if (!strcmp(name, "inplace_lauum")) { ctx->inplace_lauum = value ? 1 : 0; return GPR_OK; }
   return fail(ctx, GPR_ERR_ARG, std::string("unknown option ") + name);
 }
 
@@ -450,6 +477,7 @@ int gpr_model_destroy(gpr_model* m) {
   cudaStreamSynchronize(m->ctx->stream);
   cudaFree(m->d_x); cudaFree(m->d_y); cudaFree(m->d_hp); cudaFree(m->d_U);
   if (m->d_Kinv && !m->kinv_alias) cudaFree(m->d_Kinv);
+  cudaFree(m->d_W);
   cudaFree(m->d_dinv); cudaFree(m->d_wt); cudaFree(m->d_scal); cudaFree(m->d_G); cudaFree(m->d_gpart);
   cudaFree(m->w_kxp.p); cudaFree(m->w_xp.p); cudaFree(m->w_part.p); cudaFree(m->w_mean.p); cudaFree(m->w_var.p);
   timer_free(m->tm);
@@ -1048,15 +1076,32 @@ int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, 
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     CudaBE be{ctx};
     Blocked<CudaBE> blk(be, dinv);
+    double *dW = nullptr, *dC = nullptr;
+    if (mode == 3) {
+      if (e == cudaSuccess) e = cudaMalloc(&dW, sizeof(double) * Np * Np);
+      if (e == cudaSuccess) e = cudaMalloc(&dC, sizeof(double) * Np * Np);
+    }
     cudaEventRecord(e0, ctx->stream);
     blk.potrf(dA, Np, Np, 0);
-    if (mode >= 1) blk.trtri(dA, Np, Np, 0);
-    if (mode >= 2) blk.lauum(dA, Np, Np, 0);
+    if (mode == 3 && e == cudaSuccess) {   // out-of-place inverse: W = U^-1 with clean diagonal blocks, C = W W^T, upper(C) -> upper(A)
+      e = cudaMemcpyAsync(dW, dA, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, ctx->stream);
+      blk.trtri(dW, Np, Np, 0, true);
+      blk.lauum_oop(dW, Np, Np, dC, Np);
+    } else {
+      if (mode >= 1) blk.trtri(dA, Np, Np, 0);
+      if (mode >= 2) blk.lauum(dA, Np, Np, 0);
+    }
     cudaEventRecord(e1, ctx->stream);
+    if (mode == 3 && e == cudaSuccess) {
+      dim3 grid((unsigned)((Np + 31) / 32), (unsigned)((Np + 31) / 32)), block(32, 8);
+      copy_upper_kernel<<<grid, block, 0, ctx->stream>>>(dA, Np, dC, Np, Np);
+      ctx->launches++;
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h_info, ctx->d_info, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaEventElapsedTime(&t, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dW); cudaFree(dC);
     rc = check_pending(ctx, "gpr_dbg_factor");
     if (e == cudaSuccess && !rc) {
       e = cudaMemcpy2DAsync(A, sizeof(double) * N, dA, sizeof(double) * Np, sizeof(double) * N, N, cudaMemcpyDeviceToHost, ctx->stream);

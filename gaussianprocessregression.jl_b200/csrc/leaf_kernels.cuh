@@ -353,11 +353,26 @@ __global__ void __launch_bounds__(256, 1) leaf_mv_kernel(const double* __restric
 }
 constexpr size_t LEAF_MV_SMEM_BYTES = (size_t)(LEAF_N * LEAF_LDS + LEAF_N + 256) * sizeof(double);
 
-// dst (128x128 block of a column-major matrix, ldd): upper part <- src (ld 128)
-__global__ void copy_upper_128_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src) {
+// dst (128x128 block of a column-major matrix, ldd; batch member blockIdx.x at dst + z*stride) <- Dinv block
+// (src + z*dstride, ld 128): the upper part only, or (full) the whole block with the zeros below the diagonal.
+__global__ void copy_dinv_128_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src,
+                                     long long stride, long long dstride, int full) {
+  dst += (long long)blockIdx.x * stride;
+  src += (long long)blockIdx.x * dstride;
   for (int idx = threadIdx.x; idx < LEAF_N * LEAF_N; idx += blockDim.x) {
     const int r = idx & (LEAF_N - 1), c = idx >> 7;
-    if (r <= c) dst[r + (long long)c * ldd] = src[idx];
+    if (full || r <= c) dst[r + (long long)c * ldd] = src[idx];
+  }
+}
+
+// dst(upper) <- src(upper), n x n column major (32 x 8 threads per 32 x 32 tile)
+__global__ void copy_upper_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src, long long lds,
+                                  long long n) {
+  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+  if (blockIdx.x > blockIdx.y) return;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const long long j = (long long)blockIdx.y * 32 + r;
+    if (i < n && j < n && i <= j) dst[i + j * ldd] = src[i + j * lds];
   }
 }
 

@@ -87,7 +87,7 @@ int gpr_version(void);
 int gpr_ctx_create(int device, gpr_ctx** ctx);
 int gpr_ctx_destroy(gpr_ctx* ctx);
 const char* gpr_last_error(gpr_ctx* ctx);          /* ctx may be NULL: last error of a failed gpr_ctx_create */
-int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value);   /* "predict_tile" (test points per tile) */
+int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value);   /* "predict_tile" (test points per tile), "inplace_lauum" (0/1) */
 int64_t gpr_ctx_launch_count(gpr_ctx* ctx);        /* kernels launched by this context so far */
 
 /* dim_hp(K, dim): src/covariance.jl:27,60; src/compose_covar.jl:26-28 */
@@ -154,7 +154,8 @@ int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, d
                   int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int reps,
                   double* ms);
 /* factor (and optionally invert) a host SPD matrix in place through the blocked path; A is N x N.
- * mode 0: potrf (upper = U), 1: potrf + trtri (upper = U^-1), 2: potrf + trtri + lauum (upper = A^-1). */
+ * mode 0: potrf (upper = U), 1: potrf + trtri (upper = U^-1), 2: potrf + trtri + in-place lauum (upper = A^-1),
+ * 3: potrf + trtri + out-of-place W W^T (upper = A^-1; the path gpr_update_cache takes when memory allows). */
 int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, double* ms);
 
 #ifdef __cplusplus

@@ -15,28 +15,35 @@ namespace {
 struct CpuBE {
   long long info = 0;
   long long gemm_calls = 0;
-  void gemm(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
-            const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags) {
+  void gemm(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A0, int64_t lda,
+            const double* B0, int64_t ldb, double beta, double* C0, int64_t ldc, int flags, int64_t batch = 1,
+            int64_t sA = 0, int64_t sB = 0, int64_t sC = 0) {
     gemm_calls++;
-    // like the GPU kernel: a tile reads all of its operands before it stores, so C may alias A or B
-    std::vector<double> tmp((size_t)M * N);
-    for (int64_t n = 0; n < N; ++n)
-      for (int64_t m = 0; m < M; ++m) {
-        double s = 0.0;
-        for (int64_t k = 0; k < K; ++k) {
-          const double a = (tA == 'T') ? A[k + m * lda] : A[m + k * lda];
-          const double b = (tB == 'T') ? B[n + k * ldb] : B[k + n * ldb];
-          s += a * b;
+    for (int64_t z = 0; z < batch; ++z) {
+      const double* A = A0 + z * sA;
+      const double* B = B0 + z * sB;
+      double* C = C0 + z * sC;
+      // like the GPU kernel: a tile reads all of its operands before it stores, so C may alias A or B
+      std::vector<double> tmp((size_t)M * N);
+      for (int64_t n = 0; n < N; ++n)
+        for (int64_t m = 0; m < M; ++m) {
+          double s = 0.0;
+          const int64_t kbeg = (flags & gpr::BLK_K_FROM_N) ? (n / gpr::LEAF) * gpr::LEAF : 0;
+          for (int64_t k = kbeg; k < K; ++k) {
+            const double a = (tA == 'T') ? A[k + m * lda] : A[m + k * lda];
+            const double b = (tB == 'T') ? B[n + k * ldb] : B[k + n * ldb];
+            s += a * b;
+          }
+          tmp[m + n * M] = s;
         }
-        tmp[m + n * M] = s;
-      }
-    for (int64_t n = 0; n < N; ++n)
-      for (int64_t m = 0; m < M; ++m) {
-        if ((flags & gpr::BLK_UPPER_ONLY) && m > n) continue;
-        double r = alpha * tmp[m + n * M];
-        if (beta != 0.0) r += beta * C[m + n * ldc];
-        C[m + n * ldc] = r;
-      }
+      for (int64_t n = 0; n < N; ++n)
+        for (int64_t m = 0; m < M; ++m) {
+          if ((flags & gpr::BLK_UPPER_ONLY) && (m / gpr::LEAF > n / gpr::LEAF || (m / gpr::LEAF == n / gpr::LEAF && m > n))) continue;
+          double r = alpha * tmp[m + n * M];
+          if (beta != 0.0) r += beta * C[m + n * ldc];
+          C[m + n * ldc] = r;
+        }
+    }
   }
   void potrf_leaf(double* A, int64_t lda, double* dinv, int64_t goff) {
     const int n = gpr::LEAF;
@@ -75,9 +82,12 @@ struct CpuBE {
     }
     for (int m = 0; m < n; ++m) v[m] = tmp[m];
   }
-  void copy_upper_128(double* dst, int64_t ldd, const double* src) {
-    for (int c = 0; c < gpr::LEAF; ++c)
-      for (int r = 0; r <= c; ++r) dst[r + c * ldd] = src[r + c * gpr::LEAF];
+  void copy_dinv_128(double* dst, int64_t ldd, const double* src, int64_t batch, int64_t stride, int64_t dstride,
+                     bool full) {
+    for (int64_t z = 0; z < batch; ++z)
+      for (int c = 0; c < gpr::LEAF; ++c)
+        for (int r = 0; r < gpr::LEAF; ++r)
+          if (full || r <= c) dst[z * stride + r + c * ldd] = src[z * dstride + r + c * gpr::LEAF];
   }
 };
 
@@ -91,8 +101,17 @@ long long hl_factor(double* A, int64_t n, int mode, long long* gemm_calls) {
   std::vector<double> dinv((size_t)n * 128);
   gpr::Blocked<CpuBE> blk(be, dinv.data());
   blk.potrf(A, n, n, 0);
-  if (mode >= 1) blk.trtri(A, n, n, 0);
-  if (mode >= 2) blk.lauum(A, n, n, 0);
+  if (mode == 3) {   // out-of-place inverse: W = copy of U with clean diagonal blocks, C = W W^T written back to A (upper)
+    std::vector<double> W((size_t)n * n), C((size_t)n * n, 0.0);
+    memcpy(W.data(), A, sizeof(double) * n * n);
+    blk.trtri(W.data(), n, n, 0, true);
+    blk.lauum_oop(W.data(), n, n, C.data(), n);
+    for (int64_t j = 0; j < n; ++j)
+      for (int64_t i = 0; i <= j; ++i) A[i + j * n] = C[i + j * n];
+  } else {
+    if (mode >= 1) blk.trtri(A, n, n, 0);
+    if (mode >= 2) blk.lauum(A, n, n, 0);
+  }
   if (gemm_calls) *gemm_calls = be.gemm_calls;
   return be.info;
 }

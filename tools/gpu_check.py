@@ -129,8 +129,8 @@ def sec_factor():
         X = rng.standard_normal((n, n))
         K = X @ X.T / n + np.eye(n)
         U = sl.cholesky(K, lower=False)
-        refs = [U, np.linalg.inv(U), np.linalg.inv(K)]
-        for mode in (0, 1, 2):
+        refs = [U, np.linalg.inv(U), np.linalg.inv(K), np.linalg.inv(K)]
+        for mode in (0, 1, 2, 3):
             A, ms = _ffi.dbg_factor(ctx, K, mode)
             e = relerr(np.triu(A), np.triu(refs[mode]))
             low = float(np.abs(np.tril(A, -1) - np.tril(K, -1)).max())
@@ -152,7 +152,7 @@ def sec_factor_perf():
     for n in (4096, 8192, 16384):
         X = rng.standard_normal((n, 64))
         K = X @ X.T / 64 + np.eye(n)
-        for mode in (0, 2):
+        for mode in (0, 2, 3):
             c0 = ctx.launch_count()
             A, ms = _ffi.dbg_factor(ctx, K, mode)
             fl = n ** 3 / 3 if mode == 0 else n ** 3
