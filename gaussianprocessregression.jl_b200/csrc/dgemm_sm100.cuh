@@ -17,12 +17,15 @@
 //   B_KC = true  : op(B)[k,n] = B[k + n*ldb]   (transB = 'N', k contiguous)
 //   B_KC = false : op(B)[k,n] = B[n + k*ldb]   (transB = 'T', n contiguous)
 //
-// CTA tile 128x128x16, 256 threads = 8 warps laid out 2 (m) x 4 (n), warp tile
-// 64x32 = 8x4 DMMA 8x8 accumulator tiles (64 doubles / thread).  Operands are
-// staged global->shared with cp.async (16 B, LDGSTS) through a 4-deep ring and
-// read back as conflict-free LDS.128 fragments:
-//   k-contiguous tile : smem[row][24]  (row stride 24 doubles)
-//   m-contiguous tile : smem[k][130]   (row stride 130 doubles)
+// Three tile configurations (template MI = 8x8 accumulator tiles per warp along m, WN = warps along n):
+//   MI = 8, WN = 4 : CTA tile 128x128x16,  8 warps (2 x 4) of 64x32, 4-stage ring, 1 CTA / SM
+//   MI = 8, WN = 2 : CTA tile 128x64x16,   4 warps (2 x 2) of 64x32, 3-stage ring, 2 CTAs / SM
+//   MI = 4, WN = 4 : CTA tile 128x128x16, 16 warps (4 x 4) of 32x32, 4-stage ring, 1 CTA / SM (4 warps per
+//                    scheduler hide barrier / LDS / cp.async waits of each other)
+// Operands are staged global->shared with cp.async (16 B, LDGSTS) and read back as conflict-free LDS.128
+// fragments:
+//   k-contiguous tile : smem[row][24]      (row stride 24 doubles)
+//   m-contiguous tile : smem[k][rows + 2]  (row stride 130 / 66 doubles)
 // Inside a k-block of 8 the lane with threadID_in_group t owns k = 2t (first
 // DMMA) and k = 2t+1 (second DMMA) so one LDS.128 feeds two DMMAs; A and B use
 // the same assignment so the contraction is consistent.
@@ -33,16 +36,22 @@
 namespace gpr {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_BN = 128;
+constexpr int GEMM_BN = 128;    // granularity required of N by the callers (both tile configurations divide it)
 constexpr int GEMM_BK = 16;
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_LDK = 24;    // k-contiguous smem row stride (doubles)
-constexpr int GEMM_LDM = 130;   // m-contiguous smem row stride (doubles)
+
+template <int MI, int WN> struct GemmCfg {
+  static constexpr int WARPS_M = 16 / MI;             // 128 rows / (8*MI rows per warp)
+  static constexpr int BN = 32 * WN;
+  static constexpr int THREADS = 32 * WARPS_M * WN;
+  static constexpr int STAGES = (WN == 4) ? 4 : 3;
+  static constexpr int MIN_CTAS = (WN == 4) ? 1 : 2;
+};
 
 enum GemmFlags : int {
   GEMM_UPPER_ONLY = 1,   // C is a diagonal-anchored symmetric block: only tiles/elements with row <= col are computed/stored
   GEMM_K_FROM_N = 2,     // tile column block J contracts over k >= 128*J only (triangular product W W^T, W upper)
+  GEMM_C_ALIASES_A = 4,  // C overwrites the A operand in place (needs the full-width 128x128 tile)
 };
 
 struct GemmParams {
@@ -55,8 +64,10 @@ struct GemmParams {
   long long sA, sB, sC;   // strided batch (blockIdx.z)
 };
 
-template <bool KC> struct GemmTile {
-  static constexpr int ELEMS = KC ? (128 * GEMM_LDK) : (GEMM_BK * GEMM_LDM);
+// smem layout of one operand tile with ROWS rows (m or n extent) and 16 k
+template <bool KC, int ROWS> struct GemmTile {
+  static constexpr int LD = KC ? GEMM_LDK : (ROWS + 2);
+  static constexpr int ELEMS = KC ? (ROWS * GEMM_LDK) : (GEMM_BK * (ROWS + 2));
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -74,21 +85,21 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
       : "d"(a), "d"(b));
 }
 
-// Stage one 128 x 16 operand tile (kt-th k-tile) into shared memory.
+// Stage one ROWS x 16 operand tile (kt-th k-tile) into shared memory.
 //   KC : element (r,k) at P[k + r*ld]   -> smem[r*LDK + k]
-//   !KC: element (r,k) at P[r + k*ld]   -> smem[k*LDM + r]
-template <bool KC>
-__device__ __forceinline__ void gemm_load_tile(double* smem, const double* __restrict__ P, long long ld,
-                                               int kt, int tid) {
+//   !KC: element (r,k) at P[r + k*ld]   -> smem[k*(ROWS+2) + r]
+template <bool KC, int ROWS, int THREADS>
+__device__ __forceinline__ void gemm_load_tile(double* smem, const double* __restrict__ P, long long ld, int kt, int tid) {
+  constexpr int PER_THREAD = ROWS * 8 / THREADS;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    int c = tid + GEMM_THREADS * q;
+  for (int q = 0; q < PER_THREAD; ++q) {
+    const int c = tid + THREADS * q;
     if (KC) {
-      int r = c >> 3, kc = c & 7;
+      const int r = c >> 3, kc = c & 7;
       cp_async16(smem + r * GEMM_LDK + 2 * kc, P + (long long)kt * GEMM_BK + 2 * kc + (long long)r * ld);
     } else {
-      int k = c >> 6, rc = c & 63;
-      cp_async16(smem + k * GEMM_LDM + 2 * rc, P + 2 * rc + ((long long)kt * GEMM_BK + k) * ld);
+      const int k = c / (ROWS / 2), rc = c % (ROWS / 2);
+      cp_async16(smem + k * (ROWS + 2) + 2 * rc, P + 2 * rc + ((long long)kt * GEMM_BK + k) * ld);
     }
   }
 }
@@ -97,96 +108,107 @@ __device__ __forceinline__ void gemm_load_tile(double* smem, const double* __res
 // and tile-local column of accumulator sub-tile j (0..3) for in-tile column q
 // (B operand).  The maps differ per storage form so that fragment loads are
 // LDS.128 and bank-conflict free.
-template <bool KC> __device__ __forceinline__ int gemm_row_of(int wm, int i, int g) {
-  return KC ? (64 * wm + 8 * i + g) : (64 * wm + 16 * (i >> 1) + 2 * g + (i & 1));
+template <bool KC, int MI> __device__ __forceinline__ int gemm_row_of(int wm, int i, int g) {
+  return KC ? (8 * MI * wm + 8 * i + g) : (8 * MI * wm + 16 * (i >> 1) + 2 * g + (i & 1));
 }
 template <bool KC> __device__ __forceinline__ int gemm_col_of(int wn, int j, int q) {
   return KC ? (32 * wn + 8 * j + q) : (32 * wn + 16 * (j >> 1) + 2 * q + (j & 1));
 }
 
-template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmParams p) {
+template <bool A_KC, bool B_KC, int MI, int WN>
+__global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN_CTAS) dgemm128_kernel(const GemmParams p) {
   extern __shared__ __align__(16) double gemm_smem[];
-  constexpr int SA = GemmTile<A_KC>::ELEMS;
-  constexpr int SB = GemmTile<B_KC>::ELEMS;
+  using Cfg = GemmCfg<MI, WN>;
+  constexpr int BN = Cfg::BN;
+  constexpr int THREADS = Cfg::THREADS;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int WROWS = 8 * MI;      // rows per warp
+  constexpr int SA = GemmTile<A_KC, GEMM_BM>::ELEMS;
+  constexpr int SB = GemmTile<B_KC, BN>::ELEMS;
+  constexpr int LDA_S = GemmTile<A_KC, GEMM_BM>::LD;
+  constexpr int LDB_S = GemmTile<B_KC, BN>::LD;
 
   const int tile_m = blockIdx.x, tile_n = blockIdx.y;
-  if ((p.flags & GEMM_UPPER_ONLY) && tile_m > tile_n) return;
+  const int blk_n = (tile_n * BN) >> 7;   // 128-block column of this tile (tile_m is already a 128-block row)
+  if ((p.flags & GEMM_UPPER_ONLY) && tile_m > blk_n) return;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp & 1, wn = warp >> 1;
+  const int wm = warp % Cfg::WARPS_M, wn = warp / Cfg::WARPS_M;
 
-  const long long m0 = (long long)tile_m * GEMM_BM, n0 = (long long)tile_n * GEMM_BN;
+  const long long m0 = (long long)tile_m * GEMM_BM, n0 = (long long)tile_n * BN;
   const long long bz = blockIdx.z;
   const double* Ap = p.A + bz * p.sA + (A_KC ? m0 * p.lda : m0);
   const double* Bp = p.B + bz * p.sB + (B_KC ? n0 * p.ldb : n0);
-  const int kt0 = (p.flags & GEMM_K_FROM_N) ? tile_n * (GEMM_BN / GEMM_BK) : 0;   // first k-tile of this tile
+  const int kt0 = (p.flags & GEMM_K_FROM_N) ? blk_n * (128 / GEMM_BK) : 0;   // first k-tile of this tile
 
-  double acc[8][4][2];
+  double acc[MI][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int KT = p.K / GEMM_BK - kt0;
 
   // Pull the C tile towards L2 while the main loop runs (the epilogue reads it when beta != 0):
-  // 128 columns x 1 KiB = 8 lines per column, 4 prefetches per thread.
+  // BN columns x 1 KiB = 8 lines of 128 B per column.
   if (p.beta != 0.0) {
-    const double* cpre = p.C + bz * p.sC + m0 + (n0 + (tid >> 1)) * p.ldc + (tid & 1) * 64;
+    const double* cbase = p.C + bz * p.sC + m0 + n0 * p.ldc;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(cpre + q * 16));
+    for (int q = 0; q < BN * 8 / THREADS; ++q) {
+      const int L = tid + THREADS * q;
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(cbase + (long long)(L >> 3) * p.ldc + (L & 7) * 16));
+    }
   }
 
   // prologue
 #pragma unroll
-  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+  for (int s = 0; s < STAGES - 1; ++s) {
     if (s < KT) {
-      gemm_load_tile<A_KC>(gemm_smem + s * (SA + SB), Ap, p.lda, kt0 + s, tid);
-      gemm_load_tile<B_KC>(gemm_smem + s * (SA + SB) + SA, Bp, p.ldb, kt0 + s, tid);
+      gemm_load_tile<A_KC, GEMM_BM, THREADS>(gemm_smem + s * (SA + SB), Ap, p.lda, kt0 + s, tid);
+      gemm_load_tile<B_KC, BN, THREADS>(gemm_smem + s * (SA + SB) + SA, Bp, p.ldb, kt0 + s, tid);
     }
     cp_async_commit();
   }
 
   for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<GEMM_STAGES - 2>();
+    cp_async_wait<STAGES - 2>();
     __syncthreads();
     {
-      int nk = kt + GEMM_STAGES - 1;
+      int nk = kt + STAGES - 1;
       if (nk < KT) {
-        int s = nk % GEMM_STAGES;
-        gemm_load_tile<A_KC>(gemm_smem + s * (SA + SB), Ap, p.lda, kt0 + nk, tid);
-        gemm_load_tile<B_KC>(gemm_smem + s * (SA + SB) + SA, Bp, p.ldb, kt0 + nk, tid);
+        int s = nk % STAGES;
+        gemm_load_tile<A_KC, GEMM_BM, THREADS>(gemm_smem + s * (SA + SB), Ap, p.lda, kt0 + nk, tid);
+        gemm_load_tile<B_KC, BN, THREADS>(gemm_smem + s * (SA + SB) + SA, Bp, p.ldb, kt0 + nk, tid);
       }
       cp_async_commit();
     }
-    const double* As = gemm_smem + (kt % GEMM_STAGES) * (SA + SB);
+    const double* As = gemm_smem + (kt % STAGES) * (SA + SB);
     const double* Bs = As + SA;
 
 #pragma unroll
     for (int sp = 0; sp < 2; ++sp) {   // two k-blocks of 8 per 16-wide tile
-      double a[8][2], b[4][2];
+      double a[MI][2], b[4][2];
       if (A_KC) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const double2 v = *reinterpret_cast<const double2*>(As + (64 * wm + 8 * i + g) * GEMM_LDK + 8 * sp + 2 * t);
+        for (int i = 0; i < MI; ++i) {
+          const double2 v = *reinterpret_cast<const double2*>(As + (WROWS * wm + 8 * i + g) * LDA_S + 8 * sp + 2 * t);
           a[i][0] = v.x; a[i][1] = v.y;
         }
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int pi = 0; pi < 4; ++pi) {
-            const double2 v = *reinterpret_cast<const double2*>(As + (8 * sp + 2 * t + h) * GEMM_LDM + 64 * wm + 16 * pi + 2 * g);
+          for (int pi = 0; pi < MI / 2; ++pi) {
+            const double2 v = *reinterpret_cast<const double2*>(As + (8 * sp + 2 * t + h) * LDA_S + WROWS * wm + 16 * pi + 2 * g);
             a[2 * pi][h] = v.x; a[2 * pi + 1][h] = v.y;
           }
       }
       if (B_KC) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const double2 v = *reinterpret_cast<const double2*>(Bs + (32 * wn + 8 * j + g) * GEMM_LDK + 8 * sp + 2 * t);
+          const double2 v = *reinterpret_cast<const double2*>(Bs + (32 * wn + 8 * j + g) * LDB_S + 8 * sp + 2 * t);
           b[j][0] = v.x; b[j][1] = v.y;
         }
       } else {
@@ -194,14 +216,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
         for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int pj = 0; pj < 2; ++pj) {
-            const double2 v = *reinterpret_cast<const double2*>(Bs + (8 * sp + 2 * t + h) * GEMM_LDM + 32 * wn + 16 * pj + 2 * g);
+            const double2 v = *reinterpret_cast<const double2*>(Bs + (8 * sp + 2 * t + h) * LDB_S + 32 * wn + 16 * pj + 2 * g);
             b[2 * pj][h] = v.x; b[2 * pj + 1][h] = v.y;
           }
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i][h], b[j][h]);
     }
@@ -213,12 +235,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
   // values are fetched in batches of 16 independent loads BEFORE any store of
   // the batch is issued (a load-after-store to the same array cannot be
   // hoisted by the compiler, which would serialise 64 DRAM round trips).
-  const bool diag_tile = (p.flags & GEMM_UPPER_ONLY) && (tile_m == tile_n);
+  // On the diagonal 128-block of an UPPER_ONLY product only row <= col (inside the block) is touched.
+  const bool diag_tile = (p.flags & GEMM_UPPER_ONLY) && (tile_m == blk_n);
+  const int coff = (int)(n0 & 127);   // column offset of this tile inside its 128-block (0 or 64)
   const double alpha = p.alpha, beta = p.beta;
   double* Cp = p.C + bz * p.sC + m0 + n0 * p.ldc;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    double old[8][2];
+    double old[MI][2];
     if (beta != 0.0) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
@@ -226,27 +250,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
         const double* Ccol = Cp + (long long)col * p.ldc;
         if (A_KC) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = gemm_row_of<true>(wm, i, g);
-            old[i][v] = (diag_tile && row > col) ? 0.0 : Ccol[row];
+          for (int i = 0; i < MI; ++i) {
+            const int row = gemm_row_of<true, MI>(wm, i, g);
+            old[i][v] = (diag_tile && row > col + coff) ? 0.0 : Ccol[row];
           }
         } else {
 #pragma unroll
-          for (int pi = 0; pi < 4; ++pi) {
-            const int row = gemm_row_of<false>(wm, 2 * pi, g);
+          for (int pi = 0; pi < MI / 2; ++pi) {
+            const int row = gemm_row_of<false, MI>(wm, 2 * pi, g);
             if (!diag_tile) {
               const double2 o = *reinterpret_cast<const double2*>(Ccol + row);
               old[2 * pi][v] = o.x; old[2 * pi + 1][v] = o.y;
             } else {
-              old[2 * pi][v] = (row <= col) ? Ccol[row] : 0.0;
-              old[2 * pi + 1][v] = (row + 1 <= col) ? Ccol[row + 1] : 0.0;
+              old[2 * pi][v] = (row <= col + coff) ? Ccol[row] : 0.0;
+              old[2 * pi + 1][v] = (row + 1 <= col + coff) ? Ccol[row + 1] : 0.0;
             }
           }
         }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) old[i][0] = old[i][1] = 0.0;
+      for (int i = 0; i < MI; ++i) old[i][0] = old[i][1] = 0.0;
     }
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
@@ -254,22 +278,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
       double* Ccol = Cp + (long long)col * p.ldc;
       if (A_KC) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = gemm_row_of<true>(wm, i, g);
-          if (diag_tile && row > col) continue;
+        for (int i = 0; i < MI; ++i) {
+          const int row = gemm_row_of<true, MI>(wm, i, g);
+          if (diag_tile && row > col + coff) continue;
           Ccol[row] = alpha * acc[i][j][v] + beta * old[i][v];
         }
       } else {
 #pragma unroll
-        for (int pi = 0; pi < 4; ++pi) {
-          const int row = gemm_row_of<false>(wm, 2 * pi, g);   // even row; row+1 is sub-tile 2*pi+1
+        for (int pi = 0; pi < MI / 2; ++pi) {
+          const int row = gemm_row_of<false, MI>(wm, 2 * pi, g);   // even row; row+1 is sub-tile 2*pi+1
           const double r0 = alpha * acc[2 * pi][j][v] + beta * old[2 * pi][v];
           const double r1 = alpha * acc[2 * pi + 1][j][v] + beta * old[2 * pi + 1][v];
           if (!diag_tile) {
             *reinterpret_cast<double2*>(Ccol + row) = make_double2(r0, r1);
           } else {
-            if (row <= col) Ccol[row] = r0;
-            if (row + 1 <= col) Ccol[row + 1] = r1;
+            if (row <= col + coff) Ccol[row] = r0;
+            if (row + 1 <= col + coff) Ccol[row + 1] = r1;
           }
         }
       }
@@ -277,12 +301,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm128_kernel(const GemmPar
   }
 }
 
-template <bool A_KC, bool B_KC> constexpr size_t gemm_smem_bytes() {
-  return (size_t)GEMM_STAGES * (GemmTile<A_KC>::ELEMS + GemmTile<B_KC>::ELEMS) * sizeof(double);
+template <bool A_KC, bool B_KC, int MI, int WN> constexpr size_t gemm_smem_bytes() {
+  return (size_t)GemmCfg<MI, WN>::STAGES *
+         (GemmTile<A_KC, GEMM_BM>::ELEMS + GemmTile<B_KC, GemmCfg<MI, WN>::BN>::ELEMS) * sizeof(double);
 }
 
+template <bool A_KC, bool B_KC, int MI, int WN> inline cudaError_t gemm_set_attr() {
+  return cudaFuncSetAttribute(dgemm128_kernel<A_KC, B_KC, MI, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)gemm_smem_bytes<A_KC, B_KC, MI, WN>());
+}
+template <int MI, int WN> inline cudaError_t gemm_set_attr_cfg() {
+  cudaError_t e = gemm_set_attr<true, true, MI, WN>();
+  if (e == cudaSuccess) e = gemm_set_attr<false, true, MI, WN>();
+  if (e == cudaSuccess) e = gemm_set_attr<false, false, MI, WN>();
+  return e;
+}
+// once per context / device
+inline cudaError_t gemm_setup_attributes() {
+  cudaError_t e = gemm_set_attr_cfg<8, 4>();
+  if (e == cudaSuccess) e = gemm_set_attr_cfg<8, 2>();
+  if (e == cudaSuccess) e = gemm_set_attr_cfg<4, 4>();
+  return e;
+}
+
+template <bool A_KC, bool B_KC, int MI, int WN>
+inline cudaError_t gemm_launch_cfg(cudaStream_t st, const GemmParams& p, int batch) {
+  dim3 grid(p.M / GEMM_BM, p.N / GemmCfg<MI, WN>::BN, batch), block(GemmCfg<MI, WN>::THREADS);
+  dgemm128_kernel<A_KC, B_KC, MI, WN><<<grid, block, gemm_smem_bytes<A_KC, B_KC, MI, WN>(), st>>>(p);
+  return cudaGetLastError();
+}
+template <int MI, int WN>
+inline cudaError_t gemm_launch_form(cudaStream_t st, const GemmParams& p, int batch, bool aT, bool bT) {
+  if (aT) return gemm_launch_cfg<true, true, MI, WN>(st, p, batch);
+  if (!bT) return gemm_launch_cfg<false, true, MI, WN>(st, p, batch);
+  return gemm_launch_cfg<false, false, MI, WN>(st, p, batch);
+}
+
+// Tile configuration: 0 = automatic, 1 = 128x128 / 8 warps, 2 = 128x64 / 4 warps x 2 CTAs, 3 = 128x128 / 16 warps
+// (option "gemm_cfg": tuning and tests).
+inline int& gemm_forced_cfg() { static int v = 0; return v; }
+
 // transA/transB: 'N' or 'T' (BLAS meaning, column major).  Supported: TN, NN, NT.
-// (the dynamic shared memory attribute of the three instantiations is set once per context: gpr_api.cu)
 inline cudaError_t launch_dgemm128(cudaStream_t st, char transA, char transB, int M, int N, int K, double alpha,
                                    const double* A, long long lda, const double* B, long long ldb, double beta,
                                    double* C, long long ldc, int flags, int batch = 1, long long sA = 0,
@@ -291,17 +350,16 @@ inline cudaError_t launch_dgemm128(cudaStream_t st, char transA, char transB, in
   if ((M % GEMM_BM) || (N % GEMM_BN) || (K % GEMM_BK) || K <= 0 || batch > 65535) return cudaErrorInvalidValue;
   if ((flags & GEMM_K_FROM_N) && K < N) return cudaErrorInvalidValue;
   GemmParams p{M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, flags, sA, sB, sC};
-  dim3 grid(M / GEMM_BM, N / GEMM_BN, batch), block(GEMM_THREADS);
   const bool aT = (transA == 'T' || transA == 't'), bT = (transB == 'T' || transB == 't');
-  if (aT && !bT)
-    dgemm128_kernel<true, true><<<grid, block, gemm_smem_bytes<true, true>(), st>>>(p);
-  else if (!aT && !bT)
-    dgemm128_kernel<false, true><<<grid, block, gemm_smem_bytes<false, true>(), st>>>(p);
-  else if (!aT && bT)
-    dgemm128_kernel<false, false><<<grid, block, gemm_smem_bytes<false, false>(), st>>>(p);
-  else
-    return cudaErrorNotSupported;
-  return cudaGetLastError();
+  if (aT && bT) return cudaErrorNotSupported;
+  // C written over the A operand: a CTA must own every k column it reads -> full-width 128x128 tile.
+  const bool alias_a = (flags & GEMM_C_ALIASES_A) || (const double*)C == A;
+  int cfg = gemm_forced_cfg();
+  if (cfg < 1 || cfg > 3) cfg = 1;
+  if (alias_a && cfg == 2) cfg = 1;
+  if (cfg == 1) return gemm_launch_form<8, 4>(st, p, batch, aT, bT);
+  if (cfg == 2) return gemm_launch_form<8, 2>(st, p, batch, aT, bT);
+  return gemm_launch_form<4, 4>(st, p, batch, aT, bT);
 }
 
 }  // namespace gpr

@@ -103,9 +103,7 @@ struct CudaBE {
 };
 
 int setup_kernel_attributes(gpr_ctx* ctx) {
-  CK(cudaFuncSetAttribute(dgemm128_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<true, true>()));
-  CK(cudaFuncSetAttribute(dgemm128_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<false, true>()));
-  CK(cudaFuncSetAttribute(dgemm128_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<false, false>()));
+  CK(gemm_setup_attributes());
   CK(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM_BYTES));
   CK(cudaFuncSetAttribute(leaf_mv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_MV_SMEM_BYTES));
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -416,6 +414,7 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
     return GPR_OK;
   }
   if (!strcmp(name, "inplace_lauum")) { ctx->inplace_lauum = value ? 1 : 0; return GPR_OK; }
+  if (!strcmp(name, "gemm_cfg")) { gemm_forced_cfg() = (int)value; return GPR_OK; }   // 0 auto, 1..3: see dgemm_sm100.cuh
   return fail(ctx, GPR_ERR_ARG, std::string("unknown option ") + name);
 }
 

@@ -269,7 +269,8 @@ def test_predict_reference_suite(gpr, n, npred, dim):
     np.testing.assert_allclose(mu3, y, rtol=1e-2, atol=1e-2)
     mdo3 = o.GPRModel((o.SE, o.NOISE), hp3, x, y)
     cond3 = np.linalg.cond(o.kernel((o.SE, o.NOISE), hp3, x))
-    assert mean_err(mu3, o.predict_mean(mdo3, x, same=True), y) <= ctol(TOL_MU, cond3)
+    # sigma_n = 1e-5: cond(K) ~ 1e9-1e10, agreement of two correct Choleskys is ~1e3 * cond * eps at best
+    assert mean_err(mu3, o.predict_mean(mdo3, x, same=True), y) <= max(TOL_MU, 2000.0 * cond3 * EPS)
     md = gpr.GPRModel(SE + WN, 0.1 + rng.random(dim + 2), x, y)
     yp, Sf = gpr.predict(md, xp)
     yd, Sd = gpr.predict(md, xp, diagonal_var=True)

@@ -60,6 +60,60 @@ def sec_gemm():
                 print("   C, ref, C0, full-update at first bad upper:", C[i, j], ref[i, j], C0[i, j])
 
 
+def sec_gemm_cfgs():
+    """Correctness + throughput of the three GEMM tile configurations (option gemm_cfg)."""
+    from gpr_sm100a import _ffi
+    ctx = _ffi.get_context()
+    rng = np.random.default_rng(1)
+    n = 4096
+    Abig = np.asfortranarray(rng.standard_normal((n, n)))
+    Bbig = np.asfortranarray(rng.standard_normal((n, n)))
+    Czero = np.zeros((n, n), order="F")
+    for cfg in (1, 2, 3):
+        ctx.set_option("gemm_cfg", cfg)
+        worst = 0.0
+        for (tA, tB) in (("T", "N"), ("N", "N"), ("N", "T")):
+            M, N, K = 384, 256, 272
+            A = rng.standard_normal((K, M) if tA == "T" else (M, K))
+            B = rng.standard_normal((N, K) if tB == "T" else (K, N))
+            C0 = rng.standard_normal((M, N))
+            opA = A.T if tA == "T" else A
+            opB = B.T if tB == "T" else B
+            C, _ = _ffi.dbg_dgemm(ctx, tA, tB, 0.5, A, B, 2.0, C0)
+            worst = max(worst, relerr(C, 0.5 * opA @ opB + 2.0 * C0))
+            # upper-only on a square diagonal-anchored C
+            M = N = 384
+            A = rng.standard_normal((K, M) if tA == "T" else (M, K))
+            B = rng.standard_normal((N, K) if tB == "T" else (K, N))
+            C0 = rng.standard_normal((M, N))
+            opA = A.T if tA == "T" else A
+            opB = B.T if tB == "T" else B
+            C, _ = _ffi.dbg_dgemm(ctx, tA, tB, -1.0, A, B, 1.0, C0, flags=1)
+            ref = C0 - opA @ opB
+            worst = max(worst, relerr(np.triu(C), np.triu(ref)), float(np.abs(np.tril(C, -1) - np.tril(C0, -1)).max()))
+        # triangular product W W^T (UPPER_ONLY | K_FROM_N), W upper triangular with zero lower part
+        m = 512
+        W = np.triu(rng.standard_normal((m, m)))
+        C0 = rng.standard_normal((m, m))
+        C, _ = _ffi.dbg_dgemm(ctx, "N", "T", 1.0, W, W, 0.0, C0, flags=3)
+        worst = max(worst, relerr(np.triu(C), np.triu(W @ W.T)), float(np.abs(np.tril(C, -1) - np.tril(C0, -1)).max()))
+        print(f"gemm cfg {cfg}: worst error over forms/flags {worst:.2e}", "OK" if worst < 1e-12 else "BAD")
+        for (tA, tB) in (("T", "N"), ("N", "N"), ("N", "T")):
+            _, ms = _ffi.dbg_dgemm(ctx, tA, tB, 1.0, Abig, Bbig, 1.0, Czero, reps=5)
+            print(f"   cfg {cfg} {tA}{tB} {n}^3: {ms:.3f} ms {2 * n ** 3 / ms / 1e9:.2f} TFLOP/s")
+        for k in (128, 512):
+            _, ms = _ffi.dbg_dgemm(ctx, "T", "N", -1.0, np.asfortranarray(Abig[:k, :]), np.asfortranarray(Bbig[:k, :]), 1.0, Czero, reps=5)
+            print(f"   cfg {cfg} TN {n}x{n}x{k}: {ms:.3f} ms {2 * n * n * k / ms / 1e9:.2f} TFLOP/s")
+        _, ms = _ffi.dbg_dgemm(ctx, "T", "N", 1.0, np.asfortranarray(Abig[:128, :128]), np.asfortranarray(Bbig[:128, :2048]), 0.0, np.zeros((128, 2048), order="F"), reps=5)
+        print(f"   cfg {cfg} leaf 128x2048x128: {ms * 1e3:.1f} us")
+        K = rng.standard_normal((n, 64))
+        K = K @ K.T / 64 + np.eye(n)
+        for mode in (0, 3):
+            A, ms = _ffi.dbg_factor(ctx, K, mode)
+            print(f"   cfg {cfg} factor n={n} mode={mode}: {ms:.1f} ms")
+    ctx.set_option("gemm_cfg", 0)
+
+
 def sec_gemm_perf():
     from gpr_sm100a import _ffi
     import torch
@@ -334,7 +388,7 @@ def sec_perf():
         mh.close()
 
 
-SECTIONS = {"gemm": sec_gemm, "factor": sec_factor, "kernel": sec_kernel, "nlml": sec_nlml, "predict": sec_predict,
+SECTIONS = {"gemm_cfgs": sec_gemm_cfgs, "gemm": sec_gemm, "factor": sec_factor, "kernel": sec_kernel, "nlml": sec_nlml, "predict": sec_predict,
             "split": sec_split, "gemm_perf": sec_gemm_perf, "factor_perf": sec_factor_perf, "perf": sec_perf}
 
 if __name__ == "__main__":
