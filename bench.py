@@ -276,8 +276,18 @@ def run_gpu(args, rank, world, local_rank):
         t0 = time.perf_counter()
         mu, var, _ = mh.predict(xp, want_var=True)
         dt = time.perf_counter() - t0
+        tp = mh.timings()
         extra["predict_points_per_s"] = M / dt
         extra["predict_var_tflops"] = M * float(N) ** 2 / dt / 1e12
+        extra["predict_stage_ms"] = {k: round(v, 3) for k, v in tp.items() if k.startswith("pred")}
+        # the two streaming kernels (K* . wt and row norms of V) read 8*M*N bytes each
+        hbm = 6478.9
+        try:
+            hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        extra["predict_stream_gbs"] = {"mean_kstar_wt": 8.0 * M * N / tp["pred_mean"] / 1e6, "rownorm_v": 8.0 * M * N / tp["pred_rownorm"] / 1e6,
+                                       "hbm_peak_gbs": hbm}
         extra["predict_config"] = f"mean+diag variance, M={M} general test points, host in/out, N={N}"
 
     hp_peak = None

@@ -370,10 +370,15 @@ template <int MODE>
 __global__ void __launch_bounds__(64) rowreduce_kernel(const double* __restrict__ K, long long ld, long long rows,
                                                        long long cols, long long cols_per_split,
                                                        const double* __restrict__ w, double* __restrict__ partial) {
-  const long long r = ((long long)blockIdx.x * 64 + threadIdx.x) * 2;
-  if (r >= rows) return;
+  extern __shared__ __align__(16) double rr_w[];   // MODE 0: the split's slice of w (cols_per_split doubles)
   const long long cbeg = (long long)blockIdx.y * cols_per_split;
   long long cend = cbeg + cols_per_split; if (cend > cols) cend = cols;
+  if (MODE == 0) {
+    for (long long c = cbeg + threadIdx.x; c < cend; c += 64) rr_w[c - cbeg] = w[c];
+    __syncthreads();
+  }
+  const long long r = ((long long)blockIdx.x * 64 + threadIdx.x) * 2;
+  if (r >= rows) return;
   double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0};
   const double* p = K + r;
   long long c = cbeg;
@@ -383,13 +388,13 @@ __global__ void __launch_bounds__(64) rowreduce_kernel(const double* __restrict_
     for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const double2*>(p + (c + u) * ld));
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      if (MODE == 0) { const double ww = w[c + u]; ax[u & 3] += v[u].x * ww; ay[u & 3] += v[u].y * ww; }
+      if (MODE == 0) { const double ww = rr_w[c - cbeg + u]; ax[u & 3] += v[u].x * ww; ay[u & 3] += v[u].y * ww; }
       else { ax[u & 3] += v[u].x * v[u].x; ay[u & 3] += v[u].y * v[u].y; }
     }
   }
   for (; c < cend; ++c) {
     const double2 v = __ldcs(reinterpret_cast<const double2*>(p + c * ld));
-    if (MODE == 0) { const double ww = w[c]; ax[0] += v.x * ww; ay[0] += v.y * ww; }
+    if (MODE == 0) { const double ww = rr_w[c - cbeg]; ax[0] += v.x * ww; ay[0] += v.y * ww; }
     else { ax[0] += v.x * v.x; ay[0] += v.y * v.y; }
   }
   double* o = partial + (size_t)blockIdx.y * rows + r;

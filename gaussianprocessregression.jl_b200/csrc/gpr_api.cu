@@ -39,7 +39,7 @@ struct gpr_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   int sm_count = 0;
-  int64_t predict_tile = 8192;
+  int64_t predict_tile = 16384;
   int inplace_lauum = 0;   // option "inplace_lauum": force the recursive in-place W W^T (saves one N x N buffer)
   long long launches = 0;
   long long* d_info = nullptr;
@@ -196,6 +196,9 @@ void timer_free(Timer& t) {
   for (int i = 0; i < GPR_T_COUNT; ++i) { cudaEventDestroy(t.beg[i]); cudaEventDestroy(t.end[i]); }
 }
 void timer_reset(Timer& t) { for (int i = 0; i < GPR_T_COUNT; ++i) { t.used[i] = false; t.acc_ms[i] = 0.0; } }
+void timer_reset_predict(Timer& t) {
+  for (int i = GPR_T_PRED_KSTAR; i <= GPR_T_PRED_ROWNORM; ++i) { t.used[i] = false; t.acc_ms[i] = 0.0; }
+}
 // accumulate a previously recorded slot (needs the events to have completed)
 void timer_collect(Timer& t, int slot) {
   if (!t.used[slot]) return;
@@ -684,12 +687,13 @@ int row_reduce(gpr_model* m, int mode, const double* K, int64_t ld, int64_t rows
   const int64_t row_ctas = rows_pad / 128;
   int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 16 / std::max<int64_t>(row_ctas, 1), cols / 64));
   if (nsplit < 1) nsplit = 1;
+  if (mode == 0 && (cols + nsplit - 1) / nsplit > 4096) nsplit = (int)((cols + 4095) / 4096);   // w slice in shared memory (<= 32 KB)
   const int64_t cps = (cols + nsplit - 1) / nsplit;
   nsplit = (int)((cols + cps - 1) / cps);
   int rc = ensure(ctx, m->w_part, (size_t)nsplit * rows_pad);
   if (rc) return rc;
   dim3 grid((unsigned)row_ctas, (unsigned)nsplit);
-  if (mode == 0) rowreduce_kernel<0><<<grid, 64, 0, ctx->stream>>>(K, ld, rows_pad, cols, cps, w, m->w_part.p);
+  if (mode == 0) rowreduce_kernel<0><<<grid, 64, (size_t)cps * sizeof(double), ctx->stream>>>(K, ld, rows_pad, cols, cps, w, m->w_part.p);
   else rowreduce_kernel<1><<<grid, 64, 0, ctx->stream>>>(K, ld, rows_pad, cols, cps, w, m->w_part.p);
   ctx->launches++;
   CK(cudaGetLastError());
@@ -753,6 +757,7 @@ int gpr_predict_device(gpr_model* m, const double* d_xp, int64_t M, int same_x, 
   if (!m->have_factor || m->factor_destroyed) return fail(ctx, GPR_ERR_STATE, "predict: call gpr_update_cache first");
   if (same_x && M != m->N) return fail(ctx, GPR_ERR_ARG, "same_x requires M == N");
   CK(cudaSetDevice(ctx->device));
+  timer_reset_predict(m->tm);
   const int64_t MT = ctx->predict_tile;
   for (int64_t m0 = 0; m0 < M; m0 += MT) {
     const int64_t mt = std::min(MT, M - m0);
@@ -770,6 +775,7 @@ int gpr_predict(gpr_model* m, const double* xp, int64_t M, int same_x, double* m
   if (!m->have_factor || m->factor_destroyed) return fail(ctx, GPR_ERR_STATE, "predict: call gpr_update_cache first");
   if (same_x && M != m->N) return fail(ctx, GPR_ERR_ARG, "same_x requires M == N");
   CK(cudaSetDevice(ctx->device));
+  timer_reset_predict(m->tm);
   const int64_t Np = m->Np, N = m->N;
   const int D = m->D, ny = m->ny;
 
@@ -927,6 +933,7 @@ int gpr_split_predict(gpr_model* m, const double* xe, int64_t ne, const double* 
   if (m->ny != 1) return fail(ctx, GPR_ERR_UNSUPPORTED, "split predict needs a vector y (Diagonal(wt), src/split_predict.jl:13)");
   if (var && (e_lo < 1 || e_hi > ne || e_lo > e_hi + 1)) return fail(ctx, GPR_ERR_ARG, "var_range out of bounds");
   CK(cudaSetDevice(ctx->device));
+  timer_reset_predict(m->tm);
   const int D = m->D, nk = m->nk;
   const int64_t N = m->N, Np = m->Np;
   SplitBufs sb; sb.nep = round_up(ne, 128); sb.nqp = round_up(nq, 128);
