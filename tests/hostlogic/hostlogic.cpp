@@ -3,18 +3,55 @@
 // arithmetic of the blocked potrf / trsm / trtri / lauum / potrs drivers can be
 // checked in the CPU test-suite (pytest -m "not gpu").  The product library
 // instantiates the same template with the CUDA backend only.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
 
 #include "../../gaussianprocessregression.jl_b200/csrc/blocked.hpp"
+#include "../../gaussianprocessregression.jl_b200/csrc/dist_blocked.hpp"
 
 namespace {
 
 struct CpuBE {
   long long info = 0;
   long long gemm_calls = 0;
+  void activate() {}
+  // tile-mapped GEMM of csrc/dist_blocked.hpp (same predicate the CUDA kernel evaluates per 128-tile)
+  void gemm_map(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, const gpr::TileMap& map) {
+    gemm_calls++;
+    std::vector<double> tmp((size_t)M * N, 0.0);
+    std::vector<char> live((size_t)M * N, 0);
+    for (int64_t n = 0; n < N; ++n) {
+      const int64_t gt = map.col_gtile[n / gpr::LEAF];
+      int64_t kend = K;
+      if (flags & gpr::BLK_MAP_KUPTO) kend = std::min<int64_t>(K, (gt - map.k_gtile0 + 1) * gpr::LEAF);
+      const int64_t brow = (flags & gpr::BLK_MAP_BROWS) ? gt * gpr::LEAF + n % gpr::LEAF : n;
+      for (int64_t m = 0; m < M; ++m) {
+        if (flags & gpr::BLK_MAP_UPPER) {
+          const int64_t rt = map.row_gtile0 + m / gpr::LEAF;
+          if (rt > gt || (rt == gt && m % gpr::LEAF > n % gpr::LEAF)) continue;
+        }
+        double s = 0.0;
+        for (int64_t k = 0; k < kend; ++k) {
+          const double a = (tA == 'T') ? A[k + m * lda] : A[m + k * lda];
+          const double b = (tB == 'T') ? B[brow + k * ldb] : B[k + n * ldb];
+          s += a * b;
+        }
+        tmp[m + n * M] = s;
+        live[m + n * M] = 1;
+      }
+    }
+    for (int64_t n = 0; n < N; ++n)
+      for (int64_t m = 0; m < M; ++m) {
+        if (!live[m + n * M]) continue;
+        double r = alpha * tmp[m + n * M];
+        if (beta != 0.0) r += beta * C[m + n * ldc];
+        C[m + n * ldc] = r;
+      }
+  }
   void gemm(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A0, int64_t lda,
             const double* B0, int64_t ldb, double beta, double* C0, int64_t ldc, int flags, int64_t batch = 1,
             int64_t sA = 0, int64_t sB = 0, int64_t sC = 0) {
@@ -91,9 +128,91 @@ struct CpuBE {
   }
 };
 
+// All G ranks live in this process; a collective is a set of plain copies between the ranks' arrays.
+struct CpuComm {
+  gpr::DistLayout lay;
+  std::vector<gpr::DistRank<CpuBE>>* ranks = nullptr;
+  long long barriers = 0;
+  void barrier() { barriers++; }
+  void bcast_diag(int64_t k, bool with_owner) {
+    const int o = lay.owner(k);
+    const int64_t nb = lay.nb, kb = k / lay.G;
+    const auto& S = (*ranks)[o];
+    for (auto& R : *ranks) {
+      if (R.r == o && !with_owner) continue;
+      for (int64_t c = 0; c < nb; ++c)
+        for (int64_t p = 0; p < nb; ++p) R.Ukk[p + c * nb] = S.L[k * nb + p + (kb * nb + c) * S.ld];
+      if (R.r != o)
+        memcpy(R.dinv + k * lay.tpb() * 128 * 128, S.dinv + k * lay.tpb() * 128 * 128, sizeof(double) * lay.tpb() * 128 * 128);
+    }
+  }
+  void gather_rowpanel(int64_t k) {
+    const int64_t nb = lay.nb;
+    for (auto& R : *ranks)
+      for (int64_t J = k + 1; J < lay.nblk; ++J) {
+        const auto& S = (*ranks)[lay.owner(J)];
+        for (int64_t c = 0; c < nb; ++c)
+          for (int64_t p = 0; p < nb; ++p)
+            R.panel[p + ((J - k - 1) * nb + c) * nb] = S.L[k * nb + p + ((J / lay.G) * nb + c) * S.ld];
+      }
+  }
+  void bcast_colpanel(int64_t k) {
+    const int64_t nb = lay.nb;
+    const auto& S = (*ranks)[lay.owner(k)];
+    for (auto& R : *ranks)
+      for (int64_t c = 0; c < nb; ++c)
+        for (int64_t i = 0; i < (k + 1) * nb; ++i) R.panel[i + c * lay.Np] = S.L[i + ((k / lay.G) * nb + c) * S.ld];
+  }
+};
+
 }  // namespace
 
 extern "C" {
+
+// Distributed (block-cyclic over G simulated ranks) factorization of A (n x n, n % nb == 0) with right-hand
+// sides Y (n x nyp).  mode 0: potrf (A upper <- U, Y <- U^-T Y), 1: + trtri (A upper <- U^-1, Y <- -A^-1 Y),
+// 2: + lauum (A upper <- A^-1).  The strict lower triangle of A comes back zero.
+long long hl_dist_factor(double* A, int64_t n, int64_t nb, int G, double* Y, int64_t nyp, int mode) {
+  gpr::DistLayout lay;
+  lay.G = G; lay.Np = n; lay.nb = nb; lay.nblk = n / nb; lay.nyp = nyp;
+  std::vector<CpuBE> bes(G);
+  std::vector<gpr::DistRank<CpuBE>> ranks(G);
+  std::vector<std::vector<double>> Ls(G), dinvs(G), Ukks(G), panels(G);
+  std::vector<std::vector<int>> gts(G);
+  for (int r = 0; r < G; ++r) {
+    Ls[r].assign((size_t)n * std::max<int64_t>(lay.lcols(r), 1), 0.0);
+    dinvs[r].assign((size_t)n * 128, 0.0);
+    Ukks[r].assign((size_t)nb * nb, 0.0);
+    panels[r].assign((size_t)n * nb, 0.0);
+    gts[r].resize(std::max<int64_t>(lay.ltiles(r), 1));
+    for (int64_t t = 0; t < lay.ltiles(r); ++t) gts[r][t] = lay.gtile(r, t);
+    for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
+      const int64_t J = lb * G + r;
+      for (int64_t c = 0; c < nb; ++c)
+        for (int64_t i = 0; i <= J * nb + c; ++i) Ls[r][i + (lb * nb + c) * n] = A[i + (J * nb + c) * n];   // upper only
+    }
+    if (r == lay.y_owner())
+      for (int64_t c = 0; c < nyp; ++c) memcpy(&Ls[r][(size_t)(lay.ycol0(r) + c) * n], Y + c * n, sizeof(double) * n);
+    ranks[r] = gpr::DistRank<CpuBE>{r, &bes[r], Ls[r].data(), n, dinvs[r].data(), Ukks[r].data(), panels[r].data(), gts[r].data()};
+  }
+  CpuComm comm;
+  comm.lay = lay; comm.ranks = &ranks;
+  gpr::DistBlocked<CpuBE, CpuComm> db(lay, ranks, comm);
+  db.potrf();
+  if (mode >= 1) db.trtri();
+  if (mode >= 2) db.lauum();
+  long long info = 0;
+  for (int r = 0; r < G; ++r) {
+    if (bes[r].info && (!info || bes[r].info < info)) info = bes[r].info;
+    for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
+      const int64_t J = lb * G + r;
+      for (int64_t c = 0; c < nb; ++c) memcpy(A + (J * nb + c) * n, &Ls[r][(size_t)(lb * nb + c) * n], sizeof(double) * n);
+    }
+    if (r == lay.y_owner())
+      for (int64_t c = 0; c < nyp; ++c) memcpy(Y + c * n, &Ls[r][(size_t)(lay.ycol0(r) + c) * n], sizeof(double) * n);
+  }
+  return info;
+}
 
 // A: n x n column major (n % 128 == 0), factored in place.  mode 0: potrf, 1: +trtri, 2: +lauum.
 long long hl_factor(double* A, int64_t n, int mode, long long* gemm_calls) {

@@ -17,7 +17,7 @@ def hl(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out,
                            os.path.join(HERE, "hostlogic", "hostlogic.cpp")])
     L = ctypes.CDLL(out)
-    for f in (L.hl_factor, L.hl_potrs, L.hl_trsm_run, L.hl_potrsv):
+    for f in (L.hl_factor, L.hl_potrs, L.hl_trsm_run, L.hl_potrsv, L.hl_dist_factor):
         f.restype = ctypes.c_longlong
     return L
 
@@ -73,3 +73,31 @@ def test_blocked_solves(hl, n):
     A = np.asfortranarray(K.copy())
     assert hl.hl_trsm_run(dp(A), ctypes.c_int64(n), dp(R), ctypes.c_int64(256)) == 0
     np.testing.assert_allclose(R, R0 @ np.linalg.inv(sl.cholesky(K, lower=False)), atol=1e-12)
+
+
+# ---- block-cyclic multi-rank drivers (csrc/dist_blocked.hpp), G simulated ranks in one process
+@pytest.mark.parametrize("n,nb,G", [(512, 128, 1), (512, 128, 2), (768, 128, 3), (1024, 256, 2), (1024, 256, 3),
+                                    (1024, 128, 4), (768, 384, 2), (1280, 256, 4), (512, 256, 4)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_dist_factor(hl, n, nb, G, mode):
+    K = spd(n, n + G)
+    rng = np.random.default_rng(n + nb + G)
+    Y0 = rng.standard_normal((n, 128))
+    A = np.asfortranarray(np.triu(K))
+    Y = np.asfortranarray(Y0.copy())
+    info = hl.hl_dist_factor(dp(A), ctypes.c_int64(n), ctypes.c_int64(nb), G, dp(Y), ctypes.c_int64(128), mode)
+    assert info == 0
+    U = sl.cholesky(K, lower=False)
+    ref = [U, np.linalg.inv(U), np.linalg.inv(K)][mode]
+    np.testing.assert_allclose(np.triu(A), np.triu(ref), rtol=0, atol=1e-11 * np.abs(ref).max())
+    assert not np.tril(A, -1).any()
+    yref = sl.solve_triangular(U, Y0, trans="T") if mode == 0 else -np.linalg.solve(K, Y0)
+    np.testing.assert_allclose(Y, yref, rtol=0, atol=1e-11 * np.abs(yref).max())
+
+
+def test_dist_not_posdef(hl):
+    K = np.eye(512)
+    K[300, 300] = -2.0
+    A = np.asfortranarray(K)
+    Y = np.zeros((512, 128), order="F")
+    assert hl.hl_dist_factor(dp(A), ctypes.c_int64(512), ctypes.c_int64(128), 2, dp(Y), ctypes.c_int64(128), 0) == 301
