@@ -42,6 +42,8 @@ struct KBuildArgs {
   int sigma_one;         // force sigma := 1 (split A and B factors)
   const double* row_scale;   // optional: multiply row r by row_scale[r] (Cw = diag(wt) C), may be null
   long long diag_shift;  // row r is "the same point" as col r + diag_shift (tiles of a larger problem)
+  int zero_lower;        // entries strictly below that diagonal are written as 0 and not evaluated (block-cyclic
+                         // multi-GPU layout: only the upper triangle is referenced, csrc/dist_blocked.hpp)
 };
 
 constexpr int KB_TILE = 64;
@@ -63,6 +65,17 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_kernel(const KBuildArgs a) 
   const int D = a.D;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const long long r0 = (long long)blockIdx.x * KB_TILE, c0 = (long long)blockIdx.y * KB_TILE;
+
+  if (a.zero_lower && r0 > c0 + a.diag_shift + (KB_TILE - 1)) {   // tile entirely below the diagonal
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long r = r0 + tx + 16 * i, c = c0 + ty + 16 * j;
+        if (r < a.Rp && c < a.Cp) a.out[r + c * a.ldo] = 0.0;
+      }
+    return;
+  }
 
   // non-noise components
   int kidx[KSPEC_MAXC]; int nk = 0;
@@ -141,8 +154,9 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_kernel(const KBuildArgs a) 
         if (a.add_noise && r == c + a.diag_shift) v += noise2;
         if (a.row_scale) v *= a.row_scale[r];
       } else {
-        v = (a.pad_identity && r == c) ? 1.0 : 0.0;
+        v = (a.pad_identity && r == c + a.diag_shift) ? 1.0 : 0.0;
       }
+      if (a.zero_lower && r > c + a.diag_shift) v = 0.0;
       a.out[r + c * a.ldo] = v;
     }
 }
@@ -207,11 +221,16 @@ struct GradArgs {
   const double* alpha; const double* x; int D; long long N;
   const double* hp; KSpec spec; int P; double eps;
   double* partial;   // gridDim.x * (P+1)
+  // DIST form (block-cyclic multi-GPU layout): Kinv holds this rank's block columns only
+  int G, rank;           // local block column lb is global block column lb * G + rank
+  int nbt;               // 64-tiles per block column (nb / 64)
+  long long lcol_tiles;  // local 64-tile columns (matrix columns only)
 };
 
 constexpr int GR_TILE = 64;
 constexpr int GR_THREADS = 256;
 
+template <bool DIST>
 __global__ void __launch_bounds__(GR_THREADS) grad_reduce_kernel(const GradArgs a) {
   extern __shared__ __align__(16) double gr_smem[];
   const int D = a.D, P = a.P;
@@ -224,12 +243,22 @@ __global__ void __launch_bounds__(GR_THREADS) grad_reduce_kernel(const GradArgs 
   for (int s = 0; s <= P; ++s) acc[s * GR_THREADS + tid] = 0.0;
 
   const long long T = (a.N + GR_TILE - 1) / GR_TILE;
-  const long long ntiles = T * (T + 1) / 2;
+  const long long ntiles = DIST ? T * a.lcol_tiles : T * (T + 1) / 2;
   for (long long lin = blockIdx.x; lin < ntiles; lin += gridDim.x) {
-    long long tj = (long long)((sqrt(8.0 * (double)lin + 1.0) - 1.0) * 0.5);
-    while (tj * (tj + 1) / 2 > lin) --tj;
-    while ((tj + 1) * (tj + 2) / 2 <= lin) ++tj;
-    const long long ti = lin - tj * (tj + 1) / 2;
+    long long ti, tj, lc0;   // tile row, GLOBAL tile column, first column of the tile inside Kinv
+    if (DIST) {
+      const long long ltj = lin / T;
+      ti = lin % T;
+      tj = ((ltj / a.nbt) * a.G + a.rank) * a.nbt + ltj % a.nbt;
+      lc0 = ltj * GR_TILE;
+      if (ti > tj || tj >= T) continue;   // block uniform
+    } else {
+      tj = (long long)((sqrt(8.0 * (double)lin + 1.0) - 1.0) * 0.5);
+      while (tj * (tj + 1) / 2 > lin) --tj;
+      while ((tj + 1) * (tj + 2) / 2 <= lin) ++tj;
+      ti = lin - tj * (tj + 1) / 2;
+      lc0 = tj * GR_TILE;
+    }
     const long long r0 = ti * GR_TILE, c0 = tj * GR_TILE;
     __syncthreads();
     for (int idx = tid; idx < D * GR_TILE; idx += GR_THREADS) {
@@ -250,7 +279,7 @@ __global__ void __launch_bounds__(GR_THREADS) grad_reduce_kernel(const GradArgs 
         const long long r = r0 + tx + 16 * i, c = c0 + ty + 16 * j;
         double v = 0.0;
         if (r < a.N && c < a.N && r <= c) {
-          const double m = al1[tx + 16 * i] * al2[ty + 16 * j] - a.Kinv[r + c * a.ld];
+          const double m = al1[tx + 16 * i] * al2[ty + 16 * j] - a.Kinv[r + (lc0 + ty + 16 * j) * a.ld];
           if (r == c) { v = m; dsum += m; } else v = 2.0 * m;
         }
         wm[i][j] = v;

@@ -52,6 +52,11 @@ enum GemmFlags : int {
   GEMM_UPPER_ONLY = 1,   // C is a diagonal-anchored symmetric block: only tiles/elements with row <= col are computed/stored
   GEMM_K_FROM_N = 2,     // tile column block J contracts over k >= 128*J only (triangular product W W^T, W upper)
   GEMM_C_ALIASES_A = 4,  // C overwrites the A operand in place (needs the full-width 128x128 tile)
+  // Tile-mapped forms of the block-cyclic multi-GPU drivers (csrc/dist_blocked.hpp): the local 128-tile column
+  // jt of C stands for the GLOBAL tile column gt = col_gtile[jt].
+  GEMM_MAP_UPPER = 8,    // only elements with (row_gtile0 + tile row, row in tile) <= (gt, col in tile) exist
+  GEMM_MAP_KUPTO = 16,   // the tile column contracts over k < (gt - k_gtile0 + 1) * 128 only
+  GEMM_MAP_BROWS = 32,   // (transB = 'T') the B rows of the tile column start at gt * 128
 };
 
 struct GemmParams {
@@ -62,6 +67,8 @@ struct GemmParams {
   double* C; long long ldc;
   int flags;
   long long sA, sB, sC;   // strided batch (blockIdx.z)
+  const int* col_gtile;   // GEMM_MAP_*: global 128-tile column per local 128-tile column (device memory)
+  int row_gtile0, k_gtile0;
 };
 
 // smem layout of one operand tile with ROWS rows (m or n extent) and 16 k
@@ -131,6 +138,11 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
   const int tile_m = blockIdx.x, tile_n = blockIdx.y;
   const int blk_n = (tile_n * BN) >> 7;   // 128-block column of this tile (tile_m is already a 128-block row)
   if ((p.flags & GEMM_UPPER_ONLY) && tile_m > blk_n) return;
+  int gt = 0;   // global tile column (mapped forms)
+  if (p.flags & (GEMM_MAP_UPPER | GEMM_MAP_KUPTO | GEMM_MAP_BROWS)) {
+    gt = p.col_gtile[blk_n];
+    if ((p.flags & GEMM_MAP_UPPER) && p.row_gtile0 + tile_m > gt) return;
+  }
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
   const long long m0 = (long long)tile_m * GEMM_BM, n0 = (long long)tile_n * BN;
   const long long bz = blockIdx.z;
   const double* Ap = p.A + bz * p.sA + (A_KC ? m0 * p.lda : m0);
-  const double* Bp = p.B + bz * p.sB + (B_KC ? n0 * p.ldb : n0);
+  const double* Bp = p.B + bz * p.sB + (B_KC ? n0 * p.ldb : ((p.flags & GEMM_MAP_BROWS) ? (long long)gt * 128 + (n0 & 127) : n0));
   const int kt0 = (p.flags & GEMM_K_FROM_N) ? blk_n * (128 / GEMM_BK) : 0;   // first k-tile of this tile
 
   double acc[MI][4][2];
@@ -149,7 +161,8 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const int KT = p.K / GEMM_BK - kt0;
+  int KT = p.K / GEMM_BK - kt0;
+  if (p.flags & GEMM_MAP_KUPTO) KT = min(KT, (gt - p.k_gtile0 + 1) * (128 / GEMM_BK));
 
   // Pull the C tile towards L2 while the main loop runs (the epilogue reads it when beta != 0):
   // BN columns x 1 KiB = 8 lines of 128 B per column.
@@ -236,7 +249,8 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
   // the batch is issued (a load-after-store to the same array cannot be
   // hoisted by the compiler, which would serialise 64 DRAM round trips).
   // On the diagonal 128-block of an UPPER_ONLY product only row <= col (inside the block) is touched.
-  const bool diag_tile = (p.flags & GEMM_UPPER_ONLY) && (tile_m == blk_n);
+  const bool diag_tile = ((p.flags & GEMM_UPPER_ONLY) && (tile_m == blk_n)) ||
+                         ((p.flags & GEMM_MAP_UPPER) && (p.row_gtile0 + tile_m == gt));
   const int coff = (int)(n0 & 127);   // column offset of this tile inside its 128-block (0 or 64)
   const double alpha = p.alpha, beta = p.beta;
   double* Cp = p.C + bz * p.sC + m0 + n0 * p.ldc;
@@ -345,11 +359,13 @@ inline int& gemm_forced_cfg() { static int v = 0; return v; }
 inline cudaError_t launch_dgemm128(cudaStream_t st, char transA, char transB, int M, int N, int K, double alpha,
                                    const double* A, long long lda, const double* B, long long ldb, double beta,
                                    double* C, long long ldc, int flags, int batch = 1, long long sA = 0,
-                                   long long sB = 0, long long sC = 0) {
+                                   long long sB = 0, long long sC = 0, const int* col_gtile = nullptr,
+                                   int row_gtile0 = 0, int k_gtile0 = 0) {
   if (M <= 0 || N <= 0 || batch <= 0) return cudaSuccess;
   if ((M % GEMM_BM) || (N % GEMM_BN) || (K % GEMM_BK) || K <= 0 || batch > 65535) return cudaErrorInvalidValue;
   if ((flags & GEMM_K_FROM_N) && K < N) return cudaErrorInvalidValue;
-  GemmParams p{M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, flags, sA, sB, sC};
+  if ((flags & (GEMM_MAP_UPPER | GEMM_MAP_KUPTO | GEMM_MAP_BROWS)) && !col_gtile) return cudaErrorInvalidValue;
+  GemmParams p{M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, flags, sA, sB, sC, col_gtile, row_gtile0, k_gtile0};
   const bool aT = (transA == 'T' || transA == 't'), bT = (transB == 'T' || transB == 't');
   if (aT && bT) return cudaErrorNotSupported;
   // C written over the A operand: a CTA must own every k column it reads -> full-width 128x128 tile.

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "blocked.hpp"
+#include "dist_blocked.hpp"
 #include "cov_kernels.cuh"
 #include "dgemm_sm100.cuh"
 #include "leaf_kernels.cuh"
@@ -78,6 +79,14 @@ struct CudaBE {
       ctx->launches++;
     }
   }
+  void activate() { note(cudaSetDevice(ctx->device)); }
+  // tile-mapped GEMM of the block-cyclic multi-GPU drivers (csrc/dist_blocked.hpp)
+  void gemm_map(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, const TileMap& map) {
+    note(launch_dgemm128(ctx->stream, tA, tB, (int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, 0, 0, 0,
+                         map.col_gtile, map.row_gtile0, map.k_gtile0));
+    ctx->launches++;
+  }
   void potrf_leaf(double* A, int64_t lda, double* dinv, int64_t goff) {
     potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, ctx->stream>>>(A, lda, dinv, ctx->d_info, goff);
     note(cudaGetLastError());
@@ -109,7 +118,8 @@ int setup_kernel_attributes(gpr_ctx* ctx) {
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_SPLIT_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_SPLIT_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(grad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(grad_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(grad_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return GPR_OK;
 }
 
@@ -340,7 +350,7 @@ int compute_grad(gpr_model* m, int log_scale, double* G_host) {
     a.x = m->d_x; a.D = m->D; a.N = m->N; a.hp = m->d_hp; a.spec = m->spec; a.P = m->P; a.eps = m->eps_host;
     a.partial = m->d_gpart;
     const size_t smem = ((size_t)(m->P + 1) * GR_THREADS + 2 * (size_t)m->D * GR_TILE + 2 * GR_TILE) * sizeof(double);
-    grad_reduce_kernel<<<m->gr_blocks, GR_THREADS, smem, ctx->stream>>>(a);
+    grad_reduce_kernel<false><<<m->gr_blocks, GR_THREADS, smem, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     grad_finalize_kernel<<<1, 256, 0, ctx->stream>>>(m->d_gpart, m->gr_blocks, m->P, m->d_hp, m->spec, m->D, log_scale, m->d_G);
@@ -367,7 +377,17 @@ int compute_loss(gpr_model* m, double* F) {
 
 extern "C" {
 
-int gpr_version(void) { return 100; }
+int gpr_version(void) { return 101; }
+
+int gpr_device_count(void) {
+  int ndev = 0, ok = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  for (int d = 0; d < ndev; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+  }
+  return ok;
+}
 
 int gpr_ctx_create(int device, gpr_ctx** out) {
   gpr_ctx* ctx = nullptr;
@@ -1123,3 +1143,5 @@ int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, 
 }
 
 }  // extern "C"
+
+#include "mgpu_api.inl"

@@ -1,0 +1,651 @@
+// Single-process multi-device NLML + gradient (gpr_mgpu_*, include/gpr_sm100a.h): BASELINE.json config 5.
+// Included at the end of gpr_api.cu (same translation unit: shares gpr_ctx, CudaBE, the kernels).
+//
+// One rank per entry of the device list; a device may appear more than once ("virtual ranks": the whole
+// distributed code path then runs on a single GPU, which is how tests/test_gpu_parity.py covers it on a
+// 1-GPU box).  Cross-rank movement = pull kernels over peer memory (NVLink when the ranks sit on different
+// devices), ordered by CUDA events; the algorithms are csrc/dist_blocked.hpp.
+namespace {
+
+constexpr int MGPU_MAX_RANKS = 16;
+
+struct PeerPtrs { const double* p[MGPU_MAX_RANKS]; };
+
+// dst (rows x cols, ldd) <- src (rows x cols, lds); rows even, both 16-byte aligned.  src may be peer memory.
+__global__ void __launch_bounds__(256) copy2d_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src,
+                                                     long long lds, long long rows, long long cols) {
+  const long long r2 = rows >> 1;
+  for (long long c = blockIdx.y; c < cols; c += gridDim.y)
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < r2; p += (long long)gridDim.x * blockDim.x)
+      reinterpret_cast<double2*>(dst + c * ldd)[p] = reinterpret_cast<const double2*>(src + c * lds)[p];
+}
+
+// Row panel k of the block-cyclic factor, gathered in global column order on the calling rank:
+//   dst[p + ((J-k-1)*nb + c)*nb] = L_{J mod G}[k*nb + p + ((J/G)*nb + c)*ld],  J = k+1+blockIdx.x
+__global__ void __launch_bounds__(256) gather_rowpanel_kernel(double* __restrict__ dst, const PeerPtrs src, int G, long long ld,
+                                                              long long k, long long nb) {
+  const long long J = k + 1 + blockIdx.x;
+  const double* S = src.p[J % G] + k * nb + (J / G) * nb * ld;
+  double* D = dst + (long long)blockIdx.x * nb * nb;
+  const long long r2 = nb >> 1;
+  for (long long c = blockIdx.y; c < nb; c += gridDim.y)
+    for (long long p = threadIdx.x; p < r2; p += blockDim.x)
+      reinterpret_cast<double2*>(D + c * nb)[p] = reinterpret_cast<const double2*>(S + c * ld)[p];
+}
+
+// out[0] = sum over the local matrix columns of log(L[gcol(c), c]) (the rank's share of log det U); one CTA.
+__global__ void __launch_bounds__(1024, 1) dist_logdiag_kernel(const double* __restrict__ L, long long ld, long long ncols,
+                                                               long long nb, int G, int rank, double* __restrict__ out) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (long long c = threadIdx.x; c < ncols; c += blockDim.x) {
+    const long long g = ((c / nb) * G + rank) * nb + c % nb;
+    s += log(L[g + c * ld]);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// alpha[i] = -X[i] (the y columns hold -K^-1 y after the trtri sweep); out[1] = dot(y, alpha) over n.  One CTA.
+__global__ void __launch_bounds__(1024, 1) dist_alpha_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                             long long n, long long np, double* __restrict__ alpha,
+                                                             double* __restrict__ out) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < np; i += blockDim.x) {
+    const double a = (i < n) ? -X[i] : 0.0;
+    alpha[i] = a;
+    if (i < n) s += y[i] * a;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[1] = red[0];
+}
+
+// tot[s] = sum_b partial[b][s] in block order (deterministic)
+__global__ void grad_partial_sum_kernel(const double* __restrict__ partial, int nblocks, int P, double* __restrict__ tot) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > P) return;
+  double v = 0.0;
+  for (int b = 0; b < nblocks; ++b) v += partial[(size_t)b * (P + 1) + s];
+  tot[s] = v;
+}
+
+struct MRank {
+  gpr_ctx* ctx = nullptr;
+  CudaBE be{nullptr};
+  double *L = nullptr, *dinv = nullptr, *Ukk = nullptr, *panel = nullptr;
+  int* gtile = nullptr;
+  // model part
+  double *x = nullptr, *y = nullptr, *hp = nullptr, *alpha = nullptr, *gpart = nullptr, *scal = nullptr;   // scal: [logdiag, y.alpha, tot[P+1]...]
+  int gr_blocks = 0;
+  cudaEvent_t ev = nullptr;
+};
+
+}  // namespace
+
+struct gpr_mgpu {
+  int G = 0;
+  int64_t nb = 1024;
+  std::vector<MRank> rk;
+  std::string err;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+
+namespace {
+
+int mfail(gpr_mgpu* mg, int code, const std::string& msg) {
+  if (mg) mg->err = msg; else g_create_error = msg;
+  return code;
+}
+#define MCK(call)                                                                                          \
+  do {                                                                                                     \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess) {                                                                               \
+      char b_[512];                                                                                        \
+      snprintf(b_, sizeof b_, "CUDA error %d (%s) at %s [mgpu_api.inl:%d]", (int)e_, cudaGetErrorString(e_), #call, __LINE__); \
+      return mfail(mg, e_ == cudaErrorMemoryAllocation ? GPR_ERR_MEMORY : GPR_ERR_CUDA, b_);               \
+    }                                                                                                      \
+  } while (0)
+
+// COMM of csrc/dist_blocked.hpp for ranks that live in this process
+struct LocalComm {
+  gpr_mgpu* mg;
+  DistLayout lay;
+  int64_t ld;
+  void act(int r) { cudaSetDevice(mg->rk[r].ctx->device); }
+  void barrier() {
+    if (mg->G == 1) return;
+    for (int r = 0; r < mg->G; ++r) { act(r); mg->rk[r].be.note(cudaEventRecord(mg->rk[r].ev, mg->rk[r].ctx->stream)); }
+    for (int r = 0; r < mg->G; ++r) {
+      act(r);
+      for (int s = 0; s < mg->G; ++s)
+        if (s != r) mg->rk[r].be.note(cudaStreamWaitEvent(mg->rk[r].ctx->stream, mg->rk[s].ev, 0));
+    }
+  }
+  void copy2d(int r, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
+    MRank& R = mg->rk[r];
+    act(r);
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows / 2 + 255) / 256, 64)), (unsigned)std::min<int64_t>(cols, 1024));
+    copy2d_kernel<<<grid, 256, 0, R.ctx->stream>>>(dst, ldd, src, lds, rows, cols);
+    R.be.note(cudaGetLastError());
+    R.ctx->launches++;
+  }
+  void bcast_diag(int64_t k, bool with_owner) {
+    const int o = lay.owner(k);
+    const int64_t nb = lay.nb, kb = k / lay.G;
+    const MRank& S = mg->rk[o];
+    const int64_t dl = (int64_t)lay.tpb() * 128 * 128;
+    for (int r = 0; r < mg->G; ++r) {
+      if (r == o && !with_owner) continue;
+      copy2d(r, mg->rk[r].Ukk, nb, S.L + k * nb + kb * nb * ld, ld, nb, nb);
+      if (r != o) copy2d(r, mg->rk[r].dinv + k * dl, dl, S.dinv + k * dl, dl, dl, 1);
+    }
+  }
+  void gather_rowpanel(int64_t k) {
+    const int64_t nrem = lay.nblk - k - 1;
+    if (nrem <= 0) return;
+    PeerPtrs pp{};
+    for (int s = 0; s < mg->G; ++s) pp.p[s] = mg->rk[s].L;
+    for (int r = 0; r < mg->G; ++r) {
+      MRank& R = mg->rk[r];
+      act(r);
+      dim3 grid((unsigned)nrem, (unsigned)std::min<int64_t>(lay.nb, std::max<int64_t>(4, 2048 / nrem)));
+      gather_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel, pp, mg->G, ld, k, lay.nb);
+      R.be.note(cudaGetLastError());
+      R.ctx->launches++;
+    }
+  }
+  void bcast_colpanel(int64_t k) {
+    const MRank& S = mg->rk[lay.owner(k)];
+    for (int r = 0; r < mg->G; ++r)
+      copy2d(r, mg->rk[r].panel, lay.Np, S.L + (k / lay.G) * lay.nb * ld, ld, (k + 1) * lay.nb, lay.nb);
+  }
+};
+
+// dense state of one distributed factorization
+struct MDense {
+  DistLayout lay;
+  int64_t ld = 0;
+};
+
+void mdense_free(gpr_mgpu* mg) {
+  for (auto& R : mg->rk) {
+    if (!R.ctx) continue;
+    cudaSetDevice(R.ctx->device);
+    cudaStreamSynchronize(R.ctx->stream);
+    cudaFree(R.L); cudaFree(R.dinv); cudaFree(R.Ukk); cudaFree(R.panel); cudaFree(R.gtile);
+    cudaFree(R.x); cudaFree(R.y); cudaFree(R.hp); cudaFree(R.alpha); cudaFree(R.gpart); cudaFree(R.scal);
+    R.L = R.dinv = R.Ukk = R.panel = R.x = R.y = R.hp = R.alpha = R.gpart = R.scal = nullptr;
+    R.gtile = nullptr;
+  }
+}
+
+int mdense_alloc(gpr_mgpu* mg, MDense& md, int64_t Np, int64_t nyp) {
+  DistLayout& lay = md.lay;
+  lay.G = mg->G; lay.nb = mg->nb; lay.Np = Np; lay.nblk = Np / mg->nb; lay.nyp = nyp;
+  md.ld = Np;
+  for (int r = 0; r < mg->G; ++r) {
+    MRank& R = mg->rk[r];
+    MCK(cudaSetDevice(R.ctx->device));
+    const int64_t lc = std::max<int64_t>(lay.lcols(r), 128);
+    MCK(cudaMalloc(&R.L, sizeof(double) * Np * lc));
+    MCK(cudaMalloc(&R.dinv, sizeof(double) * Np * 128));
+    MCK(cudaMalloc(&R.Ukk, sizeof(double) * lay.nb * lay.nb));
+    MCK(cudaMalloc(&R.panel, sizeof(double) * Np * lay.nb));
+    const int64_t lt = std::max<int64_t>(lay.ltiles(r), 1);
+    MCK(cudaMalloc(&R.gtile, sizeof(int) * lt));
+    std::vector<int> gt((size_t)lt, 0);
+    for (int64_t t = 0; t < lay.ltiles(r); ++t) gt[t] = lay.gtile(r, t);
+    MCK(cudaMemcpyAsync(R.gtile, gt.data(), sizeof(int) * lt, cudaMemcpyHostToDevice, R.ctx->stream));
+    MCK(cudaMemsetAsync(R.ctx->d_info, 0, sizeof(long long), R.ctx->stream));
+    MCK(cudaStreamSynchronize(R.ctx->stream));
+  }
+  return GPR_OK;
+}
+
+std::vector<DistRank<CudaBE>> mdense_ranks(gpr_mgpu* mg, const MDense& md) {
+  std::vector<DistRank<CudaBE>> v((size_t)mg->G);
+  for (int r = 0; r < mg->G; ++r) {
+    MRank& R = mg->rk[r];
+    v[r] = DistRank<CudaBE>{r, &R.be, R.L, md.ld, R.dinv, R.Ukk, R.panel, R.gtile};
+  }
+  return v;
+}
+
+int msync_all(gpr_mgpu* mg, const char* where, long long* info) {
+  long long first = 0;
+  for (int r = 0; r < mg->G; ++r) {
+    MRank& R = mg->rk[r];
+    MCK(cudaSetDevice(R.ctx->device));
+    long long h = 0;
+    MCK(cudaMemcpyAsync(&h, R.ctx->d_info, sizeof h, cudaMemcpyDeviceToHost, R.ctx->stream));
+    MCK(cudaStreamSynchronize(R.ctx->stream));
+    if (R.ctx->pending != cudaSuccess) {
+      cudaError_t e = R.ctx->pending; R.ctx->pending = cudaSuccess;
+      char b[256];
+      snprintf(b, sizeof b, "CUDA error %d (%s) in %s on rank %d", (int)e, cudaGetErrorString(e), where, r);
+      return mfail(mg, GPR_ERR_CUDA, b);
+    }
+    if (h && (!first || h < first)) first = h;
+  }
+  if (info) *info = first;
+  return GPR_OK;
+}
+
+}  // namespace
+
+struct gpr_mgpu_model {
+  gpr_mgpu* mg = nullptr;
+  KSpec spec;
+  int ncomp = 0, D = 0, P = 0, nk = 0, ny = 1, train_axis = 1;
+  int64_t N = 0, Np = 0, nyp = 128;
+  MDense md;
+  bool have_inverse = false;
+  double ms[GPR_T_COUNT] = {0};
+};
+
+extern "C" {
+
+int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** out) {
+  gpr_mgpu* mg = nullptr;
+  if (!out || !devices) return mfail(nullptr, GPR_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (nranks < 1 || nranks > MGPU_MAX_RANKS) return mfail(nullptr, GPR_ERR_ARG, "number of ranks must be in 1..16");
+  if (nb < 128 || nb % 128) return mfail(nullptr, GPR_ERR_ARG, "panel width nb must be a positive multiple of 128");
+  mg = new gpr_mgpu();
+  mg->G = nranks; mg->nb = nb;
+  mg->rk.resize(nranks);
+  for (int r = 0; r < nranks; ++r) {
+    int rc = gpr_ctx_create(devices[r], &mg->rk[r].ctx);
+    if (rc) { std::string e = g_create_error; gpr_mgpu_destroy(mg); g_create_error = e; return rc; }
+    mg->rk[r].be = CudaBE{mg->rk[r].ctx};
+    if (cudaEventCreateWithFlags(&mg->rk[r].ev, cudaEventDisableTiming) != cudaSuccess) {
+      gpr_mgpu_destroy(mg);
+      return mfail(nullptr, GPR_ERR_CUDA, "cudaEventCreate failed");
+    }
+  }
+  // peer access between every pair of distinct devices (NVLink / NVSwitch on the 8 x B200 box)
+  for (int a = 0; a < nranks; ++a)
+    for (int b = 0; b < nranks; ++b) {
+      const int da = devices[a], db = devices[b];
+      if (da == db) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, da, db);
+      if (!can) { gpr_mgpu_destroy(mg); return mfail(nullptr, GPR_ERR_UNSUPPORTED, "devices " + std::to_string(da) + " and " + std::to_string(db) + " have no peer access"); }
+      cudaSetDevice(da);
+      cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) { gpr_mgpu_destroy(mg); return mfail(nullptr, GPR_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); }
+    }
+  cudaSetDevice(devices[0]);
+  cudaEventCreate(&mg->t0); cudaEventCreate(&mg->t1);
+  *out = mg;
+  return GPR_OK;
+}
+
+int gpr_mgpu_destroy(gpr_mgpu* mg) {
+  if (!mg) return GPR_OK;
+  mdense_free(mg);
+  for (auto& R : mg->rk) {
+    if (!R.ctx) continue;
+    cudaSetDevice(R.ctx->device);
+    if (R.ev) cudaEventDestroy(R.ev);
+    gpr_ctx_destroy(R.ctx);
+  }
+  if (mg->t0) cudaEventDestroy(mg->t0);
+  if (mg->t1) cudaEventDestroy(mg->t1);
+  delete mg;
+  return GPR_OK;
+}
+
+const char* gpr_mgpu_last_error(gpr_mgpu* mg) { return mg ? mg->err.c_str() : g_create_error.c_str(); }
+
+int64_t gpr_mgpu_launch_count(gpr_mgpu* mg) {
+  int64_t n = 0;
+  if (mg) for (auto& R : mg->rk) n += R.ctx->launches;
+  return n;
+}
+
+int gpr_mgpu_model_create(gpr_mgpu* mg, const int* comp_types, int ncomp, int D, int64_t N, const double* x, const double* y,
+                          int ny, int train_axis, gpr_mgpu_model** out) {
+  if (!mg) return GPR_ERR_ARG;
+  if (!out || !x || !y) return mfail(mg, GPR_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (N < 1) return mfail(mg, GPR_ERR_ARG, "x and y size mismatch.");
+  if (ny < 1 || train_axis < 1 || train_axis > ny) return mfail(mg, GPR_ERR_ARG, "train_axis out of range");
+  if (mg->rk[0].L) return mfail(mg, GPR_ERR_STATE, "this multi-GPU context already holds a model");
+  gpr_mgpu_model* m = new gpr_mgpu_model();
+  m->mg = mg;
+  int rc = make_spec(mg->rk[0].ctx, comp_types, ncomp, D, &m->spec, &m->P, &m->nk);
+  if (rc) { mg->err = mg->rk[0].ctx->err; delete m; return rc; }
+  if (m->P > 90) { delete m; return mfail(mg, GPR_ERR_UNSUPPORTED, "more than 90 hyper-parameters are not supported"); }
+  m->ncomp = ncomp; m->D = D; m->N = N; m->ny = ny; m->train_axis = train_axis;
+  m->Np = round_up(N, mg->nb); m->nyp = round_up(ny, 128);
+  rc = mdense_alloc(mg, m->md, m->Np, m->nyp);
+  if (rc) { mdense_free(mg); delete m; return rc; }
+  for (int r = 0; r < mg->G; ++r) {
+    MRank& R = mg->rk[r];
+    cudaError_t e = cudaSetDevice(R.ctx->device);
+    auto A = [&](double** p, size_t elems) { if (e == cudaSuccess) e = cudaMalloc(p, elems * sizeof(double)); };
+    A(&R.x, (size_t)D * N);
+    A(&R.y, (size_t)N * ny);
+    A(&R.hp, (size_t)m->P);
+    A(&R.alpha, (size_t)m->Np);
+    A(&R.scal, (size_t)(m->P + 3));
+    R.gr_blocks = R.ctx->sm_count * 4;
+    A(&R.gpart, (size_t)R.gr_blocks * (m->P + 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(R.x, x, sizeof(double) * D * N, cudaMemcpyHostToDevice, R.ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(R.y, y, sizeof(double) * N * ny, cudaMemcpyHostToDevice, R.ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(R.ctx->stream);
+    if (e != cudaSuccess) {
+      mdense_free(mg); delete m;
+      return mfail(mg, e == cudaErrorMemoryAllocation ? GPR_ERR_MEMORY : GPR_ERR_CUDA, std::string("model allocation / upload: ") + cudaGetErrorString(e));
+    }
+  }
+  *out = m;
+  return GPR_OK;
+}
+
+int gpr_mgpu_model_destroy(gpr_mgpu_model* m) {
+  if (!m) return GPR_OK;
+  mdense_free(m->mg);
+  delete m;
+  return GPR_OK;
+}
+
+/* loss_grad! / log_loss_grad! (src/cost.jl:50-70) with K block-cyclic over the ranks */
+int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_scale, double eps, double* F, double* G,
+                       int64_t* info) {
+  if (!m) return GPR_ERR_ARG;
+  gpr_mgpu* mg = m->mg;
+  if (!hp_in) return mfail(mg, GPR_ERR_ARG, "hp is NULL");
+  if (P != m->P) return mfail(mg, GPR_ERR_ARG, "Parameter size mismatch.");
+  std::vector<double> hp(hp_in, hp_in + P);
+  if (log_scale) for (auto& v : hp) v = std::exp(v);
+  if (info) *info = 0;
+  const DistLayout& lay = m->md.lay;
+  const int64_t N = m->N, Np = m->Np, nb = lay.nb, ld = m->md.ld;
+  const int Gn = mg->G;
+  for (int i = 0; i < GPR_T_COUNT; ++i) m->ms[i] = 0.0;
+  auto tick = [&]() { cudaSetDevice(mg->rk[0].ctx->device); cudaEventRecord(mg->t0, mg->rk[0].ctx->stream); };
+  auto tock = [&](int slot) -> int {
+    // phase time = rank 0's stream from tick to the point where every rank has finished the phase
+    for (int r = 0; r < Gn; ++r) { cudaSetDevice(mg->rk[r].ctx->device); MCK(cudaStreamSynchronize(mg->rk[r].ctx->stream)); }
+    cudaSetDevice(mg->rk[0].ctx->device);
+    MCK(cudaEventRecord(mg->t1, mg->rk[0].ctx->stream));
+    MCK(cudaEventSynchronize(mg->t1));
+    float t = 0.f; cudaEventElapsedTime(&t, mg->t0, mg->t1);
+    m->ms[slot] += t;
+    return GPR_OK;
+  };
+  cudaEvent_t tot0, tot1;
+  cudaSetDevice(mg->rk[0].ctx->device);
+  cudaEventCreate(&tot0); cudaEventCreate(&tot1);
+  cudaEventRecord(tot0, mg->rk[0].ctx->stream);
+
+  // ---- covariance build into the block-cyclic layout (upper triangle, zero below), y columns
+  tick();
+  for (int r = 0; r < Gn; ++r) {
+    MRank& R = mg->rk[r];
+    gpr_ctx* ctx = R.ctx;
+    MCK(cudaSetDevice(ctx->device));
+    MCK(cudaMemcpyAsync(R.hp, hp.data(), sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
+    MCK(cudaMemsetAsync(ctx->d_info, 0, sizeof(long long), ctx->stream));
+    for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
+      const int64_t J = lb * Gn + r;
+      const int64_t cvalid = std::max<int64_t>(0, std::min<int64_t>(nb, N - J * nb));
+      KBuildArgs a{};
+      a.out = R.L + lb * nb * ld; a.ldo = ld; a.R = N; a.C = cvalid; a.Rp = Np; a.Cp = nb;
+      a.x1 = R.x; a.x2 = R.x + (cvalid > 0 ? J * nb * m->D : 0); a.D = m->D; a.hp = R.hp; a.spec = m->spec;
+      a.eps = eps; a.same = 1; a.add_noise = 1; a.pad_identity = 1; a.sigma_one = 0; a.row_scale = nullptr;
+      a.diag_shift = J * nb; a.zero_lower = 1;
+      int rc = launch_kbuild(ctx, DM_EUCLID, a);
+      if (rc) return mfail(mg, rc, ctx->err);
+    }
+    if (r == lay.y_owner()) {
+      const int64_t total = Np * m->nyp;
+      pad_copy_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 65535), 256, 0, ctx->stream>>>(
+          R.L + lay.ycol0(r) * ld, ld, Np, m->nyp, R.y, N, N, m->ny);
+      ctx->launches++;
+      MCK(cudaGetLastError());
+    }
+  }
+  { int rc = tock(GPR_T_KBUILD); if (rc) return rc; }
+
+  auto ranks = mdense_ranks(mg, m->md);
+  LocalComm comm{mg, lay, ld};
+  DistBlocked<CudaBE, LocalComm> db(lay, ranks, comm);
+
+  // ---- potrf (+ forward substitution of y), log det
+  tick();
+  db.potrf();
+  for (int r = 0; r < Gn; ++r) {
+    MRank& R = mg->rk[r];
+    MCK(cudaSetDevice(R.ctx->device));
+    dist_logdiag_kernel<<<1, 1024, 0, R.ctx->stream>>>(R.L, ld, lay.nloc(r) * nb, nb, Gn, r, R.scal);
+    R.ctx->launches++;
+    MCK(cudaGetLastError());
+  }
+  { int rc = tock(GPR_T_POTRF); if (rc) return rc; }
+  long long h_info = 0;
+  { int rc = msync_all(mg, "potrf", &h_info); if (rc) return rc; }
+  if (info) *info = h_info;
+  m->have_inverse = false;
+  if (h_info != 0) {
+    cudaEventDestroy(tot0); cudaEventDestroy(tot1);
+    char buf[128];
+    snprintf(buf, sizeof buf, "matrix is not positive definite; Cholesky failed at pivot %lld", h_info);
+    return mfail(mg, GPR_ERR_NOT_POSDEF, buf);
+  }
+
+  // ---- trtri (+ back substitution): W = U^-1 in place, y columns = -alpha
+  tick();
+  db.trtri();
+  { int rc = tock(GPR_T_TRTRI); if (rc) return rc; }
+  tick();
+  {
+    const int yo = lay.y_owner();
+    MRank& R = mg->rk[yo];
+    MCK(cudaSetDevice(R.ctx->device));
+    const double* X = R.L + (lay.ycol0(yo) + (m->train_axis - 1)) * ld;
+    dist_alpha_kernel<<<1, 1024, 0, R.ctx->stream>>>(X, R.y + (int64_t)(m->train_axis - 1) * N, N, Np, R.alpha, R.scal);
+    R.ctx->launches++;
+    MCK(cudaGetLastError());
+    comm.barrier();
+    for (int r = 0; r < Gn; ++r)
+      if (r != yo) comm.copy2d(r, mg->rk[r].alpha, Np, R.alpha, Np, Np, 1);
+  }
+  { int rc = tock(GPR_T_POTRS); if (rc) return rc; }
+
+  double Fv = 0.0;
+  {
+    double logdiag = 0.0, ya = 0.0;
+    for (int r = 0; r < Gn; ++r) {
+      MRank& R = mg->rk[r];
+      double sc[2];
+      MCK(cudaSetDevice(R.ctx->device));
+      MCK(cudaMemcpyAsync(sc, R.scal, sizeof sc, cudaMemcpyDeviceToHost, R.ctx->stream));
+      MCK(cudaStreamSynchronize(R.ctx->stream));
+      logdiag += sc[0];
+      if (r == lay.y_owner()) ya = sc[1];
+    }
+    Fv = 0.5 * (ya + 2.0 * logdiag + (double)N * std::log(2.0 * M_PI));   // src/loss_grad.jl:40
+  }
+
+  if (G) {
+    // ---- K^-1 = W W^T in place, then the fused all-hyper-parameter reduction over the local columns
+    tick();
+    db.lauum();
+    { int rc = tock(GPR_T_LAUUM); if (rc) return rc; }
+    m->have_inverse = true;
+    tick();
+    std::vector<double> tot((size_t)P + 1, 0.0), part((size_t)P + 1);
+    for (int r = 0; r < Gn; ++r) {
+      MRank& R = mg->rk[r];
+      gpr_ctx* ctx = R.ctx;
+      MCK(cudaSetDevice(ctx->device));
+      GradArgs a{};
+      a.Kinv = R.L; a.ld = ld; a.alpha = R.alpha; a.x = R.x; a.D = m->D; a.N = N; a.hp = R.hp; a.spec = m->spec; a.P = P;
+      a.eps = eps; a.partial = R.gpart; a.G = Gn; a.rank = r; a.nbt = (int)(nb / GR_TILE); a.lcol_tiles = lay.nloc(r) * (nb / GR_TILE);
+      const size_t smem = ((size_t)(P + 1) * GR_THREADS + 2 * (size_t)m->D * GR_TILE + 2 * GR_TILE) * sizeof(double);
+      grad_reduce_kernel<true><<<R.gr_blocks, GR_THREADS, smem, ctx->stream>>>(a);
+      ctx->launches++;
+      MCK(cudaGetLastError());
+      grad_partial_sum_kernel<<<(P + 1 + 127) / 128, 128, 0, ctx->stream>>>(R.gpart, R.gr_blocks, P, R.scal + 2);
+      ctx->launches++;
+      MCK(cudaGetLastError());
+    }
+    for (int r = 0; r < Gn; ++r) {   // fixed rank order: deterministic
+      MRank& R = mg->rk[r];
+      MCK(cudaSetDevice(R.ctx->device));
+      MCK(cudaMemcpyAsync(part.data(), R.scal + 2, sizeof(double) * (P + 1), cudaMemcpyDeviceToHost, R.ctx->stream));
+      MCK(cudaStreamSynchronize(R.ctx->stream));
+      for (int s = 0; s <= P; ++s) tot[s] += part[s];
+    }
+    // sigma: -acc/|sigma| ; l_d: +l_d * acc ; noise: -sigma_n * acc_diag  (loss_grad.jl:43-52, deriv_covar.jl:23,26,31)
+    for (int c = 0; c < m->spec.ncomp; ++c) {
+      const int off = m->spec.hp_off[c];
+      if (m->spec.type[c] == KT_NOISE) G[off] = -hp[off] * tot[P];
+      else {
+        G[off] = -tot[off] / std::fabs(hp[off]);
+        for (int d = 0; d < m->D; ++d) G[off + 1 + d] = hp[off + 1 + d] * tot[off + 1 + d];
+      }
+    }
+    if (log_scale) for (int p = 0; p < P; ++p) G[p] *= hp[p];   // src/cost.jl:65
+    { int rc = tock(GPR_T_GRAD); if (rc) return rc; }
+  }
+  if (F) *F = Fv;
+  cudaSetDevice(mg->rk[0].ctx->device);
+  cudaEventRecord(tot1, mg->rk[0].ctx->stream);
+  cudaEventSynchronize(tot1);
+  { float t = 0.f; cudaEventElapsedTime(&t, tot0, tot1); m->ms[GPR_T_TOTAL] = t; }
+  cudaEventDestroy(tot0); cudaEventDestroy(tot1);
+  return msync_all(mg, "nlml_grad", nullptr);
+}
+
+int gpr_mgpu_timings(gpr_mgpu_model* m, double* ms, int n) {
+  if (!m || !ms) return GPR_ERR_ARG;
+  for (int i = 0; i < n && i < GPR_T_COUNT; ++i) ms[i] = m->ms[i];
+  return GPR_OK;
+}
+
+/* which: GPR_FETCH_ALPHA (N) or GPR_FETCH_KINV (N x N, full symmetric; needs a preceding gradient evaluation) */
+int gpr_mgpu_fetch(gpr_mgpu_model* m, int which, double* out) {
+  if (!m || !out) return GPR_ERR_ARG;
+  gpr_mgpu* mg = m->mg;
+  const DistLayout& lay = m->md.lay;
+  const int64_t N = m->N, nb = lay.nb, ld = m->md.ld;
+  if (which == GPR_FETCH_ALPHA) {
+    MRank& R = mg->rk[0];
+    MCK(cudaSetDevice(R.ctx->device));
+    MCK(cudaMemcpyAsync(out, R.alpha, sizeof(double) * N, cudaMemcpyDeviceToHost, R.ctx->stream));
+    MCK(cudaStreamSynchronize(R.ctx->stream));
+    return GPR_OK;
+  }
+  if (which != GPR_FETCH_KINV) return mfail(mg, GPR_ERR_ARG, "unknown fetch selector");
+  if (!m->have_inverse) return mfail(mg, GPR_ERR_STATE, "fetch K^-1: cache holds no inverse");
+  for (int r = 0; r < mg->G; ++r) {
+    MRank& R = mg->rk[r];
+    MCK(cudaSetDevice(R.ctx->device));
+    for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
+      const int64_t J = lb * mg->G + r;
+      const int64_t cv = std::max<int64_t>(0, std::min<int64_t>(nb, N - J * nb));
+      if (cv > 0)
+        MCK(cudaMemcpy2DAsync(out + J * nb * N, sizeof(double) * N, R.L + lb * nb * ld, sizeof(double) * ld, sizeof(double) * N, cv,
+                              cudaMemcpyDeviceToHost, R.ctx->stream));
+    }
+    MCK(cudaStreamSynchronize(R.ctx->stream));
+  }
+  for (int64_t j = 0; j < N; ++j)
+    for (int64_t i = j + 1; i < N; ++i) out[i + j * N] = out[j + i * N];
+  return GPR_OK;
+}
+
+/* diagnostics: distributed factorization of a host SPD matrix A (N x N, upper triangle referenced) with right-hand
+ * sides Y (N x ny, may be NULL with ny = 0).  mode 0: potrf (upper(A) <- U, Y <- U^-T Y), 1: + trtri (upper(A) <- U^-1,
+ * Y <- -A^-1 Y), 2: + lauum (upper(A) <- A^-1).  ms[0..2] = phase times. */
+int gpr_mgpu_dbg_factor(gpr_mgpu* mg, double* A, int64_t N, double* Y, int ny, int mode, int64_t* info, double* ms) {
+  if (!mg) return GPR_ERR_ARG;
+  if (!A || N < 1 || (ny > 0 && !Y)) return mfail(mg, GPR_ERR_ARG, "NULL or empty argument");
+  if (mg->rk[0].L) return mfail(mg, GPR_ERR_STATE, "this multi-GPU context already holds a model");
+  const int64_t nb = mg->nb, Np = round_up(N, nb), nyp = ny > 0 ? round_up(ny, 128) : 0;
+  MDense md;
+  int rc = mdense_alloc(mg, md, Np, nyp);
+  if (rc) { mdense_free(mg); return rc; }
+  const DistLayout& lay = md.lay;
+  std::vector<double> col((size_t)Np * nb);
+  auto body = [&]() -> int {
+    for (int r = 0; r < mg->G; ++r) {
+      MRank& R = mg->rk[r];
+      MCK(cudaSetDevice(R.ctx->device));
+      for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
+        const int64_t J = lb * mg->G + r;
+        std::fill(col.begin(), col.end(), 0.0);
+        for (int64_t c = 0; c < nb; ++c) {
+          const int64_t gc = J * nb + c;
+          if (gc < N) for (int64_t i = 0; i <= gc; ++i) col[i + c * Np] = A[i + gc * N];
+          else col[gc + c * Np] = 1.0;
+        }
+        MCK(cudaMemcpyAsync(R.L + lb * nb * md.ld, col.data(), sizeof(double) * Np * nb, cudaMemcpyHostToDevice, R.ctx->stream));
+        MCK(cudaStreamSynchronize(R.ctx->stream));
+      }
+      if (r == lay.y_owner() && nyp > 0) {
+        std::vector<double> yb((size_t)Np * nyp, 0.0);
+        for (int c = 0; c < ny; ++c) memcpy(&yb[(size_t)c * Np], Y + (int64_t)c * N, sizeof(double) * N);
+        MCK(cudaMemcpyAsync(R.L + lay.ycol0(r) * md.ld, yb.data(), sizeof(double) * Np * nyp, cudaMemcpyHostToDevice, R.ctx->stream));
+        MCK(cudaStreamSynchronize(R.ctx->stream));
+      }
+    }
+    auto ranks = mdense_ranks(mg, md);
+    LocalComm comm{mg, lay, md.ld};
+    DistBlocked<CudaBE, LocalComm> db(lay, ranks, comm);
+    double t[3] = {0, 0, 0};
+    for (int ph = 0; ph <= mode && ph < 3; ++ph) {
+      cudaSetDevice(mg->rk[0].ctx->device);
+      cudaEventRecord(mg->t0, mg->rk[0].ctx->stream);
+      if (ph == 0) db.potrf(); else if (ph == 1) db.trtri(); else db.lauum();
+      for (int r = 0; r < mg->G; ++r) { cudaSetDevice(mg->rk[r].ctx->device); MCK(cudaStreamSynchronize(mg->rk[r].ctx->stream)); }
+      cudaSetDevice(mg->rk[0].ctx->device);
+      cudaEventRecord(mg->t1, mg->rk[0].ctx->stream);
+      MCK(cudaEventSynchronize(mg->t1));
+      float f = 0.f; cudaEventElapsedTime(&f, mg->t0, mg->t1);
+      t[ph] = f;
+    }
+    if (ms) { ms[0] = t[0]; ms[1] = t[1]; ms[2] = t[2]; }
+    long long h_info = 0;
+    int rc2 = msync_all(mg, "dbg_factor", &h_info);
+    if (rc2) return rc2;
+    if (info) *info = h_info;
+    for (int r = 0; r < mg->G; ++r) {
+      MRank& R = mg->rk[r];
+      MCK(cudaSetDevice(R.ctx->device));
+      for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
+        const int64_t J = lb * mg->G + r;
+        const int64_t cv = std::max<int64_t>(0, std::min<int64_t>(nb, N - J * nb));
+        if (cv > 0)
+          MCK(cudaMemcpy2DAsync(A + J * nb * N, sizeof(double) * N, R.L + lb * nb * md.ld, sizeof(double) * md.ld, sizeof(double) * N, cv,
+                                cudaMemcpyDeviceToHost, R.ctx->stream));
+      }
+      if (r == lay.y_owner() && ny > 0)
+        MCK(cudaMemcpy2DAsync(Y, sizeof(double) * N, R.L + lay.ycol0(r) * md.ld, sizeof(double) * md.ld, sizeof(double) * N, ny,
+                              cudaMemcpyDeviceToHost, R.ctx->stream));
+      MCK(cudaStreamSynchronize(R.ctx->stream));
+    }
+    return h_info ? GPR_ERR_NOT_POSDEF : GPR_OK;
+  };
+  rc = body();
+  mdense_free(mg);
+  return rc;
+}
+
+}  // extern "C"

@@ -32,6 +32,7 @@ _vp = C.c_void_p
 
 _SIGS = {
     "gpr_version": (C.c_int, []),
+    "gpr_device_count": (C.c_int, []),
     "gpr_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "gpr_ctx_destroy": (C.c_int, [_vp]),
     "gpr_last_error": (C.c_char_p, [_vp]),
@@ -57,6 +58,16 @@ _SIGS = {
     "gpr_dbg_dgemm": (C.c_int, [_vp, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _i64, _dp, _i64,
                                 C.c_double, _dp, _i64, C.c_int, C.c_int, _dp]),
     "gpr_dbg_factor": (C.c_int, [_vp, _dp, _i64, C.c_int, C.POINTER(_i64), _dp]),
+    "gpr_mgpu_create": (C.c_int, [C.c_int, _ip, _i64, C.POINTER(_vp)]),
+    "gpr_mgpu_destroy": (C.c_int, [_vp]),
+    "gpr_mgpu_last_error": (C.c_char_p, [_vp]),
+    "gpr_mgpu_launch_count": (_i64, [_vp]),
+    "gpr_mgpu_model_create": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _i64, _dp, _dp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "gpr_mgpu_model_destroy": (C.c_int, [_vp]),
+    "gpr_mgpu_nlml_grad": (C.c_int, [_vp, _dp, C.c_int, C.c_int, C.c_double, _dp, _dp, C.POINTER(_i64)]),
+    "gpr_mgpu_fetch": (C.c_int, [_vp, C.c_int, _dp]),
+    "gpr_mgpu_timings": (C.c_int, [_vp, _dp, C.c_int]),
+    "gpr_mgpu_dbg_factor": (C.c_int, [_vp, _dp, _i64, _dp, C.c_int, C.c_int, C.POINTER(_i64), _dp]),
 }
 
 
@@ -85,6 +96,11 @@ def lib():
             f.argtypes = args
         _lib = L
     return _lib
+
+
+def device_count():
+    """Number of usable sm_100-class devices (0 when there is none: nothing in this package runs then)."""
+    return int(lib().gpr_device_count())
 
 
 class GPRError(RuntimeError):
@@ -331,3 +347,117 @@ def dbg_factor(ctx, A, mode=0):
     rc = lib().gpr_dbg_factor(ctx.handle, dptr(A), A.shape[0], int(mode), C.byref(info), C.byref(ms))
     ctx.check(rc, info)
     return A, ms.value
+
+
+class MultiContext:
+    """gpr_mgpu: one process driving several ranks (one per entry of `devices`; a device may repeat) for the
+    block-cyclic multi-GPU NLML + gradient (BASELINE.json config 5)."""
+
+    def __init__(self, devices, nb=1024):
+        self.devices = [int(d) for d in devices]
+        self.nb = int(nb)
+        self._h = _vp()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        rc = lib().gpr_mgpu_create(len(self.devices), arr, self.nb, C.byref(self._h))
+        if rc != 0:
+            msg = lib().gpr_mgpu_last_error(None)
+            self._h = None
+            raise GPRError(f"gpr_mgpu_create(devices={self.devices}) failed ({rc}): {msg.decode() if msg else ''}")
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise GPRError("multi-GPU context destroyed")
+        return self._h
+
+    def check(self, rc, info=None):
+        if rc == 0:
+            return
+        if rc == GPR_ERR_NOT_POSDEF:
+            raise PosDefException(int(info.value) if info is not None else -1)
+        msg = lib().gpr_mgpu_last_error(self._h)
+        raise GPRError(f"libgpr_sm100a (multi-GPU) error {rc}: {msg.decode() if msg else ''}")
+
+    def launch_count(self):
+        return int(lib().gpr_mgpu_launch_count(self.handle))
+
+    def dbg_factor(self, A, Y=None, mode=0):
+        A = np.array(A, dtype=np.float64, order="F")
+        Yc = None if Y is None else np.array(Y, dtype=np.float64, order="F").reshape(A.shape[0], -1)
+        info = _i64(0)
+        ms = np.zeros(3)
+        rc = lib().gpr_mgpu_dbg_factor(self.handle, dptr(A), A.shape[0], dptr(Yc), 0 if Yc is None else Yc.shape[1], int(mode),
+                                       C.byref(info), dptr(ms))
+        self.check(rc, info)
+        return A, Yc, ms
+
+    def close(self):
+        if self._h is not None:
+            lib().gpr_mgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiModelHandle:
+    """gpr_mgpu_model: x, y replicated, K / U / K^-1 block-cyclic over the ranks of a MultiContext."""
+
+    def __init__(self, mctx, types, D, x, y, train_axis=1):
+        self.mctx = mctx
+        self.types = list(types)
+        x = f64(x)
+        y2 = f64(y.reshape(y.shape[0], -1))
+        self.D, self.N = int(x.shape[0]), int(x.shape[1])
+        self.ny = int(y2.shape[1])
+        if D != self.D:
+            raise GPRError("x dimension mismatch")
+        if y2.shape[0] != self.N:
+            raise GPRError("x and y size mismatch.")
+        self.P = lib().gpr_dim_hp(types_array(self.types), len(self.types), self.D)
+        self._h = _vp()
+        rc = lib().gpr_mgpu_model_create(mctx.handle, types_array(self.types), len(self.types), self.D, self.N, dptr(x), dptr(y2),
+                                         self.ny, int(train_axis), C.byref(self._h))
+        if rc != 0:
+            self._h = None
+        mctx.check(rc)
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise GPRError("model destroyed")
+        return self._h
+
+    def nlml_grad(self, hp, log_scale=False, eps=1e-8, want_f=True, want_g=True):
+        hp = f64(np.asarray(hp, dtype=np.float64).ravel())
+        F = C.c_double(0.0)
+        G = np.empty(self.P) if want_g else None
+        info = _i64(0)
+        rc = lib().gpr_mgpu_nlml_grad(self.handle, dptr(hp), hp.size, int(bool(log_scale)), float(eps),
+                                      C.byref(F) if want_f else None, dptr(G), C.byref(info))
+        self.mctx.check(rc, info)
+        return (F.value if want_f else None), G
+
+    def fetch(self, which):
+        out = np.empty((self.N, self.N), order="F") if which == FETCH_KINV else np.empty(self.N)
+        self.mctx.check(lib().gpr_mgpu_fetch(self.handle, which, dptr(out)))
+        return out
+
+    def timings(self):
+        ms = np.zeros(T_COUNT)
+        self.mctx.check(lib().gpr_mgpu_timings(self.handle, dptr(ms), T_COUNT))
+        return {n: float(ms[i]) for i, n in enumerate(T_NAMES)}
+
+    def close(self):
+        if self._h is not None:
+            lib().gpr_mgpu_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

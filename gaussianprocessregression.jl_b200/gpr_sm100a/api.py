@@ -294,6 +294,42 @@ class MllGradCache(_DeviceCache):
     want_inverse = True
 
 
+class MultiGPUGradCache:
+    """Gradient cache whose K / U / K^-1 are block-cyclic over several ranks (one per entry of `devices`;
+    default: every visible GPU once): BASELINE.json config 5, SURVEY.md 8e.  Drop-in for MllGradCache in
+    loss_grad! / log_loss_grad! (src/cost.jl:50-70) and therefore in `train`."""
+    want_inverse = True
+
+    def __init__(self, md, devices=None, nb=1024):
+        if devices is None:
+            devices = list(range(max(1, _ffi.device_count())))
+        self.mctx = _ffi.MultiContext(devices, nb=nb)
+        self.hp = np.array(md.params, dtype=np.float64)
+        self._x_ref, self._y_snapshot = md.x, np.array(md.y, copy=True)
+        self.handle = _ffi.MultiModelHandle(self.mctx, _types(md.covar), md.x.shape[0], md.x, md.y, md.train_axis)
+
+    def _sync_data(self, md):
+        if md.x is not self._x_ref or not np.array_equal(md.y, self._y_snapshot):
+            raise GPRError("MultiGPUGradCache: x / y changed; build a new cache")
+
+    @property
+    def α(self):
+        return self.handle.fetch(_ffi.FETCH_ALPHA)
+
+    alpha = α
+
+    @property
+    def K_inv(self):
+        return self.handle.fetch(_ffi.FETCH_KINV)
+
+    def timings(self):
+        return self.handle.timings()
+
+    def close(self):
+        self.handle.close()
+        self.mctx.close()
+
+
 def loss_cache(cost):
     return MllLossCache
 

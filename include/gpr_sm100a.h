@@ -82,6 +82,7 @@ typedef struct gpr_ctx gpr_ctx;
 typedef struct gpr_model gpr_model;
 
 int gpr_version(void);
+int gpr_device_count(void);                        /* usable sm_100-class devices visible to this process */
 
 /* one context per GPU / per thread */
 int gpr_ctx_create(int device, gpr_ctx** ctx);
@@ -157,6 +158,38 @@ int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, d
  * mode 0: potrf (upper = U), 1: potrf + trtri (upper = U^-1), 2: potrf + trtri + in-place lauum (upper = A^-1),
  * 3: potrf + trtri + out-of-place W W^T (upper = A^-1; the path gpr_update_cache takes when memory allows). */
 int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, double* ms);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Multi-GPU NLML + gradient for training sets whose N x N covariance does not fit (or is too slow on) one
+ * device: BASELINE.json config 5 (N = 131072, 137 GB of FP64 K), SURVEY.md 8b ("gpr_ctx_create_multi") / 8e.
+ * Single process, one rank per entry of `devices`; K, its factor and K^-1 are 1-D block-cyclic over the ranks
+ * (block columns of width nb), panels move between devices as peer-memory reads over NVLink.  Same arithmetic
+ * and same results as gpr_nlml_grad (update_cache!(tc::MllGradCache...) + loss + grad!, src/cost.jl:96-127).
+ * A device may be listed more than once (several ranks on one GPU; used by the 1-GPU tests of this path).
+ * One model per multi-GPU context.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct gpr_mgpu gpr_mgpu;
+typedef struct gpr_mgpu_model gpr_mgpu_model;
+
+int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** mg);
+int gpr_mgpu_destroy(gpr_mgpu* mg);
+const char* gpr_mgpu_last_error(gpr_mgpu* mg);     /* mg may be NULL: last error of a failed gpr_mgpu_create */
+int64_t gpr_mgpu_launch_count(gpr_mgpu* mg);
+/* GPRModel(cov, hp, x, y; train_axis): src/models.jl:17-37; x and y are replicated on every rank */
+int gpr_mgpu_model_create(gpr_mgpu* mg, const int* comp_types, int ncomp, int D, int64_t N, const double* x,
+                          const double* y, int ny, int train_axis, gpr_mgpu_model** model);
+int gpr_mgpu_model_destroy(gpr_mgpu_model* model);
+/* loss_grad! / log_loss_grad!: src/cost.jl:50-70 (same contract as gpr_nlml_grad) */
+int gpr_mgpu_nlml_grad(gpr_mgpu_model* model, const double* hp_in, int P, int log_scale, double eps, double* F,
+                       double* G, int64_t* info);
+/* GPR_FETCH_ALPHA (N) or GPR_FETCH_KINV (N x N full symmetric; after an evaluation with G != NULL) */
+int gpr_mgpu_fetch(gpr_mgpu_model* model, int which, double* out);
+int gpr_mgpu_timings(gpr_mgpu_model* model, double* ms, int n);   /* GPR_T_* slots; POTRS = alpha extraction + broadcast */
+/* diagnostics: block-cyclic factorization of a host SPD matrix A (N x N, upper triangle referenced; the strict
+ * lower triangle comes back zero) with right-hand sides Y (N x ny; NULL with ny = 0).
+ * mode 0: potrf (upper(A) <- U, Y <- U^-T Y), 1: + trtri (upper(A) <- U^-1, Y <- -A^-1 Y), 2: + lauum (upper(A) <- A^-1).
+ * ms[0..2]: potrf / trtri / lauum milliseconds. */
+int gpr_mgpu_dbg_factor(gpr_mgpu* mg, double* A, int64_t N, double* Y, int ny, int mode, int64_t* info, double* ms);
 
 #ifdef __cplusplus
 }

@@ -387,3 +387,100 @@ def test_invariants_n16384(gpr):
     Fm = gpr.loss(ll, hp - h * v, md, tc)
     assert (Fp - Fm) / (2 * h) == pytest.approx(float(G @ v), rel=1e-5)
     tc.close()
+
+
+# ------------------------------------------------------------------ (5) block-cyclic multi-GPU path (config 5)
+# The ranks of the multi-device path cycle over the visible GPUs, so on a 1-GPU box the whole distributed code
+# path (tile-mapped GEMMs, panel gathers, event barriers) runs with several ranks on cuda:0.
+def _devices(G):
+    from gpr_sm100a import _ffi
+    nd = max(1, _ffi.device_count())
+    return [r % nd for r in range(G)]
+
+
+@pytest.mark.parametrize("n,nb,G", [(512, 128, 1), (768, 128, 3), (1000, 256, 2), (2048, 512, 4), (1536, 256, 8)])
+def test_mgpu_dense_phases(gpr, n, nb, G):
+    """potrf (+ forward solve), trtri (+ back substitution), lauum of csrc/dist_blocked.hpp against LAPACK."""
+    import scipy.linalg as sl
+    from gpr_sm100a import _ffi
+    rng = np.random.default_rng(n + G)
+    X = rng.standard_normal((n, n))
+    K = X @ X.T / n + np.eye(n)
+    Y0 = rng.standard_normal((n, 3))
+    U = sl.cholesky(K, lower=False)
+    for mode in (0, 1, 2):
+        mc = _ffi.MultiContext(_devices(G), nb=nb)
+        A, Y, _ = mc.dbg_factor(np.triu(K), Y0, mode)
+        mc.close()
+        ref = [U, np.linalg.inv(U), np.linalg.inv(K)][mode]
+        yref = sl.solve_triangular(U, Y0, trans="T") if mode == 0 else -np.linalg.solve(K, Y0)
+        assert np.abs(np.triu(A) - np.triu(ref)).max() <= 1e-11 * np.abs(ref).max(), (mode,)
+        assert np.abs(Y - yref).max() <= 1e-11 * np.abs(yref).max(), (mode,)
+        assert not np.tril(A, -1).any()
+
+
+def test_mgpu_not_positive_definite(gpr):
+    from gpr_sm100a import _ffi
+    K = np.eye(512)
+    K[300, 300] = -2.0
+    mc = _ffi.MultiContext(_devices(2), nb=128)
+    with pytest.raises(gpr.PosDefException) as ei:
+        mc.dbg_factor(K, None, 0)
+    assert ei.value.info == 301
+    mc.close()
+
+
+@pytest.mark.parametrize("cov,N,D,ny,nb,G", [((o.SE, o.NOISE), 300, 5, 1, 128, 2), ((o.SE, o.SE, o.NOISE), 1000, 8, 1, 256, 3),
+                                             ((o.SE, o.NOISE), 257, 3, 4, 128, 4), ((o.SE, o.MATERN52, o.NOISE), 700, 4, 1, 128, 2),
+                                             ((o.SE, o.NOISE), 2000, 16, 1, 256, 8)])
+def test_mgpu_nlml_grad_vs_oracle(gpr, cov, N, D, ny, nb, G):
+    rng = np.random.default_rng(N + D)
+    x = rng.random((D, N))
+    y = np.sin(3 * x).sum(0) + 0.1 * rng.standard_normal(N)
+    if ny > 1:
+        y = np.stack([y * (0.5 + 0.3 * k) for k in range(ny)], axis=1)
+    hp = 0.3 + rng.random(o.dim_hp(cov, D))
+    hp[-1] = 0.1
+    ta = 2 if ny > 1 else 1
+    mdo = o.GPRModel(cov, hp, x, y, train_axis=ta)
+    tco = o.MllGradCache(mdo)
+    Fo, Go = o.loss_grad(hp, mdo, tco)
+    md = gpr.GPRModel(to_gpr_cov(gpr, cov), hp, x, y, train_axis=ta)
+    tc = gpr.MultiGPUGradCache(md, devices=_devices(G), nb=nb)
+    ll = gpr.MarginalLikelihood()
+    Gd = np.empty(len(hp))
+    F = gpr.loss_grad_(ll, True, Gd, hp, md, tc)
+    assert abs(F - Fo) <= TOL_F * abs(Fo)
+    assert grad_err(Gd, Go) <= TOL_G
+    assert np.abs(tc.alpha - tco.alpha).max() <= 1e-8 * np.abs(tco.alpha).max()
+    assert np.abs(tc.K_inv - tco.Kinv).max() <= 1e-8 * np.abs(tco.Kinv).max()
+    Gl = np.empty(len(hp))
+    Fl = gpr.log_loss_grad_(ll, True, Gl, np.log(hp), md, tc)
+    assert abs(Fl - Fo) <= TOL_F * abs(Fo)
+    assert grad_err(Gl, Go * hp) <= TOL_G
+    assert gpr.loss_grad_(ll, True, None, hp, md, tc) == pytest.approx(Fo, rel=TOL_F)      # F only
+    tc.close()
+
+
+def test_mgpu_rank_count_independence_n8192(gpr):
+    """Config 5's invariant at a size the 1-GPU box finishes quickly: F and G do not depend on the number of ranks
+    or the panel width, and agree with the single-GPU path (rtol 1e-9)."""
+    D, N = 16, 8192
+    rng = np.random.default_rng(5005)
+    x = rng.random((D, N))
+    y = np.sin(3 * x).sum(0) + 0.1 * rng.standard_normal(N)
+    hp = np.concatenate([[1.0], 0.4 * np.ones(D), [0.1]])
+    cov = gpr.SquaredExp() + gpr.WhiteNoise()
+    md = gpr.GPRModel(cov, hp, x, y)
+    ll = gpr.MarginalLikelihood()
+    tc1 = gpr.MllGradCache(md)
+    G1 = np.empty(len(hp))
+    F1 = gpr.loss_grad_(ll, True, G1, hp, md, tc1)
+    tc1.close()
+    for G, nb in ((1, 1024), (2, 512), (4, 1024), (8, 256)):
+        tc = gpr.MultiGPUGradCache(md, devices=_devices(G), nb=nb)
+        Gd = np.empty(len(hp))
+        F = gpr.loss_grad_(ll, True, Gd, hp, md, tc)
+        tc.close()
+        assert abs(F - F1) <= 1e-9 * abs(F1), (G, nb)
+        assert grad_err(Gd, G1) <= 1e-9, (G, nb, grad_err(Gd, G1))

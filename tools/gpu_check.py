@@ -388,8 +388,109 @@ def sec_perf():
         mh.close()
 
 
+def _spd(n, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, n))
+    return X @ X.T / n + np.eye(n)
+
+
+def sec_mgpu_factor():
+    """block-cyclic drivers with virtual ranks on the visible device(s): device list cycles over what exists"""
+    import scipy.linalg as sl
+    from gpr_sm100a import _ffi
+    import torch
+    ndev = torch.cuda.device_count()
+    for (n, nb, G) in ((512, 128, 1), (512, 128, 2), (768, 128, 3), (1024, 256, 2), (1000, 256, 3), (1536, 512, 2), (2048, 256, 4), (2048, 512, 8)):
+        K = _spd(n, n + G)
+        rng = np.random.default_rng(n)
+        Y0 = rng.standard_normal((n, 3))
+        U = sl.cholesky(K, lower=False)
+        for mode in (0, 1, 2):
+            mc = _ffi.MultiContext([r % ndev for r in range(G)], nb=nb)
+            A, Y, ms = mc.dbg_factor(np.triu(K), Y0, mode)
+            ref = [U, np.linalg.inv(U), np.linalg.inv(K)][mode]
+            yref = sl.solve_triangular(U, Y0, trans="T") if mode == 0 else -np.linalg.solve(K, Y0)
+            e = relerr(np.triu(A), np.triu(ref))
+            ey = relerr(Y, yref)
+            low = float(np.abs(np.tril(A, -1)).max())
+            ok = e < 1e-11 and ey < 1e-11 and low == 0
+            print(f"mgpu factor n={n} nb={nb} G={G} mode={mode}: relerr {e:.2e} rhs {ey:.2e} lower {low:.1e} launches {mc.launch_count()} ms {np.round(ms, 2).tolist()}", "OK" if ok else "BAD")
+            mc.close()
+
+
+def sec_mgpu_nlml():
+    from gpr_sm100a import _ffi
+    import gpr_oracle as o
+    import torch
+    ndev = torch.cuda.device_count()
+    ctx = _ffi.get_context()
+    for cov, N, D, ny, nb, G in (((o.SE, o.NOISE), 300, 5, 1, 128, 2), ((o.SE, o.SE, o.NOISE), 1000, 8, 1, 256, 3),
+                                 ((o.SE, o.NOISE), 257, 3, 4, 128, 4), ((o.SE, o.MATERN52, o.NOISE), 700, 4, 1, 128, 2),
+                                 ((o.SE, o.SE, o.NOISE), 2048, 8, 1, 512, 4), ((o.SE, o.NOISE), 2000, 16, 1, 256, 1)):
+        x, y = _model(cov, N, D, 11, ny)
+        rng = np.random.default_rng(5)
+        hp = 0.3 + rng.random(o.dim_hp(cov, D))
+        hp[-1] = 0.1
+        ta = 2 if ny > 1 else 1
+        md = o.GPRModel(cov, hp, x, y, train_axis=ta)
+        tc = o.MllGradCache(md)
+        Fo, Go = o.loss_grad(hp, md, tc)
+        types = [TYPES[c] for c in cov]
+        mc = _ffi.MultiContext([r % ndev for r in range(G)], nb=nb)
+        mm = _ffi.MultiModelHandle(mc, types, D, x, y, train_axis=ta)
+        F, Gd = mm.nlml_grad(hp)
+        eF = abs(F - Fo) / abs(Fo)
+        eGi = float((np.abs(Gd - Go) / np.maximum(np.abs(Go), 1e-8 * np.linalg.norm(Go))).max())
+        ea = relerr(mm.fetch(_ffi.FETCH_ALPHA), tc.alpha)
+        eK = relerr(mm.fetch(_ffi.FETCH_KINV), tc.Kinv)
+        Fl, Gl = mm.nlml_grad(np.log(hp), log_scale=True)
+        eL = float(np.abs(Gl - Go * hp).max() / np.abs(Go * hp).max())
+        # against the single-GPU path of the same library
+        mh = _ffi.ModelHandle(ctx, types, D, x, y, train_axis=ta)
+        F1, G1 = mh.nlml_grad(hp)
+        e1 = max(abs(F - F1) / abs(F1), float(np.abs(Gd - G1).max() / np.abs(G1).max()))
+        mh.close()
+        ok = eF < 1e-8 and eGi < 1e-8 and ea < 1e-8 and eK < 1e-8 and eL < 1e-8
+        print(f"mgpu nlml {cov} N={N} D={D} ny={ny} nb={nb} G={G}: relF {eF:.1e} relG(comp) {eGi:.1e} alpha {ea:.1e} Kinv {eK:.1e} logG {eL:.1e} vs1gpu {e1:.1e}", "OK" if ok else "BAD")
+        mm.close(); mc.close()
+
+
+def sec_mgpu_perf():
+    """timing of the block-cyclic path (ranks cycle over the visible devices)"""
+    from gpr_sm100a import _ffi
+    import torch
+    ndev = torch.cuda.device_count()
+    N, D = int(os.environ.get("MGPU_N", "16384")), 8
+    rng = np.random.default_rng(3003)
+    x = rng.random((D, N))
+    y = np.sin(3 * x).sum(0) + 0.1 * rng.standard_normal(N)
+    hp = np.concatenate([[1.0], 0.5 * np.ones(D), [0.1]])
+    ctx = _ffi.get_context()
+    mh = _ffi.ModelHandle(ctx, [1, 2], D, x, y)
+    mh.nlml_grad(hp)
+    F1, G1 = mh.nlml_grad(hp * 1.01)
+    t1 = mh.timings()
+    print(f"1gpu recursive N={N}:", {k: round(v, 1) for k, v in t1.items() if v > 0})
+    mh.close()
+    for G in sorted(set([1, ndev, 2 * ndev])):
+        for nb in (512, 1024):
+            mc = _ffi.MultiContext([r % ndev for r in range(G)], nb=nb)
+            mm = _ffi.MultiModelHandle(mc, [1, 2], D, x, y)
+            mm.nlml_grad(hp)
+            t0 = time.perf_counter()
+            F, Gd = mm.nlml_grad(hp * 1.01)
+            dt = time.perf_counter() - t0
+            tm = mm.timings()
+            e = max(abs(F - F1) / abs(F1), float(np.abs(Gd - G1).max() / np.abs(G1).max()))
+            dense = tm["potrf"] + tm["trtri"] + tm["lauum"]
+            print(f"mgpu N={N} G={G} (devices {ndev}) nb={nb}: wall {dt*1e3:.1f} ms, dense {dense:.1f} ms = {N**3 / dense / 1e9:.2f} TFLOP/s aggregate, vs 1gpu {e:.1e}",
+                  {k: round(v, 1) for k, v in tm.items() if v > 0})
+            mm.close(); mc.close()
+
+
 SECTIONS = {"gemm_cfgs": sec_gemm_cfgs, "gemm": sec_gemm, "factor": sec_factor, "kernel": sec_kernel, "nlml": sec_nlml, "predict": sec_predict,
-            "split": sec_split, "gemm_perf": sec_gemm_perf, "factor_perf": sec_factor_perf, "perf": sec_perf}
+            "split": sec_split, "gemm_perf": sec_gemm_perf, "factor_perf": sec_factor_perf, "perf": sec_perf,
+            "mgpu_factor": sec_mgpu_factor, "mgpu_nlml": sec_mgpu_nlml, "mgpu_perf": sec_mgpu_perf}
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--one":
