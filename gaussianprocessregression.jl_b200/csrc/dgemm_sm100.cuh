@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
   constexpr int LDA_S = GemmTile<A_KC, GEMM_BM>::LD;
   constexpr int LDB_S = GemmTile<B_KC, BN>::LD;
 
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  // KUPTO: the contraction length grows with the column tile -> issue the longest tiles first (shorter tail)
+  const int tile_m = blockIdx.x, tile_n = (p.flags & GEMM_MAP_KUPTO) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int blk_n = (tile_n * BN) >> 7;   // 128-block column of this tile (tile_m is already a 128-block row)
   if ((p.flags & GEMM_UPPER_ONLY) && tile_m > blk_n) return;
   int gt = 0;   // global tile column (mapped forms)
