@@ -38,14 +38,25 @@
 //                              gt(n) = map.col_gtile[n / 128]  (global 128-tile column of local tile n/128)
 //               BLK_MAP_KUPTO  column tile contracts over k < (gt(n) - map.k_gtile0 + 1) * 128 only
 //               BLK_MAP_BROWS  (tB = 'T') rows of B for column tile n/128 start at gt(n) * 128 instead of n
-//   COMM (collective: called once per step, acts on every local rank):
-//     comm.bcast_diag(k, with_owner)   Ukk (nb x nb, ld nb) and dinv blocks k*tpb.. <- owner's diagonal block k
-//     comm.gather_rowpanel(k)          panel[p + ((J-k-1)*nb + c)*nb] <- U(k*nb + p, J*nb + c), J = k+1 .. nblk-1
-//     comm.bcast_colpanel(k)           panel[i + c*Np] <- L_owner(i, block k col c), i < (k+1)*nb
-//     comm.barrier()                   every rank's queued work is ordered before every rank's later work
+//     be.activate()          select the rank's device
+//     be.fork() / be.join()  side queue waits for everything queued on the main queue so far / vice versa
+//     be.side(on)            route the following launches (and the rank's part of collectives) to the side queue
+//   COMM (collective: called once per step, acts on every local rank, on the rank's CURRENT queue; b = 0/1
+//   selects one of the two panel / Ukk buffers):
+//     comm.bcast_diag(k, with_owner, b)   Ukk[b] (nb x nb, ld nb) and dinv blocks k*tpb.. <- owner's diagonal block k
+//     comm.gather_rowpanel(k, b)          panel[b][p + ((J-k-1)*nb + c)*nb] <- U(k*nb + p, J*nb + c), J = k+1 .. nblk-1
+//     comm.bcast_colpanel(k, b)           panel[b][i + c*Np] <- L_owner(i, block k col c), i < (k+1)*nb
+//     comm.barrier()                      every rank's main-queue work so far is ordered before every rank's later
+//                                         main-queue work
 //   The collectives themselves do not synchronise: the drivers place a barrier between producing a block on
-//   one rank and reading it from another, and between the last remote read of a block and overwriting it
-//   (a stream-ordered transport such as NCCL makes barrier() a no-op).  be.activate() selects the rank's device.
+//   one rank and reading it from another, and between the last remote read of a block and overwriting it.
+//
+// Overlap.  potrf looks one block ahead: right after the owner of block k+1 has updated that block column in
+// step k it factors the diagonal block on its side queue while the main queue finishes the trailing update, so
+// the only serial work per step is the row-panel solve and its gather.  trtri and lauum read data that is
+// already final (U, resp. W), so the copies for step k -+ 1 are issued on the side queue during step k (two
+// panel buffers) and never wait for arithmetic; the barrier of step k only orders "every rank holds its copy"
+// before "the source is overwritten".
 #pragma once
 #include <stdint.h>
 
@@ -91,8 +102,8 @@ struct DistRank {
   double* L = nullptr;       // Np x lcols(r), ld
   int64_t ld = 0;
   double* dinv = nullptr;    // Np/128 leaves, global leaf index (every rank holds all leaves it ever needs)
-  double* Ukk = nullptr;     // nb x nb
-  double* panel = nullptr;   // Np * nb doubles: row panel (nb x Np) or column panel (Np x nb)
+  double* Ukk[2] = {nullptr, nullptr};     // nb x nb each
+  double* panel[2] = {nullptr, nullptr};   // Np * nb doubles each: row panel (nb x Np) or column panel (Np x nb)
   const int* gtile = nullptr;   // ltiles(r) entries, readable by BE
 };
 
@@ -104,44 +115,73 @@ struct DistBlocked {
 
   DistBlocked(const DistLayout& l, std::vector<DistRank<BE>>& rk, COMM& c) : lay(l), ranks(rk), comm(c) {}
 
+  void all_join() { for (auto& R : ranks) { R.be->activate(); R.be->join(); } }
+  void all_side(bool on) {
+    for (auto& R : ranks) {
+      R.be->activate();
+      if (on) R.be->fork();
+      R.be->side(on);
+    }
+  }
+
   // L(upper) <- U, y columns <- U^-T y
   void potrf() {
     const int64_t nb = lay.nb, Np = lay.Np;
     const int tpb = lay.tpb();
+    for (auto& R : ranks)
+      if (R.r == lay.owner(0)) {
+        R.be->activate();
+        Blocked<BE> blk(*R.be, R.dinv);
+        blk.potrf_panel(R.L, R.ld, nb, 0, 0);
+      }
     for (int64_t k = 0; k < lay.nblk; ++k) {
       const int o = lay.owner(k);
-      for (auto& R : ranks) {
-        if (R.r != o) continue;
-        R.be->activate();
-        const int64_t kb = k / lay.G;
-        Blocked<BE> blk(*R.be, R.dinv);
-        blk.potrf_panel(R.L + k * nb + kb * nb * R.ld, R.ld, nb, lay.lcols(o) - (kb + 1) * nb, k * tpb);
-      }
+      // diagonal block k was factored on its owner's side queue during step k-1 (main queue for k = 0)
+      for (auto& R : ranks)
+        if (R.r == o) { R.be->activate(); R.be->join(); }
       if (lay.G > 1) {
         comm.barrier();
-        comm.bcast_diag(k, false);
+        comm.bcast_diag(k, false, 0);
       }
       for (auto& R : ranks) {
-        if (R.r == o) continue;
         const int64_t c0 = lay.count_le(R.r, k) * nb, m = lay.lcols(R.r) - c0;
         if (m <= 0) continue;
         R.be->activate();
         Blocked<BE> blk(*R.be, R.dinv);
-        blk.trsm_LUT(R.Ukk, nb, nb, k * tpb, R.L + k * nb + c0 * R.ld, R.ld, m, 1.0);
+        if (R.r == o) blk.trsm_LUT(R.L + k * nb + (c0 - nb) * R.ld, R.ld, nb, k * tpb, R.L + k * nb + c0 * R.ld, R.ld, m, 1.0);
+        else blk.trsm_LUT(R.Ukk[0], nb, nb, k * tpb, R.L + k * nb + c0 * R.ld, R.ld, m, 1.0);
       }
       const int64_t Mrows = Np - (k + 1) * nb;
       if (Mrows <= 0) break;   // last block row: nothing below it
       comm.barrier();
-      comm.gather_rowpanel(k);
+      comm.gather_rowpanel(k, 0);
+      const int o2 = lay.owner(k + 1);
       for (auto& R : ranks) {
         const int64_t c0 = lay.count_le(R.r, k) * nb, m = lay.lcols(R.r) - c0;
         if (m <= 0) continue;
         R.be->activate();
+        const double* rowp = R.L + k * nb + c0 * R.ld;
+        double* C = R.L + (k + 1) * nb + c0 * R.ld;
         TileMap map{R.gtile + c0 / LEAF, (int)((k + 1) * tpb), 0};
-        R.be->gemm_map('T', 'N', Mrows, m, nb, -1.0, R.panel, nb, R.L + k * nb + c0 * R.ld, R.ld, 1.0,
-                       R.L + (k + 1) * nb + c0 * R.ld, R.ld, BLK_MAP_UPPER, map);
+        if (R.r == o2) {
+          // block column k+1 first, then its diagonal block is factored while the rest of the update runs
+          R.be->gemm_map('T', 'N', Mrows, nb, nb, -1.0, R.panel[0], nb, rowp, R.ld, 1.0, C, R.ld, BLK_MAP_UPPER, map);
+          R.be->fork();
+          R.be->side(true);
+          Blocked<BE> blk(*R.be, R.dinv);
+          blk.potrf_panel(C, R.ld, nb, 0, (k + 1) * tpb);
+          R.be->side(false);
+          if (m > nb) {
+            TileMap map2{R.gtile + (c0 + nb) / LEAF, (int)((k + 1) * tpb), 0};
+            R.be->gemm_map('T', 'N', Mrows, m - nb, nb, -1.0, R.panel[0], nb, rowp + nb * R.ld, R.ld, 1.0, C + nb * R.ld, R.ld,
+                           BLK_MAP_UPPER, map2);
+          }
+        } else {
+          R.be->gemm_map('T', 'N', Mrows, m, nb, -1.0, R.panel[0], nb, rowp, R.ld, 1.0, C, R.ld, BLK_MAP_UPPER, map);
+        }
       }
     }
+    all_join();
   }
 
   // L(upper) <- W = U^-1 (diagonal 128-blocks with explicit zeros below the diagonal), y columns <- -U^-1 (y columns)
@@ -149,12 +189,25 @@ struct DistBlocked {
     const int64_t nb = lay.nb, Np = lay.Np;
     const int tpb = lay.tpb();
     comm.barrier();
+    comm.bcast_diag(lay.nblk - 1, true, (int)((lay.nblk - 1) & 1));   // copies for the first step (no row panel: nothing right of it)
     for (int64_t k = lay.nblk - 1; k >= 0; --k) {
       const int o = lay.owner(k);
+      const int b = (int)(k & 1);
       const int64_t Krem = Np - (k + 1) * nb;
-      comm.bcast_diag(k, true);
-      if (Krem > 0) comm.gather_rowpanel(k);
-      comm.barrier();   // every rank holds its copies before row panel k / the diagonal block are overwritten
+      all_join();       // the copies for step k (side queue of step k+1)
+      comm.barrier();   // every rank holds its copies: row panel k and diagonal block k may be overwritten
+      all_side(true);
+      if (k > 0) {      // copies for step k-1: U is final there, so they only wait for the buffers
+        comm.bcast_diag(k - 1, true, b ^ 1);
+        comm.gather_rowpanel(k - 1, b ^ 1);
+      }
+      for (auto& R : ranks)
+        if (R.r == o) {
+          R.be->activate();
+          Blocked<BE> blk(*R.be, R.dinv);
+          blk.trtri(R.L + k * nb + (k / lay.G) * nb * R.ld, R.ld, nb, k * tpb, true);
+        }
+      all_side(false);
       for (auto& R : ranks) {
         const int64_t c0 = lay.count_le(R.r, k) * nb;
         const int64_t mreg = lay.nloc(R.r) * nb - c0, m = lay.lcols(R.r) - c0;
@@ -163,30 +216,34 @@ struct DistBlocked {
         const double* below = R.L + (k + 1) * nb + c0 * R.ld;
         if (Krem > 0 && mreg > 0) {
           TileMap map{R.gtile + c0 / LEAF, 0, (int)((k + 1) * tpb)};
-          R.be->gemm_map('N', 'N', nb, mreg, Krem, 1.0, R.panel, nb, below, R.ld, 0.0, rowp, R.ld, BLK_MAP_KUPTO, map);
+          R.be->gemm_map('N', 'N', nb, mreg, Krem, 1.0, R.panel[b], nb, below, R.ld, 0.0, rowp, R.ld, BLK_MAP_KUPTO, map);
         }
         if (Krem > 0 && m > mreg)
-          R.be->gemm('N', 'N', nb, m - mreg, Krem, 1.0, R.panel, nb, below + mreg * R.ld, R.ld, 1.0, rowp + mreg * R.ld, R.ld, 0, 1, 0, 0, 0);
+          R.be->gemm('N', 'N', nb, m - mreg, Krem, 1.0, R.panel[b], nb, below + mreg * R.ld, R.ld, 1.0, rowp + mreg * R.ld, R.ld, 0, 1, 0, 0, 0);
         if (m > 0) {
           Blocked<BE> blk(*R.be, R.dinv);
-          blk.trsm_LUN(R.Ukk, nb, nb, k * tpb, rowp, R.ld, m, -1.0);
-        }
-        if (R.r == o) {
-          Blocked<BE> blk(*R.be, R.dinv);
-          blk.trtri(R.L + k * nb + (k / lay.G) * nb * R.ld, R.ld, nb, k * tpb, true);
+          blk.trsm_LUN(R.Ukk[b], nb, nb, k * tpb, rowp, R.ld, m, -1.0);
         }
       }
     }
+    all_join();
   }
 
   // L(upper) <- W W^T (matrix columns only)
   void lauum() {
     const int64_t nb = lay.nb, Np = lay.Np;
     comm.barrier();
+    comm.bcast_colpanel(0, 0);
     for (int64_t k = 0; k < lay.nblk; ++k) {
       const int o = lay.owner(k);
-      comm.bcast_colpanel(k);
-      comm.barrier();   // the owner overwrites block column k below
+      const int b = (int)(k & 1);
+      all_join();       // column panel k (side queue of step k-1)
+      comm.barrier();   // every rank holds it: the owner may overwrite block column k
+      if (k + 1 < lay.nblk) {
+        all_side(true);
+        comm.bcast_colpanel(k + 1, b ^ 1);   // W is final: only waits for the buffer
+        all_side(false);
+      }
       for (auto& R : ranks) {
         const int64_t cnt = lay.count_le(R.r, k);
         const int64_t nacc = (R.r == o) ? cnt - 1 : cnt;
@@ -194,16 +251,17 @@ struct DistBlocked {
         R.be->activate();
         if (nacc > 0) {
           TileMap map{R.gtile, 0, 0};
-          R.be->gemm_map('N', 'T', Mrows, nacc * nb, nb, 1.0, R.panel, Np, R.panel, Np, 1.0, R.L, R.ld,
+          R.be->gemm_map('N', 'T', Mrows, nacc * nb, nb, 1.0, R.panel[b], Np, R.panel[b], Np, 1.0, R.L, R.ld,
                          BLK_MAP_UPPER | BLK_MAP_BROWS, map);
         }
         if (R.r == o) {
           TileMap map{R.gtile + (cnt - 1) * lay.tpb(), 0, 0};
-          R.be->gemm_map('N', 'T', Mrows, nb, nb, 1.0, R.panel, Np, R.panel, Np, 0.0, R.L + (cnt - 1) * nb * R.ld, R.ld,
+          R.be->gemm_map('N', 'T', Mrows, nb, nb, 1.0, R.panel[b], Np, R.panel[b], Np, 0.0, R.L + (cnt - 1) * nb * R.ld, R.ld,
                          BLK_MAP_UPPER | BLK_MAP_BROWS, map);
         }
       }
     }
+    all_join();
   }
 };
 

@@ -45,6 +45,10 @@ struct gpr_ctx {
   long long launches = 0;
   long long* d_info = nullptr;
   cudaError_t pending = cudaSuccess;   // first launch error seen by the backend
+  // second queue of the multi-GPU drivers (look-ahead / prefetch, csrc/dist_blocked.hpp); `stream` is the queue
+  // launches currently go to and equals main_stream outside those drivers
+  cudaStream_t main_stream = nullptr, side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -80,6 +84,9 @@ struct CudaBE {
     }
   }
   void activate() { note(cudaSetDevice(ctx->device)); }
+  void fork() { note(cudaEventRecord(ctx->ev_fork, ctx->main_stream)); note(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0)); }
+  void join() { note(cudaEventRecord(ctx->ev_join, ctx->side_stream)); note(cudaStreamWaitEvent(ctx->main_stream, ctx->ev_join, 0)); }
+  void side(bool on) { ctx->stream = on ? ctx->side_stream : ctx->main_stream; }
   // tile-mapped GEMM of the block-cyclic multi-GPU drivers (csrc/dist_blocked.hpp)
   void gemm_map(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, const TileMap& map) {
@@ -420,7 +427,11 @@ int gpr_ctx_create(int device, gpr_ctx** out) {
 int gpr_ctx_destroy(gpr_ctx* ctx) {
   if (!ctx) return GPR_OK;
   cudaSetDevice(ctx->device);
+  if (ctx->main_stream) ctx->stream = ctx->main_stream;
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   cudaFree(ctx->d_info);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -83,7 +83,7 @@ __global__ void grad_partial_sum_kernel(const double* __restrict__ partial, int 
 struct MRank {
   gpr_ctx* ctx = nullptr;
   CudaBE be{nullptr};
-  double *L = nullptr, *dinv = nullptr, *Ukk = nullptr, *panel = nullptr;
+  double *L = nullptr, *dinv = nullptr, *Ukk[2] = {nullptr, nullptr}, *panel[2] = {nullptr, nullptr};
   int* gtile = nullptr;
   // model part
   double *x = nullptr, *y = nullptr, *hp = nullptr, *alpha = nullptr, *gpart = nullptr, *scal = nullptr;   // scal: [logdiag, y.alpha, tot[P+1]...]
@@ -140,18 +140,18 @@ struct LocalComm {
     R.be.note(cudaGetLastError());
     R.ctx->launches++;
   }
-  void bcast_diag(int64_t k, bool with_owner) {
+  void bcast_diag(int64_t k, bool with_owner, int b) {
     const int o = lay.owner(k);
     const int64_t nb = lay.nb, kb = k / lay.G;
     const MRank& S = mg->rk[o];
     const int64_t dl = (int64_t)lay.tpb() * 128 * 128;
     for (int r = 0; r < mg->G; ++r) {
       if (r == o && !with_owner) continue;
-      copy2d(r, mg->rk[r].Ukk, nb, S.L + k * nb + kb * nb * ld, ld, nb, nb);
+      copy2d(r, mg->rk[r].Ukk[b], nb, S.L + k * nb + kb * nb * ld, ld, nb, nb);
       if (r != o) copy2d(r, mg->rk[r].dinv + k * dl, dl, S.dinv + k * dl, dl, dl, 1);
     }
   }
-  void gather_rowpanel(int64_t k) {
+  void gather_rowpanel(int64_t k, int b) {
     const int64_t nrem = lay.nblk - k - 1;
     if (nrem <= 0) return;
     PeerPtrs pp{};
@@ -160,15 +160,15 @@ struct LocalComm {
       MRank& R = mg->rk[r];
       act(r);
       dim3 grid((unsigned)nrem, (unsigned)std::min<int64_t>(lay.nb, std::max<int64_t>(4, 2048 / nrem)));
-      gather_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel, pp, mg->G, ld, k, lay.nb);
+      gather_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], pp, mg->G, ld, k, lay.nb);
       R.be.note(cudaGetLastError());
       R.ctx->launches++;
     }
   }
-  void bcast_colpanel(int64_t k) {
+  void bcast_colpanel(int64_t k, int b) {
     const MRank& S = mg->rk[lay.owner(k)];
     for (int r = 0; r < mg->G; ++r)
-      copy2d(r, mg->rk[r].panel, lay.Np, S.L + (k / lay.G) * lay.nb * ld, ld, (k + 1) * lay.nb, lay.nb);
+      copy2d(r, mg->rk[r].panel[b], lay.Np, S.L + (k / lay.G) * lay.nb * ld, ld, (k + 1) * lay.nb, lay.nb);
   }
 };
 
@@ -183,9 +183,10 @@ void mdense_free(gpr_mgpu* mg) {
     if (!R.ctx) continue;
     cudaSetDevice(R.ctx->device);
     cudaStreamSynchronize(R.ctx->stream);
-    cudaFree(R.L); cudaFree(R.dinv); cudaFree(R.Ukk); cudaFree(R.panel); cudaFree(R.gtile);
+    cudaFree(R.L); cudaFree(R.dinv); cudaFree(R.gtile);
+    for (int b = 0; b < 2; ++b) { cudaFree(R.Ukk[b]); cudaFree(R.panel[b]); R.Ukk[b] = R.panel[b] = nullptr; }
     cudaFree(R.x); cudaFree(R.y); cudaFree(R.hp); cudaFree(R.alpha); cudaFree(R.gpart); cudaFree(R.scal);
-    R.L = R.dinv = R.Ukk = R.panel = R.x = R.y = R.hp = R.alpha = R.gpart = R.scal = nullptr;
+    R.L = R.dinv = R.x = R.y = R.hp = R.alpha = R.gpart = R.scal = nullptr;
     R.gtile = nullptr;
   }
 }
@@ -200,8 +201,10 @@ int mdense_alloc(gpr_mgpu* mg, MDense& md, int64_t Np, int64_t nyp) {
     const int64_t lc = std::max<int64_t>(lay.lcols(r), 128);
     MCK(cudaMalloc(&R.L, sizeof(double) * Np * lc));
     MCK(cudaMalloc(&R.dinv, sizeof(double) * Np * 128));
-    MCK(cudaMalloc(&R.Ukk, sizeof(double) * lay.nb * lay.nb));
-    MCK(cudaMalloc(&R.panel, sizeof(double) * Np * lay.nb));
+    for (int b = 0; b < 2; ++b) {
+      MCK(cudaMalloc(&R.Ukk[b], sizeof(double) * lay.nb * lay.nb));
+      MCK(cudaMalloc(&R.panel[b], sizeof(double) * Np * lay.nb));
+    }
     const int64_t lt = std::max<int64_t>(lay.ltiles(r), 1);
     MCK(cudaMalloc(&R.gtile, sizeof(int) * lt));
     std::vector<int> gt((size_t)lt, 0);
@@ -217,7 +220,7 @@ std::vector<DistRank<CudaBE>> mdense_ranks(gpr_mgpu* mg, const MDense& md) {
   std::vector<DistRank<CudaBE>> v((size_t)mg->G);
   for (int r = 0; r < mg->G; ++r) {
     MRank& R = mg->rk[r];
-    v[r] = DistRank<CudaBE>{r, &R.be, R.L, md.ld, R.dinv, R.Ukk, R.panel, R.gtile};
+    v[r] = DistRank<CudaBE>{r, &R.be, R.L, md.ld, R.dinv, {R.Ukk[0], R.Ukk[1]}, {R.panel[0], R.panel[1]}, R.gtile};
   }
   return v;
 }
@@ -269,6 +272,14 @@ int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** out) 
     int rc = gpr_ctx_create(devices[r], &mg->rk[r].ctx);
     if (rc) { std::string e = g_create_error; gpr_mgpu_destroy(mg); g_create_error = e; return rc; }
     mg->rk[r].be = CudaBE{mg->rk[r].ctx};
+    {
+      gpr_ctx* c = mg->rk[r].ctx;   // gpr_ctx_create left the device current
+      c->main_stream = c->stream;
+      cudaError_t e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+      if (e != cudaSuccess) { gpr_mgpu_destroy(mg); return mfail(nullptr, GPR_ERR_CUDA, std::string("side queue: ") + cudaGetErrorString(e)); }
+    }
     if (cudaEventCreateWithFlags(&mg->rk[r].ev, cudaEventDisableTiming) != cudaSuccess) {
       gpr_mgpu_destroy(mg);
       return mfail(nullptr, GPR_ERR_CUDA, "cudaEventCreate failed");

@@ -18,6 +18,9 @@ struct CpuBE {
   long long info = 0;
   long long gemm_calls = 0;
   void activate() {}
+  void fork() {}
+  void join() {}
+  void side(bool) {}
   // tile-mapped GEMM of csrc/dist_blocked.hpp (same predicate the CUDA kernel evaluates per 128-tile)
   void gemm_map(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, const gpr::TileMap& map) {
@@ -134,34 +137,34 @@ struct CpuComm {
   std::vector<gpr::DistRank<CpuBE>>* ranks = nullptr;
   long long barriers = 0;
   void barrier() { barriers++; }
-  void bcast_diag(int64_t k, bool with_owner) {
+  void bcast_diag(int64_t k, bool with_owner, int b) {
     const int o = lay.owner(k);
     const int64_t nb = lay.nb, kb = k / lay.G;
     const auto& S = (*ranks)[o];
     for (auto& R : *ranks) {
       if (R.r == o && !with_owner) continue;
       for (int64_t c = 0; c < nb; ++c)
-        for (int64_t p = 0; p < nb; ++p) R.Ukk[p + c * nb] = S.L[k * nb + p + (kb * nb + c) * S.ld];
+        for (int64_t p = 0; p < nb; ++p) R.Ukk[b][p + c * nb] = S.L[k * nb + p + (kb * nb + c) * S.ld];
       if (R.r != o)
         memcpy(R.dinv + k * lay.tpb() * 128 * 128, S.dinv + k * lay.tpb() * 128 * 128, sizeof(double) * lay.tpb() * 128 * 128);
     }
   }
-  void gather_rowpanel(int64_t k) {
+  void gather_rowpanel(int64_t k, int b) {
     const int64_t nb = lay.nb;
     for (auto& R : *ranks)
       for (int64_t J = k + 1; J < lay.nblk; ++J) {
         const auto& S = (*ranks)[lay.owner(J)];
         for (int64_t c = 0; c < nb; ++c)
           for (int64_t p = 0; p < nb; ++p)
-            R.panel[p + ((J - k - 1) * nb + c) * nb] = S.L[k * nb + p + ((J / lay.G) * nb + c) * S.ld];
+            R.panel[b][p + ((J - k - 1) * nb + c) * nb] = S.L[k * nb + p + ((J / lay.G) * nb + c) * S.ld];
       }
   }
-  void bcast_colpanel(int64_t k) {
+  void bcast_colpanel(int64_t k, int b) {
     const int64_t nb = lay.nb;
     const auto& S = (*ranks)[lay.owner(k)];
     for (auto& R : *ranks)
       for (int64_t c = 0; c < nb; ++c)
-        for (int64_t i = 0; i < (k + 1) * nb; ++i) R.panel[i + c * lay.Np] = S.L[i + ((k / lay.G) * nb + c) * S.ld];
+        for (int64_t i = 0; i < (k + 1) * nb; ++i) R.panel[b][i + c * lay.Np] = S.L[i + ((k / lay.G) * nb + c) * S.ld];
   }
 };
 
@@ -177,13 +180,15 @@ long long hl_dist_factor(double* A, int64_t n, int64_t nb, int G, double* Y, int
   lay.G = G; lay.Np = n; lay.nb = nb; lay.nblk = n / nb; lay.nyp = nyp;
   std::vector<CpuBE> bes(G);
   std::vector<gpr::DistRank<CpuBE>> ranks(G);
-  std::vector<std::vector<double>> Ls(G), dinvs(G), Ukks(G), panels(G);
+  std::vector<std::vector<double>> Ls(G), dinvs(G), Ukks(2 * G), panels(2 * G);
   std::vector<std::vector<int>> gts(G);
   for (int r = 0; r < G; ++r) {
     Ls[r].assign((size_t)n * std::max<int64_t>(lay.lcols(r), 1), 0.0);
     dinvs[r].assign((size_t)n * 128, 0.0);
-    Ukks[r].assign((size_t)nb * nb, 0.0);
-    panels[r].assign((size_t)n * nb, 0.0);
+    for (int b = 0; b < 2; ++b) {
+      Ukks[2 * r + b].assign((size_t)nb * nb, 0.0);
+      panels[2 * r + b].assign((size_t)n * nb, 0.0);
+    }
     gts[r].resize(std::max<int64_t>(lay.ltiles(r), 1));
     for (int64_t t = 0; t < lay.ltiles(r); ++t) gts[r][t] = lay.gtile(r, t);
     for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
@@ -193,7 +198,8 @@ long long hl_dist_factor(double* A, int64_t n, int64_t nb, int G, double* Y, int
     }
     if (r == lay.y_owner())
       for (int64_t c = 0; c < nyp; ++c) memcpy(&Ls[r][(size_t)(lay.ycol0(r) + c) * n], Y + c * n, sizeof(double) * n);
-    ranks[r] = gpr::DistRank<CpuBE>{r, &bes[r], Ls[r].data(), n, dinvs[r].data(), Ukks[r].data(), panels[r].data(), gts[r].data()};
+    ranks[r] = gpr::DistRank<CpuBE>{r, &bes[r], Ls[r].data(), n, dinvs[r].data(), {Ukks[2 * r].data(), Ukks[2 * r + 1].data()},
+                                    {panels[2 * r].data(), panels[2 * r + 1].data()}, gts[r].data()};
   }
   CpuComm comm;
   comm.lay = lay; comm.ranks = &ranks;
