@@ -216,17 +216,19 @@ def run_gpu(args, rank, world, local_rank):
     t0 = time.perf_counter()
     for s in range(args.steps):
         F, G = step(args.warmup + s)
-        for k, v in mh.timings().items():
+        for k, v in mh.timings().items():     # CUDA events recorded by the library on ITS stream (torch.cuda.Event cannot see it)
             stage[k] = stage.get(k, 0.0) + v
     barrier()
-    t_loc = time.perf_counter() - t0
+    t_wall = time.perf_counter() - t0
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
+    # device time of the K timed steps: event pair around every evaluation on the library stream, summed; max over ranks
+    t_loc = stage["eval"] * 1e-3
     t_max = t_loc
     if dist is not None:
-        tt = torch.tensor([t_loc], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([t_loc, t_wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_max = float(tt.item())
+        t_max, t_wall = float(tt[0].item()), float(tt[1].item())
     value = world * args.steps / t_max
 
     # end-to-end through the C ABI with host buffers
@@ -267,7 +269,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # secondary metrics of BASELINE.json: Cholesky TFLOP/s, predict points/s
     extra = {"cholesky_tflops": N ** 3 / 3 / ms["potrf"] / 1e9, "inverse_tflops": 2 * N ** 3 / 3 / (ms["trtri"] + ms["lauum"]) / 1e9,
-             "stage_ms_per_step": {k: round(v, 3) for k, v in ms.items() if v > 0}}
+             "stage_ms_per_step": {k: round(v, 3) for k, v in ms.items() if v > 0 and not k.startswith("pred")}}
     if not args.no_predict:
         M = 16384
         xp = np.asfortranarray(np.random.default_rng(4004).random((D, M)))
@@ -295,8 +297,16 @@ def run_gpu(args, rank, world, local_rank):
         hp_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # DRAM traffic of the dominant kernel per step: from the committed ncu capture of this command (profiles/), GB
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+        if N == tj.get("N"):
+            traffic = tj["dgemm128_dram_gb_per_eval"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": fp64_sust, "unit": "TFLOP/s", "frac": achieved / fp64_sust,
-                "traffic": None,
+                "traffic": traffic, "traffic_unit": "GB of DRAM read+write by all dgemm128 launches of one step (ncu, profiles/dram_traffic.json)",
                 "kernel": "dgemm128_kernel (DMMA) inside blocked potrf+trtri+lauum: N^3 flop per step / (potrf+trtri+lauum) CUDA-event ms",
                 "peak_source": f"cuBLAS DGEMM 8192^3 via torch.matmul, sustained {fp64_sust:.1f} / burst {fp64_burst:.1f} TFLOP/s measured in this run "
                                "(MEASURED_PEAKS.json holds no FP64 figure" + (f"; its HBM copy figure is {hp_peak.get('hbm_gbs')} GB/s)" if hp_peak else ")"),
@@ -313,8 +323,9 @@ def run_gpu(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD if N == N_FULL else WORKLOAD.replace("N=32768", f"N={N}"),
                        "parallelism": "replicas only (one hyper-parameter set per GPU, no data-path collective)" if world > 1 else "1 GPU",
                        "l2": "inputs larger than L2 (K is 8.6 GB per evaluation); no explicit flush needed",
-                       "timing": "host wall clock around K synchronous C-ABI calls, barrier + torch.cuda.synchronize on both sides, max over ranks; "
-                                 "stage times from CUDA events on the library stream"},
+                       "timing": "CUDA events on the library stream around every evaluation (hp upload .. F, G read back), summed over the K "
+                                 "steps, max over ranks; barrier + torch.cuda.synchronize on both sides; wall clock reported beside it"},
+            "wall_ms_per_step": t_wall / args.steps * 1e3,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": base,
             "extra": extra, "F_last": F, "G_norm_last": float(np.linalg.norm(G))}
     print(json.dumps(line), flush=True)

@@ -135,8 +135,23 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
   constexpr int LDA_S = GemmTile<A_KC, GEMM_BM>::LD;
   constexpr int LDB_S = GemmTile<B_KC, BN>::LD;
 
+  // CTA rasterisation.  The hardware issues CTAs in x-fastest order; taken literally (tile_m = blockIdx.x) one wave
+  // of ~300 CTAs would span every row tile of a single column tile, i.e. stream the WHOLE A operand from DRAM once per
+  // column tile (ncu, N = 32768: 1.3 TB of DRAM reads per evaluation against 26 GB algorithmic).  Instead consecutive
+  // CTAs walk GM row tiles x all column tiles, so a wave covers a near-square patch of C and its operand slabs stay in L2.
+  constexpr int GM = (WN == 2) ? 16 : 12;
+  int tile_m, tile_n;
+  {
+    const int Mx = gridDim.x, Ny = gridDim.y;
+    const int pid = blockIdx.x + blockIdx.y * Mx;
+    const int group = pid / (GM * Ny), first_m = group * GM;
+    const int gsize = min(Mx - first_m, GM);
+    const int rem = pid - group * GM * Ny;
+    tile_m = first_m + rem % gsize;
+    tile_n = rem / gsize;
+  }
   // KUPTO: the contraction length grows with the column tile -> issue the longest tiles first (shorter tail)
-  const int tile_m = blockIdx.x, tile_n = (p.flags & GEMM_MAP_KUPTO) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  if (p.flags & GEMM_MAP_KUPTO) tile_n = gridDim.y - 1 - tile_n;
   const int blk_n = (tile_n * BN) >> 7;   // 128-block column of this tile (tile_m is already a 128-block row)
   if ((p.flags & GEMM_UPPER_ONLY) && tile_m > blk_n) return;
   int gt = 0;   // global tile column (mapped forms)

@@ -648,10 +648,15 @@ int gpr_nlml_grad(gpr_model* m, const double* hp_in, int P, int log_scale, doubl
   if (P != m->P) return fail(ctx, GPR_ERR_ARG, "Parameter size mismatch.");
   std::vector<double> hp(hp_in, hp_in + P);
   if (log_scale) for (auto& v : hp) v = std::exp(v);   // hp = exp.(log_hp)  (src/cost.jl:61)
+  CK(cudaSetDevice(ctx->device));
+  cudaEventRecord(m->tm.beg[GPR_T_EVAL], ctx->stream);   // (timer_reset inside gpr_update_cache leaves the recorded event alone)
   int rc = gpr_update_cache(m, hp.data(), P, eps, G != nullptr, info);
   if (rc) return rc;
   if (G) { rc = compute_grad(m, log_scale, G); if (rc) return rc; }
   if (F) { rc = compute_loss(m, F); if (rc) return rc; }
+  cudaEventRecord(m->tm.end[GPR_T_EVAL], ctx->stream);
+  m->tm.acc_ms[GPR_T_EVAL] = 0.0;
+  m->tm.used[GPR_T_EVAL] = true;
   CK(cudaStreamSynchronize(ctx->stream));
   return GPR_OK;
 }

@@ -76,6 +76,7 @@ extern "C" {
 #define GPR_T_PRED_MEAN 8
 #define GPR_T_PRED_TRSM 9
 #define GPR_T_PRED_ROWNORM 10
+#define GPR_T_EVAL 11        /* one whole gpr_nlml_grad call: hp upload .. F, G on the host side of the stream */
 #define GPR_T_COUNT 16
 
 typedef struct gpr_ctx gpr_ctx;

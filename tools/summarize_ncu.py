@@ -1,6 +1,9 @@
 """Summaries of ncu outputs for profiles/ (run here, on the CPU box).
   python tools/summarize_ncu.py launches <launches.csv>            -> per-kernel share table (markdown)
   python tools/summarize_ncu.py full <report.ncu-rep> [max_rows]   -> key counters per captured launch (markdown)
+  python tools/summarize_ncu.py eval <launches.csv> [N] [json_out] -> ONE evaluation (first kbuild .. first grad_finalize) of a
+        launch list taken with gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum: per-kernel time share and
+        DRAM traffic; json_out receives the per-evaluation totals bench.py reports as roofline.traffic
 """
 import collections
 import csv
@@ -27,6 +30,39 @@ def launches(path):
     for k, v in sorted(tot.items(), key=lambda x: -x[1]):
         print(f"| `{k[:80]}` | {cnt[k]} | {v / 1e3:.2f} | {100 * v / T:.1f}% | {v / cnt[k]:.1f} |")
     print(f"\ntotal {T / 1e3:.1f} ms over {sum(cnt.values())} launches (cold-cache, serialised: compare shares, not absolutes)")
+
+
+def one_eval(path, N=32768, json_out=None):
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    by = {}
+    for r in csv.DictReader(lines):
+        d = by.setdefault(int(r["ID"]), {"name": re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").strip()})
+        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+    ids = sorted(by)
+    k0 = next(i for i in ids if "kbuild" in by[i]["name"])
+    k1 = next(i for i in ids if "grad_finalize" in by[i]["name"] and i > k0)
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+    for i in ids:
+        if k0 <= i <= k1:
+            a = agg[by[i]["name"]]
+            a[0] += 1
+            a[1] += by[i].get("gpu__time_duration.sum", 0.0)
+            a[2] += by[i].get("dram__bytes_read.sum", 0.0)
+            a[3] += by[i].get("dram__bytes_write.sum", 0.0)
+    T = sum(a[1] for a in agg.values())
+    print("| kernel | launches | total ms | share | DRAM read GB | DRAM write GB | avg GB/s |\n|---|---:|---:|---:|---:|---:|---:|")
+    for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+        print(f"| `{k[:70]}` | {a[0]} | {a[1] / 1e6:.2f} | {100 * a[1] / T:.1f}% | {a[2] / 1e9:.2f} | {a[3] / 1e9:.2f} | {(a[2] + a[3]) / a[1]:.0f} |")
+    tot_r, tot_w = sum(a[2] for a in agg.values()), sum(a[3] for a in agg.values())
+    print(f"\none evaluation: {k1 - k0 + 1} launches, {T / 1e6:.1f} ms under ncu (cold-cache, serialised), DRAM read {tot_r / 1e9:.1f} GB + write {tot_w / 1e9:.1f} GB; "
+          f"algorithmic minimum 24 N^2 = {24 * N * N / 1e9:.1f} GB")
+    if json_out:
+        g = [a for k, a in agg.items() if "dgemm128" in k]
+        json.dump({"N": N, "source": path.split("/")[-1], "launches_per_eval": k1 - k0 + 1,
+                   "dgemm128_launches": sum(a[0] for a in g), "dgemm128_dram_gb_per_eval": round(sum(a[2] + a[3] for a in g) / 1e9, 2),
+                   "all_kernels_dram_gb_per_eval": round((tot_r + tot_w) / 1e9, 2), "algorithmic_gb_per_eval": round(24 * N * N / 1e9, 2),
+                   "dgemm128_time_share_under_ncu": round(sum(a[1] for a in g) / T, 4)}, open(json_out, "w"), indent=1)
 
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -56,7 +92,9 @@ def full(path, max_rows=6):
 
 
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "eval":
+        one_eval(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 32768, sys.argv[4] if len(sys.argv) > 4 else None)
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2])
     else:
         full(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 6)
