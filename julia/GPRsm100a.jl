@@ -146,4 +146,53 @@ function predict!(μₚ, Σₚ::Diagonal, md::SM100, xeq::Cmap, pc::SM100SplitPr
     check(pc.h.c, rc)
 end
 
+# ---------------------------------------------------------------------------------------------------------
+# Multi-GPU gradient cache (BASELINE.json config 5: N = 131072, 137 GB of FP64 K): K / U / K^-1 block-cyclic over
+# `devices`, one Julia process drives all of them (gpr_mgpu_*, include/gpr_sm100a.h).  Drop-in for
+# SM100GradCache in loss_grad! / log_loss_grad!, hence in `train(SM100Multi(md; devices = 0:7), ...)`.
+# ---------------------------------------------------------------------------------------------------------
+mutable struct MultiHandle
+    mg::Ptr{Cvoid}
+    h::Ptr{Cvoid}
+end
+struct SM100MultiGradCache <: AbstractGradCache
+    hp::Vector{Float64}
+    h::MultiHandle
+end
+function mcheck(h::MultiHandle, rc::Cint, info::Int64 = 0)
+    rc == 0 && return nothing
+    rc == 1 && throw(PosDefException(info))
+    error("libgpr_sm100a: ", unsafe_string(ccall((:gpr_mgpu_last_error, LIB), Cstring, (Ptr{Cvoid},), h.mg)))
+end
+function SM100MultiGradCache(md::GPRModel; devices = 0:(ccall((:gpr_device_count, LIB), Cint, ()) - 1), nb::Integer = 1024)
+    devs = Cint.(collect(devices))
+    mg = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:gpr_mgpu_create, LIB), Cint, (Cint, Ptr{Cint}, Int64, Ref{Ptr{Cvoid}}), length(devs), devs, nb, mg)
+    rc == 0 || error("gpr_mgpu_create: ", unsafe_string(ccall((:gpr_mgpu_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    t = comp_types(md.covar)
+    y = md.y isa AbstractVector ? reshape(md.y, :, 1) : md.y
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    mh = MultiHandle(mg[], C_NULL)
+    rc = ccall((:gpr_mgpu_model_create, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cint}, Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Ref{Ptr{Cvoid}}),
+        mg[], t, length(t), size(md.x, 1), size(md.x, 2), md.x, y, size(y, 2), md.train_axis, h)
+    mcheck(mh, rc)
+    mh.h = h[]
+    finalizer(mh) do x
+        ccall((:gpr_mgpu_model_destroy, LIB), Cint, (Ptr{Cvoid},), x.h)
+        ccall((:gpr_mgpu_destroy, LIB), Cint, (Ptr{Cvoid},), x.mg)
+    end
+    SM100MultiGradCache(copy(md.params), mh)
+end
+function _fg!(F, G, v, tc::SM100MultiGradCache, logscale::Bool)
+    f = Ref{Float64}(0.0); info = Ref{Int64}(0)
+    rc = ccall((:gpr_mgpu_nlml_grad, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cdouble, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
+        tc.h.h, v, length(v), logscale, 1e-8, F === nothing ? C_NULL : f, G === nothing ? C_NULL : G, info)
+    mcheck(tc.h, rc, info[])
+    F === nothing ? nothing : f[]
+end
+loss_grad!(::MarginalLikelihood, F, G, hp, md, tc::SM100MultiGradCache) = _fg!(F, G, hp, tc, false)
+log_loss_grad!(::MarginalLikelihood, F, G, log_hp, md, tc::SM100MultiGradCache) = _fg!(F, G, log_hp, tc, true)
+
 end # module
