@@ -44,6 +44,12 @@ struct KBuildArgs {
   long long diag_shift;  // row r is "the same point" as col r + diag_shift (tiles of a larger problem)
   int zero_lower;        // entries strictly below that diagonal are written as 0 and not evaluated (block-cyclic
                          // multi-GPU layout: only the upper triangle is referenced, csrc/dist_blocked.hpp)
+  // Fused posterior mean (mu = K* wt, src/predict.jl:73-76): when mean_w != nullptr every CTA also writes
+  //   mean_partial[blockIdx.y * Rp + r] = sum over its 64 columns of out(r, c) * mean_w[c]
+  // so the K* tile is never re-read for the mean (the partials are 1/64 of the tile).  out may then be nullptr
+  // (mean-only prediction: K* is not stored at all).
+  const double* mean_w;
+  double* mean_partial;
 };
 
 constexpr int KB_TILE = 64;
@@ -142,11 +148,14 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_kernel(const KBuildArgs a) 
     for (int c = 0; c < a.spec.ncomp; ++c)
       if (a.spec.type[c] == KT_NOISE) { const double s = a.hp[a.spec.hp_off[c]]; noise2 = s * s; break; }   // findfirst: compose_covar.jl:65
   }
+  double msum[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < 4; ++j) {
+    const long long c = c0 + ty + 16 * j;
+    const double wc = (a.mean_w && c < a.C) ? a.mean_w[c] : 0.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const long long r = r0 + tx + 16 * i, c = c0 + ty + 16 * j;
+      const long long r = r0 + tx + 16 * i;
       if (r >= a.Rp || c >= a.Cp) continue;
       double v;
       if (r < a.R && c < a.C) {
@@ -157,8 +166,25 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_kernel(const KBuildArgs a) 
         v = (a.pad_identity && r == c + a.diag_shift) ? 1.0 : 0.0;
       }
       if (a.zero_lower && r > c + a.diag_shift) v = 0.0;
-      a.out[r + c * a.ldo] = v;
+      if (a.out) a.out[r + c * a.ldo] = v;
+      msum[i] += v * wc;
     }
+  }
+  if (a.mean_w) {
+    // 16 threads (ty = 0..15) hold partial sums of the same row: reduce through shared memory in a fixed order
+    __syncthreads();                       // xs1 / xs2 are dead from here on
+    double* red = kb_smem;                 // [16][64]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) red[ty * KB_TILE + tx + 16 * i] = msum[i];
+    __syncthreads();
+    if (tid < KB_TILE) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s += red[q * KB_TILE + tid];
+      const long long r = r0 + tid;
+      if (r < a.Rp) a.mean_partial[(long long)blockIdx.y * a.Rp + r] = s;
+    }
+  }
 }
 
 // Dense dK/dtheta for ONE non-noise component (API parity with grad(cov,i,hp,x):
@@ -222,7 +248,7 @@ struct GradArgs {
   const double* hp; KSpec spec; int P; double eps;
   double* partial;   // gridDim.x * (P+1)
   // DIST form (block-cyclic multi-GPU layout): Kinv holds this rank's block columns only
-  int G, rank;           // local block column lb is global block column lb * G + rank
+  int G, rank;           // local block column lb is global block column DistLayout::gblock(rank, lb)
   int nbt;               // 64-tiles per block column (nb / 64)
   long long lcol_tiles;  // local 64-tile columns (matrix columns only)
 };
@@ -249,7 +275,8 @@ __global__ void __launch_bounds__(GR_THREADS) grad_reduce_kernel(const GradArgs 
     if (DIST) {
       const long long ltj = lin / T;
       ti = lin % T;
-      tj = ((ltj / a.nbt) * a.G + a.rank) * a.nbt + ltj % a.nbt;
+      const long long lb = ltj / a.nbt;   // local block column -> global block column (DistLayout::gblock, snake order)
+      tj = (lb * a.G + ((lb & 1) ? a.G - 1 - a.rank : a.rank)) * a.nbt + ltj % a.nbt;
       lc0 = ltj * GR_TILE;
       if (ti > tj || tj >= T) continue;   // block uniform
     } else {

@@ -6,8 +6,9 @@
 //   K^-1 (dpotrs on the identity) /root/reference/src/cost.jl:107-109   (here trtri + lauum, 2N^3/3)
 //
 // Layout.  The padded Np x Np matrix is cut into block columns of width nb (a multiple of 128); block column J
-// lives on rank J mod G as local block J / G (1-D block-cyclic).  The right-hand sides y (padded to nyp columns)
-// form one more, narrower block column with index nblk, owned by rank nblk mod G and stored after that rank's
+// lives on one rank as its local block J / G (1-D block-cyclic; the order of the ranks alternates from round to
+// round, see DistLayout::owner).  The right-hand sides y (padded to nyp columns)
+// form one more, narrower block column with index nblk, owned by owner(nblk) and stored after that rank's
 // matrix columns.  Every rank keeps its columns in ONE column-major array L (Np rows, leading dimension ld), so
 // the row panel U(k, :) of step k is a contiguous-by-column slab of every rank's L and all trailing updates of a
 // step are a single GEMM launch per rank.  Only the upper triangle is ever referenced; the strict lower
@@ -81,17 +82,29 @@ struct DistLayout {
   int G = 1;
   int64_t Np = 0, nb = 0, nblk = 0, nyp = 0;
   int tpb() const { return (int)(nb / LEAF); }
-  int owner(int64_t J) const { return (int)(J % G); }
-  int y_owner() const { return (int)(nblk % G); }
-  int64_t nloc(int r) const { return nblk > r ? (nblk - r + G - 1) / G : 0; }          // matrix blocks owned by r
-  int64_t count_le(int r, int64_t k) const { return k >= r ? (k - r) / G + 1 : 0; }    // owned blocks J <= k
+  // Block column J belongs to round q = J / G.  Even rounds deal the blocks to ranks 0..G-1, odd rounds to
+  // G-1..0 ("snake" order), which evens out the TOTAL work and memory per rank (with the plain cyclic order the
+  // last rank owns the longest column of every round).  Every rank owns exactly one block per round, so the local
+  // block index is still q.  Measured (2 x B200, N = 32768): no change in run time -- the steps are globally
+  // ordered by the panel exchange, so what counts is the per-step maximum (one block of nb columns more on
+  // some rank), which no 1-D order can remove.
+  int owner(int64_t J) const { const int p = (int)(J % G); return ((J / G) & 1) ? G - 1 - p : p; }
+  int64_t gblock(int r, int64_t lb) const { return lb * G + ((lb & 1) ? G - 1 - r : r); }   // global block of local block lb
+  int y_owner() const { return owner(nblk); }
+  int64_t count_le(int r, int64_t k) const {     // owned matrix blocks J <= k
+    if (k < 0) return 0;
+    const int64_t q = (k + 1) / G, rem = (k + 1) % G;
+    const int64_t pos = (q & 1) ? G - 1 - r : r;   // position of rank r inside the partial round q
+    return q + (pos < rem ? 1 : 0);
+  }
+  int64_t nloc(int r) const { return count_le(r, nblk - 1); }          // matrix blocks owned by r
   int64_t ycol0(int r) const { return nloc(r) * nb; }
   int64_t lcols(int r) const { return nloc(r) * nb + (r == y_owner() ? nyp : 0); }
   int64_t ltiles(int r) const { return lcols(r) / LEAF; }
   int gtile(int r, int64_t jt) const {
     const int64_t t = tpb();
     if (jt >= nloc(r) * t) return GTILE_RHS + (int)(jt - nloc(r) * t);
-    return (int)(((jt / t) * G + r) * t + jt % t);
+    return (int)(gblock(r, jt / t) * t + jt % t);
   }
 };
 

@@ -153,7 +153,8 @@ int make_spec(gpr_ctx* ctx, const int* types, int ncomp, int D, KSpec* spec, int
 int launch_kbuild(gpr_ctx* ctx, int mode, const KBuildArgs& a) {
   int nk = 0;
   for (int c = 0; c < a.spec.ncomp; ++c) if (a.spec.type[c] != KT_NOISE) nk++;
-  const size_t smem = (size_t)2 * nk * a.D * KB_TILE * sizeof(double);
+  size_t smem = (size_t)2 * nk * a.D * KB_TILE * sizeof(double);
+  if (a.mean_w) smem = std::max(smem, (size_t)16 * KB_TILE * sizeof(double));
   if (smem > 200 * 1024) return fail(ctx, GPR_ERR_UNSUPPORTED, "covariance build: (#components x D) too large for shared memory");
   dim3 grid((unsigned)((a.Rp + KB_TILE - 1) / KB_TILE), (unsigned)((a.Cp + KB_TILE - 1) / KB_TILE));
   if (grid.y > 65535) return fail(ctx, GPR_ERR_UNSUPPORTED, "covariance build: too many column tiles");
@@ -746,8 +747,11 @@ int predict_tile(gpr_model* m, const double* d_xp, int64_t mt, int64_t m0, int s
   gpr_ctx* ctx = m->ctx;
   const int64_t Np = m->Np, N = m->N;
   const int64_t mtp = round_up(mt, 128);
-  int rc = ensure(ctx, m->w_kxp, (size_t)mtp * Np);
-  if (rc) return rc;
+  int rc = GPR_OK;
+  if (d_var || m->ny > 1) {   // the K* tile is only materialised for the variance (or a matrix y)
+    rc = ensure(ctx, m->w_kxp, (size_t)mtp * Np);
+    if (rc) return rc;
+  }
   double* Kxp = m->w_kxp.p;
   {
     Scope s(m->tm, GPR_T_PRED_KSTAR, ctx->stream);
@@ -756,10 +760,25 @@ int predict_tile(gpr_model* m, const double* d_xp, int64_t mt, int64_t m0, int s
     a.x1 = d_xp; a.x2 = m->d_x; a.D = m->D; a.hp = m->d_hp; a.spec = m->spec;
     a.eps = m->eps_host; a.same = same_x; a.add_noise = 0; a.pad_identity = 0; a.sigma_one = 0; a.row_scale = nullptr;
     a.diag_shift = -m0;
+    // vector y: mu = K* wt is reduced inside the build (per-CTA partial sums over 64 columns), so the K* tile is not
+    // re-read; without a variance request K* is not even stored
+    const bool fuse_mean = (m->ny == 1);
+    int64_t ncol_tiles = (Np + KB_TILE - 1) / KB_TILE;
+    if (fuse_mean) {
+      rc = ensure(ctx, m->w_part, (size_t)ncol_tiles * mtp);
+      if (rc) return rc;
+      a.mean_w = m->d_wt; a.mean_partial = m->w_part.p;
+      if (!d_var) a.out = nullptr;
+    }
     rc = launch_kbuild(ctx, DM_EUCLID, a);
     if (rc) return rc;
+    if (fuse_mean) {
+      rowreduce_finalize_kernel<<<(unsigned)((mt + 255) / 256), 256, 0, ctx->stream>>>(m->w_part.p, (int)ncol_tiles, mtp, mt, 0.0, 1.0, d_mean);
+      ctx->launches++;
+      CK(cudaGetLastError());
+    }
   }
-  {
+  if (m->ny > 1) {
     Scope s(m->tm, GPR_T_PRED_MEAN, ctx->stream);
     for (int e = 0; e < m->ny; ++e) {
       rc = row_reduce(m, 0, Kxp, mtp, mtp, mt, N, m->d_wt + (int64_t)e * Np, 0.0, 1.0, d_mean + (int64_t)e * ldmean);

@@ -21,11 +21,13 @@ __global__ void __launch_bounds__(256) copy2d_kernel(double* __restrict__ dst, l
 }
 
 // Row panel k of the block-cyclic factor, gathered in global column order on the calling rank:
-//   dst[p + ((J-k-1)*nb + c)*nb] = L_{J mod G}[k*nb + p + ((J/G)*nb + c)*ld],  J = k+1+blockIdx.x
+//   dst[p + ((J-k-1)*nb + c)*nb] = L_{owner(J)}[k*nb + p + ((J/G)*nb + c)*ld],  J = k+1+blockIdx.x
+// (owner(J): snake order of DistLayout::owner)
 __global__ void __launch_bounds__(256) gather_rowpanel_kernel(double* __restrict__ dst, const PeerPtrs src, int G, long long ld,
                                                               long long k, long long nb) {
   const long long J = k + 1 + blockIdx.x;
-  const double* S = src.p[J % G] + k * nb + (J / G) * nb * ld;
+  const int pos = (int)(J % G);
+  const double* S = src.p[((J / G) & 1) ? G - 1 - pos : pos] + k * nb + (J / G) * nb * ld;
   double* D = dst + (long long)blockIdx.x * nb * nb;
   const long long r2 = nb >> 1;
   for (long long c = blockIdx.y; c < nb; c += gridDim.y)
@@ -39,7 +41,8 @@ __global__ void __launch_bounds__(1024, 1) dist_logdiag_kernel(const double* __r
   __shared__ double red[1024];
   double s = 0.0;
   for (long long c = threadIdx.x; c < ncols; c += blockDim.x) {
-    const long long g = ((c / nb) * G + rank) * nb + c % nb;
+    const long long lb = c / nb;
+    const long long g = (lb * G + ((lb & 1) ? G - 1 - rank : rank)) * nb + c % nb;   // DistLayout::gblock
     s += log(L[g + c * ld]);
   }
   red[threadIdx.x] = s;
@@ -413,7 +416,7 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
     MCK(cudaMemcpyAsync(R.hp, hp.data(), sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
     MCK(cudaMemsetAsync(ctx->d_info, 0, sizeof(long long), ctx->stream));
     for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
-      const int64_t J = lb * Gn + r;
+      const int64_t J = lay.gblock(r, lb);
       const int64_t cvalid = std::max<int64_t>(0, std::min<int64_t>(nb, N - J * nb));
       KBuildArgs a{};
       a.out = R.L + lb * nb * ld; a.ldo = ld; a.R = N; a.C = cvalid; a.Rp = Np; a.Cp = nb;
@@ -569,7 +572,7 @@ int gpr_mgpu_fetch(gpr_mgpu_model* m, int which, double* out) {
     MRank& R = mg->rk[r];
     MCK(cudaSetDevice(R.ctx->device));
     for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
-      const int64_t J = lb * mg->G + r;
+      const int64_t J = lay.gblock(r, lb);
       const int64_t cv = std::max<int64_t>(0, std::min<int64_t>(nb, N - J * nb));
       if (cv > 0)
         MCK(cudaMemcpy2DAsync(out + J * nb * N, sizeof(double) * N, R.L + lb * nb * ld, sizeof(double) * ld, sizeof(double) * N, cv,
@@ -600,7 +603,7 @@ int gpr_mgpu_dbg_factor(gpr_mgpu* mg, double* A, int64_t N, double* Y, int ny, i
       MRank& R = mg->rk[r];
       MCK(cudaSetDevice(R.ctx->device));
       for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
-        const int64_t J = lb * mg->G + r;
+        const int64_t J = lay.gblock(r, lb);
         std::fill(col.begin(), col.end(), 0.0);
         for (int64_t c = 0; c < nb; ++c) {
           const int64_t gc = J * nb + c;
@@ -641,7 +644,7 @@ int gpr_mgpu_dbg_factor(gpr_mgpu* mg, double* A, int64_t N, double* Y, int ny, i
       MRank& R = mg->rk[r];
       MCK(cudaSetDevice(R.ctx->device));
       for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
-        const int64_t J = lb * mg->G + r;
+        const int64_t J = lay.gblock(r, lb);
         const int64_t cv = std::max<int64_t>(0, std::min<int64_t>(nb, N - J * nb));
         if (cv > 0)
           MCK(cudaMemcpy2DAsync(A + J * nb * N, sizeof(double) * N, R.L + lb * nb * md.ld, sizeof(double) * md.ld, sizeof(double) * N, cv,

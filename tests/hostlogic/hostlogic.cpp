@@ -192,7 +192,7 @@ long long hl_dist_factor(double* A, int64_t n, int64_t nb, int G, double* Y, int
     gts[r].resize(std::max<int64_t>(lay.ltiles(r), 1));
     for (int64_t t = 0; t < lay.ltiles(r); ++t) gts[r][t] = lay.gtile(r, t);
     for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
-      const int64_t J = lb * G + r;
+      const int64_t J = lay.gblock(r, lb);
       for (int64_t c = 0; c < nb; ++c)
         for (int64_t i = 0; i <= J * nb + c; ++i) Ls[r][i + (lb * nb + c) * n] = A[i + (J * nb + c) * n];   // upper only
     }
@@ -211,7 +211,7 @@ long long hl_dist_factor(double* A, int64_t n, int64_t nb, int G, double* Y, int
   for (int r = 0; r < G; ++r) {
     if (bes[r].info && (!info || bes[r].info < info)) info = bes[r].info;
     for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
-      const int64_t J = lb * G + r;
+      const int64_t J = lay.gblock(r, lb);
       for (int64_t c = 0; c < nb; ++c) memcpy(A + (J * nb + c) * n, &Ls[r][(size_t)(lb * nb + c) * n], sizeof(double) * n);
     }
     if (r == lay.y_owner())
