@@ -50,6 +50,7 @@ struct KBuildArgs {
   // (mean-only prediction: K* is not stored at all).
   const double* mean_w;
   double* mean_partial;
+  double all_shift;      // added to EVERY valid entry (prior sampling: `Sigma .+ 1e-7`, src/distributions.jl:25)
 };
 
 constexpr int KB_TILE = 64;
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_kernel(const KBuildArgs a) 
         v = sum[i][j];
         if (a.add_noise && r == c + a.diag_shift) v += noise2;
         if (a.row_scale) v *= a.row_scale[r];
+        v += a.all_shift;
       } else {
         v = (a.pad_identity && r == c + a.diag_shift) ? 1.0 : 0.0;
       }

@@ -1063,6 +1063,62 @@ int gpr_split_predict(gpr_model* m, const double* xe, int64_t ne, const double* 
 }
 
 // ---------------------------------------------------------------------------
+// prior sampling (src/distributions.jl)
+// ---------------------------------------------------------------------------
+int gpr_sample_mvn(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, const double* hp, const double* x, int64_t N,
+                   double shift, const double* z, const double* mu, double* out, int64_t* info) {
+  if (!ctx) return GPR_ERR_ARG;
+  if (!hp || !x || !z || !out || N < 1) return fail(ctx, GPR_ERR_ARG, "NULL or empty argument");
+  CK(cudaSetDevice(ctx->device));
+  if (info) *info = 0;
+  KSpec spec; int P = 0, nk = 0;
+  int rc = make_spec(ctx, comp_types, ncomp, D, &spec, &P, &nk);
+  if (rc) return rc;
+  const int64_t Np = round_up(N, 128);
+  double *d_x = nullptr, *d_hp = nullptr, *d_S = nullptr, *d_dinv = nullptr, *d_z = nullptr, *d_o = nullptr;
+  cudaError_t e = cudaMalloc(&d_x, sizeof(double) * D * N);
+  if (e == cudaSuccess) e = cudaMalloc(&d_hp, sizeof(double) * P);
+  if (e == cudaSuccess) e = cudaMalloc(&d_S, sizeof(double) * Np * Np);
+  if (e == cudaSuccess) e = cudaMalloc(&d_dinv, sizeof(double) * Np * 128);
+  if (e == cudaSuccess) e = cudaMalloc(&d_z, sizeof(double) * Np);
+  if (e == cudaSuccess) e = cudaMalloc(&d_o, sizeof(double) * Np);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, x, sizeof(double) * D * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_hp, hp, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_z, 0, sizeof(double) * Np, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_o, 0, sizeof(double) * Np, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_z, z, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && mu) e = cudaMemcpyAsync(d_o, mu, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_info, 0, sizeof(long long), ctx->stream);
+  long long h_info = 0;
+  rc = GPR_OK;
+  if (e == cudaSuccess) {
+    // Sigma (upper triangle, zero below: the product U^T z below then is a plain transposed matrix-vector product)
+    KBuildArgs a{};
+    a.out = d_S; a.ldo = Np; a.R = N; a.C = N; a.Rp = Np; a.Cp = Np;
+    a.x1 = d_x; a.x2 = d_x; a.D = D; a.hp = d_hp; a.spec = spec;
+    a.eps = 1e-8; a.same = 1; a.add_noise = 1; a.pad_identity = 1; a.zero_lower = 1; a.all_shift = shift;   // kernel(cov, theta, x): src/distributions.jl:43
+    rc = launch_kbuild(ctx, DM_EUCLID, a);
+    if (!rc) {
+      CudaBE be{ctx};
+      Blocked<CudaBE> blk(be, d_dinv);
+      blk.potrf(d_S, Np, Np, 0);                                  // Sigma = U^T U, L = U^T  (cholesky(Sigma .+ 1e-7), :25)
+      be.gemv('T', Np, Np, 1.0, d_S, Np, d_z, d_o);               // out = mu + U^T z              (:32)
+      e = cudaMemcpyAsync(&h_info, ctx->d_info, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e == cudaSuccess) rc = check_pending(ctx, "gpr_sample_mvn");
+    }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_x); cudaFree(d_hp); cudaFree(d_S); cudaFree(d_dinv); cudaFree(d_z); cudaFree(d_o);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "gpr_sample_mvn", __LINE__);
+  if (info) *info = h_info;
+  if (h_info != 0) return fail(ctx, GPR_ERR_NOT_POSDEF, "matrix is not positive definite; Cholesky failed at pivot " + std::to_string(h_info));
+  return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------
 // diagnostics
 // ---------------------------------------------------------------------------
 int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, double alpha, const double* A,

@@ -55,6 +55,7 @@ _SIGS = {
     "gpr_split_kernel": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _dp, _dp, _i64, _dp, _i64, _dp, _i64, _dp, _dp, _dp]),
     "gpr_split_predict": (C.c_int, [_vp, _dp, _i64, _dp, _i64, _i64, _i64, _dp, _dp]),
     "gpr_timings": (C.c_int, [_vp, _dp, C.c_int]),
+    "gpr_sample_mvn": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _dp, _dp, _i64, C.c_double, _dp, _dp, _dp, C.POINTER(_i64)]),
     "gpr_dbg_dgemm": (C.c_int, [_vp, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _i64, _dp, _i64,
                                 C.c_double, _dp, _i64, C.c_int, C.c_int, _dp]),
     "gpr_dbg_factor": (C.c_int, [_vp, _dp, _i64, C.c_int, C.POINTER(_i64), _dp]),
@@ -327,6 +328,23 @@ def split_kernel_arrays(ctx, types, D, hp, xe, xq, x):
     ctx.check(lib().gpr_split_kernel(ctx.handle, types_array(types), len(types), int(D), dptr(hp), dptr(xe), ne, dptr(xq), nq,
                                      dptr(x), N, dptr(A), dptr(B), dptr(Cc)))
     return A, B, Cc
+
+
+def sample_mvn(ctx, types, D, hp, x, z, mu=None, shift=1e-7):
+    """out = chol(kernel(cov, hp, x) .+ shift).L @ z + mu  (src/distributions.jl:20-45)"""
+    x = f64(x)
+    hp = f64(np.asarray(hp, dtype=np.float64).ravel())
+    z = f64(np.asarray(z, dtype=np.float64).ravel())
+    N = int(x.shape[1])
+    if z.size != N:
+        raise GPRError("z must hold one standard-normal draw per point")
+    mu_c = None if mu is None else f64(np.asarray(mu, dtype=np.float64).ravel())
+    out = np.empty(N)
+    info = _i64(0)
+    rc = lib().gpr_sample_mvn(ctx.handle, types_array(types), len(types), int(D), dptr(hp), dptr(x), N, float(shift), dptr(z),
+                              dptr(mu_c), dptr(out), C.byref(info))
+    ctx.check(rc, info)
+    return out
 
 
 def dbg_dgemm(ctx, transA, transB, alpha, A, B, beta, Cm, flags=0, reps=1):

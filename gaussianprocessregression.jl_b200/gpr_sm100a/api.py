@@ -611,3 +611,265 @@ def _split_kernel(cov, hp, xeq, x, ctx=None):
         raise GPRError("SplitKernel is defined for Cmap(+, xe, xq) only")
     A, B, C = _ffi.split_kernel_arrays(ctx, _types(cov), x.shape[0], hp, xeq.xe, xeq.xq, x)
     return SplitKernel(A, B, C)
+
+
+# =========================================================================== SURVEY.md 8f "next" rows: callers of the hot path
+# Host logic exactly as in the reference (these drivers are Julia code there too); every factorization, solve,
+# gradient and prediction they issue goes through the same device entry points as above.
+
+# --------------------------------------------------------------------------- loss_grad.jl:6-30 (M-estimators)
+class MSE(AbstractLoss):
+    """src/loss_grad.jl:6,11-14"""
+
+
+class ChiSq(AbstractLoss):
+    """src/loss_grad.jl:7,16-22"""
+
+
+class Mahalanobis(AbstractLoss):
+    """src/loss_grad.jl:8,24-29"""
+
+
+def m_loss(cost, y, yp, Σp):
+    """loss(::MSE | ::ChiSq | ::Mahalanobis, y, yp, Σp)  (src/loss_grad.jl:11-29).  ntst-sized host arithmetic."""
+    y, yp = np.asarray(y, dtype=np.float64), np.asarray(yp, dtype=np.float64)
+    if isinstance(cost, MSE):
+        return float(np.sum((y - yp) ** 2) / len(y))
+    S = Σp.diag if isinstance(Σp, Diagonal) else np.asarray(Σp)
+    if isinstance(cost, ChiSq):
+        d = S if S.ndim == 1 else np.diag(S)
+        return float(np.sum((y - yp) ** 2 / d))
+    if isinstance(cost, Mahalanobis):
+        import scipy.linalg as sl
+        dl = sl.solve_triangular(sl.cholesky(S, lower=True), y - yp, lower=True)
+        return float(dl @ dl)
+    raise TypeError("m_loss: unknown cost")
+
+
+# --------------------------------------------------------------------------- crossval.jl
+def kfoldcv(n, k, nb=None, rng=None):
+    """kfoldcv(n, k, nb = div(n, k))  (src/crossval.jl:1-12); 0-based indices"""
+    nb = n // k if nb is None else nb
+    nsh = (rng or np.random.default_rng()).permutation(n)
+    trn, tst = [], []
+    for i in range(nb):
+        idx = np.arange(i * k, (i + 1) * k)
+        tst.append(nsh[idx])
+        trn.append(np.delete(nsh, idx))
+    return trn, tst
+
+
+def cv_step_(cost, mdt, xtst, ytst, pc, yp, Σp):
+    """cv_step!(cost, mdt, xtst, ytst, pc, yp, Σp)  (src/crossval.jl:45-50)"""
+    update_cache_(pc, mdt)
+    predict_(yp, Σp, mdt, xtst, pc)
+    return m_loss(cost, ytst, yp, Σp)
+
+
+def cv_step(md, cost, xtr, ytr, xtst, ytst):
+    """cv_step(md, cost, xtr, ytr, xtst, ytst)  (src/crossval.jl:37-43)"""
+    mdt = GPRModel(md.covar, md.params, xtr, ytr)
+    pc = predict_cache(mdt, xtst)(mdt, xtst)
+    yp = np.empty(np.asarray(ytst).shape[0])
+    Σp = np.empty((yp.shape[0], yp.shape[0]), order="F")
+    try:
+        return cv_step_(cost, mdt, xtst, ytst, pc, yp, Σp)
+    finally:
+        pc.close()
+
+
+def cv_batch(md, cost, x, y, cvset):
+    """cv_batch(md, cost, x, y, cvset)  (src/crossval.jl:14-35): one device model re-used across the folds (every fold
+    has the same training size, as in the reference, which overwrites mdt.x / mdt.y in place)."""
+    trn, tst = cvset
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    ntst = len(tst[0])
+    yp = np.empty(ntst)
+    Σp = np.empty((ntst, ntst), order="F")
+    lss = np.empty(len(trn))
+    mdt = GPRModel(md.covar, md.params, np.asfortranarray(x[:, trn[0]]), y[trn[0]].copy())
+    pc = predict_cache(mdt, x[:, tst[0]])(mdt, None)
+    try:
+        for i in range(len(trn)):
+            mdt.x = np.asfortranarray(x[:, trn[i]])      # a new object: the cache re-uploads it (md.x is compared by identity)
+            mdt.y = y[trn[i]].copy()
+            lss[i] = cv_step_(cost, mdt, np.asfortranarray(x[:, tst[i]]), y[tst[i]], pc, yp, Σp)
+    finally:
+        pc.close()
+    return lss
+
+
+# --------------------------------------------------------------------------- update_model.jl
+class BFGSQuad:
+    """src/update_model.jl:2"""
+
+
+class BFGSQuadCache:
+    """src/caches/update_model.jl:4-20: hp (log space), J, hess_inv"""
+
+    def __init__(self, md):
+        n = len(md.params)
+        self.hp, self.J, self.hess_inv = np.empty(n), np.empty(n), np.empty((n, n))
+
+
+def updater_cache(upd):
+    return BFGSQuadCache
+
+
+def bfgs_hessian(Bi, s, t, ρ=None):
+    """bfgs_hessian(Bi, s, t, ρ = 1 / dot(s, t))  (src/update_model.jl:50-54); Bi = None stands for `I`"""
+    s, t = np.asarray(s, dtype=np.float64), np.asarray(t, dtype=np.float64)
+    ρ = 1.0 / float(s @ t) if ρ is None else ρ
+    n = len(s)
+    Bi = np.eye(n) if Bi is None else np.asarray(Bi)
+    Cm = np.eye(n) - ρ * np.outer(s, t)
+    B = Cm @ Bi @ Cm.T + ρ * np.outer(s, s)
+    return 0.5 * (B + B.T)
+
+
+def bfgs_quad_(θ, JJ, B, gradL, ϵ, max_iter=100):
+    """bfgs_quad!(θ, JJ, B, ∇L, ϵ, max_iter)  (src/update_model.jl:64-79)"""
+    it = 0
+    while np.linalg.norm(JJ) > ϵ and it < max_iter:
+        s, t = θ.copy(), JJ.copy()
+        θ -= B @ JJ
+        JJ[...] = gradL(θ)
+        s, t = θ - s, JJ - t
+        B[...] = bfgs_hessian(B, s, t)
+        it += 1
+    return it
+
+
+def bfgs_quad(xx, JJ, HH, jac, ϵ=1e-5, max_iter=100):
+    """bfgs_quad(xx, JJ, HH, jac; ϵ, max_iter)  (src/update_model.jl:56-62); HH = None stands for `I`"""
+    x0, J0 = np.array(xx, dtype=np.float64), np.array(JJ, dtype=np.float64)
+    B = np.eye(len(x0)) if HH is None else np.linalg.inv(HH)
+    it = bfgs_quad_(x0, J0, B, jac, ϵ, max_iter)
+    return x0, J0, np.linalg.inv(B), it
+
+
+def hessian_fd_(hess, gradL, x, ϵ=1e-6):
+    """hessian_fd!(hess, ∇L, x, ϵ)  (src/update_model.jl:87-94): P + 1 independent gradient evaluations.  If ∇L has a
+    `many(list_of_points) -> list_of_gradients` attribute (ReplicaGradient below: one evaluation per GPU at a time,
+    SURVEY.md 8e "replicas"), the P + 1 points are evaluated through it in one batch."""
+    x = np.asarray(x, dtype=np.float64)
+    pts = [x.copy()]
+    for i in range(len(x)):
+        xe = x.copy()
+        xe[i] += ϵ
+        pts.append(xe)
+    gs = gradL.many(pts) if hasattr(gradL, "many") else [gradL(p) for p in pts]
+    for i in range(len(x)):
+        hess[:, i] = (gs[i + 1] - gs[0]) / ϵ
+    return hess
+
+
+def hessian_fd(gradL, x, ϵ=1e-6):
+    """hessian_fd(∇L, x, ϵ)  (src/update_model.jl:81-85)"""
+    n = len(x)
+    return hessian_fd_(np.empty((n, n)), gradL, x, ϵ)
+
+
+class ReplicaGradient:
+    """∇L closure of update_sample! (`jj`, src/update_model.jl:21-27,38-44) over one gradient cache per device:
+    `many(points)` spreads independent hyper-parameter points over the devices (one host thread per device; the C
+    calls release the GIL and distinct contexts may be used from distinct threads), a plain call uses device 0."""
+
+    def __init__(self, cost, md, caches):
+        self.cost, self.md, self.caches = cost, md, list(caches)
+
+    def __call__(self, log_x):
+        G = np.empty(len(log_x))
+        log_loss_grad_(self.cost, None, G, log_x, self.md, self.caches[0])
+        return G
+
+    def many(self, points):
+        from concurrent.futures import ThreadPoolExecutor
+        n = len(self.caches)
+        if n == 1:
+            return [self(p) for p in points]
+        out = [None] * len(points)
+
+        def work(w):
+            for i in range(w, len(points), n):
+                G = np.empty(len(points[i]))
+                log_loss_grad_(self.cost, None, G, points[i], self.md, self.caches[w])
+                out[i] = G
+
+        with ThreadPoolExecutor(n) as ex:
+            list(ex.map(work, range(n)))
+        return out
+
+
+def update_cache_bfgs_(uc, md, cost, tc, replicas=None):
+    """update_cache!(uc::BFGSQuadCache, md, cost, tc)  (src/update_model.jl:18-32)"""
+    uc.hp[...] = np.log(md.params)
+    jac = ReplicaGradient(cost, md, [tc] + list(replicas or []))
+    uc.J[...] = jac(uc.hp)
+    hess = hessian_fd(jac, uc.hp)
+    uc.hess_inv[...] = np.linalg.inv(np.triu(hess) + np.triu(hess, 1).T)      # inv(Hermitian(hess)): upper triangle
+    return jac
+
+
+def update_sample_(md, δy, *args, replicas=None):
+    """update_sample!(md, δy, upd, cost[, ϵJ]) | update_sample!(md, δy, cost, uc, tc[, ϵJ])  (src/update_model.jl:8-48):
+    md.y .+= δy, then a quasi-Newton re-optimisation of the log hyper-parameters started from the gradient and the
+    finite-difference Hessian at the current (previously optimal) point.  `replicas`: extra gradient caches on other
+    devices for the P + 1 evaluations of the Hessian.  Returns the number of iterations."""
+    if isinstance(args[0], BFGSQuad):
+        cost = args[1]
+        ϵJ = args[2] if len(args) > 2 else 1e-3
+        md.y += δy
+        tc = grad_cache(cost)(md)
+        uc = updater_cache(args[0])(md)
+        try:
+            return _update_sample_core(md, cost, uc, tc, ϵJ, replicas)
+        finally:
+            tc.close()
+    cost, uc, tc = args[0], args[1], args[2]
+    ϵJ = args[3] if len(args) > 3 else 1e-3
+    md.y += δy
+    return _update_sample_core(md, cost, uc, tc, ϵJ, replicas)
+
+
+def _update_sample_core(md, cost, uc, tc, ϵJ, replicas):
+    for c in [tc] + list(replicas or []):
+        c._sync_data(md)
+    jac = update_cache_bfgs_(uc, md, cost, tc, replicas)
+    iters = bfgs_quad_(uc.hp, uc.J, uc.hess_inv, jac, ϵJ)
+    md.params[...] = np.exp(uc.hp)
+    return iters
+
+
+# --------------------------------------------------------------------------- distributions.jl
+class NormalDistribution:
+    """src/distributions.jl:4-9,20-28.  Holds what `sample` needs: the covariance spec instead of a dense Σ."""
+
+    def __init__(self, μ, cov, θ, x):
+        self.μ, self.cov, self.θ, self.x = μ, cov, np.asarray(θ, dtype=np.float64), np.asarray(x, dtype=np.float64)
+
+
+class GaussianProcess:
+    """GaussianProcess(f_μ, kernel); gp(x[, θ]) -> NormalDistribution  (src/distributions.jl:11-14,37-46)"""
+
+    def __init__(self, f_μ, kernel):
+        self.f_μ, self.kernel = f_μ, kernel
+
+    def __call__(self, x, θ=None):
+        x = np.asarray(x, dtype=np.float64)
+        if θ is None:
+            θ = np.random.rand(dim_hp(self.kernel, x.shape[0]))
+        μ = np.array([self.f_μ(x[:, j]) for j in range(x.shape[1])], dtype=np.float64)
+        return NormalDistribution(μ, self.kernel, θ, x)
+
+
+def sample(dist_or_gp, *args, rng=None, z=None, ctx=None):
+    """sample(N::NormalDistribution; rng) | sample(gp, x[, θ])  (src/distributions.jl:30-35):
+    s = cholesky(Σ .+ 1e-7).L * randn(rng, dim) .+ μ with Σ = kernel(cov, θ, x).  The draws come from `rng`
+    (numpy Generator; the reference uses Xoshiro(1)) or are passed explicitly as `z`; the factorization and the
+    product run on the device (gpr_sample_mvn)."""
+    N = dist_or_gp(*args) if isinstance(dist_or_gp, GaussianProcess) else dist_or_gp
+    n = N.x.shape[1]
+    if z is None:
+        z = (rng or np.random.default_rng(1)).standard_normal(n)
+    return _ffi.sample_mvn(ctx or get_context(), _types(N.cov), N.x.shape[0], N.θ, N.x, z, N.μ, 1e-7)

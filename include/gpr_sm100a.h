@@ -149,6 +149,13 @@ int gpr_split_predict(gpr_model* model, const double* xe, int64_t ne, const doub
 
 int gpr_timings(gpr_model* model, double* ms, int n);
 
+/* sample(gp(x, theta)) / sample(::NormalDistribution): src/distributions.jl:20-45 (row f-5 of SURVEY.md 8f).
+ * Sigma = kernel(cov, theta, x) .+ shift  -- the reference adds 1e-7 to EVERY entry, not to the diagonal --
+ * factored as Sigma = L L^T; out = L z + mu.  z: N standard-normal draws supplied by the caller (the Xoshiro
+ * stream of the reference stays on the host), mu: N means or NULL (zero mean).  x is D x N. */
+int gpr_sample_mvn(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, const double* hp, const double* x, int64_t N,
+                   double shift, const double* z, const double* mu, double* out, int64_t* info);
+
 /* diagnostics (used by tests / bench only): the DMMA tile GEMM on host matrices, C = alpha op(A) op(B) + beta C.
  * M, N multiples of 128, K multiple of 16; transA/transB in {'N','T'} (TT unsupported).
  * reps > 1 re-runs the kernel and returns the mean kernel time in *ms. */

@@ -195,4 +195,23 @@ end
 loss_grad!(::MarginalLikelihood, F, G, hp, md, tc::SM100MultiGradCache) = _fg!(F, G, hp, tc, false)
 log_loss_grad!(::MarginalLikelihood, F, G, log_hp, md, tc::SM100MultiGradCache) = _fg!(F, G, log_hp, tc, true)
 
+# ---------------------------------------------------------------------------------------------------------
+# sample(N::NormalDistribution) on the device (src/distributions.jl:30-35): the draws stay on the Julia side (rng),
+# the factorization of `Sigma .+ 1e-7` and the product L * s + mu run in gpr_sample_mvn.
+# update_sample! (src/update_model.jl), cv_batch / cv_step! (src/crossval.jl) need no binding of their own: they only
+# call log_loss_grad! / update_cache! / predict! on the caches above.
+# ---------------------------------------------------------------------------------------------------------
+function sample_sm100(cov, θ::Vector{Float64}, x::Matrix{Float64}, μ::Vector{Float64}; rng = Xoshiro(1), c::Ctx = ctx())
+    n = size(x, 2)
+    z = randn(rng, n)
+    out = Vector{Float64}(undef, n)
+    t = comp_types(cov)
+    info = Ref{Int64}(0)
+    rc = ccall((:gpr_sample_mvn, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cint}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Int64, Cdouble, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
+        c.h, t, length(t), size(x, 1), θ, x, n, 1e-7, z, μ, out, info)
+    check(c, rc, info[])
+    out
+end
+
 end # module

@@ -408,3 +408,124 @@ def split_predict(md, xeq, var_range=(1, 3), pc=None):
         V = sl.solve_triangular(pc.U, Kxq.T, trans="T", lower=False).T
         var[(e - 1) * nq:e * nq] -= np.sum(V * V, axis=1)
     return mu, var
+
+
+# =========================================================================== SURVEY.md 8f "next" rows (callers of the hot path)
+# --------------------------------------------------------------------------- loss_grad.jl:11-30 (M-estimators used by crossval.jl)
+def loss_mse(y, yp, Sp=None):
+    """loss(::MSE, y, yp, Sigma_p) loss_grad.jl:11-14"""
+    return float(np.sum((y - yp) ** 2) / len(y))
+
+
+def loss_chisq(y, yp, Sp):
+    """loss(::ChiSq, ...) loss_grad.jl:16-22: sum (y_i - yp_i)^2 / Sigma_p[i, i]"""
+    return float(np.sum((y - yp) ** 2 / np.diag(Sp)))
+
+
+def loss_mahalanobis(y, yp, Sp):
+    """loss(::Mahalanobis, ...) loss_grad.jl:24-29: |L^-1 (y - yp)|^2 with Sigma_p = L L^T"""
+    d = sl.solve_triangular(sl.cholesky(Sp, lower=True), y - yp, lower=True)
+    return float(d @ d)
+
+
+# --------------------------------------------------------------------------- crossval.jl
+def kfoldcv(n, k, nb=None, rng=None):
+    """kfoldcv(n, k, nb = div(n, k)) crossval.jl:1-12: nb folds of k test points each out of one shuffle of 1:n
+    (1-based point labels in the reference; 0-based indices here).  Note the reference's training set of fold i:
+    every entry nsh[j] whose POSITION j is not in the fold's position range."""
+    nb = n // k if nb is None else nb
+    nsh = (rng or np.random.default_rng()).permutation(n)
+    trn, tst = [], []
+    for i in range(nb):
+        idx = np.arange(i * k, (i + 1) * k)
+        tst.append(nsh[idx])
+        trn.append(np.delete(nsh, idx))
+    return trn, tst
+
+
+def cv_step(md, cost, xtr, ytr, xtst, ytst):
+    """cv_step / cv_step! crossval.jl:37-50: refit the cache on the training part, dense predictive covariance on the
+    test part, M-estimator loss."""
+    mdt = GPRModel(md.covar, md.params, xtr, ytr)
+    yp, Sp = predict(mdt, xtst, diagonal_var=False)
+    return cost(ytst, yp, Sp)
+
+
+def cv_batch(md, cost, x, y, cvset):
+    """cv_batch crossval.jl:14-35"""
+    trn, tst = cvset
+    return np.array([cv_step(md, cost, x[:, trn[i]], y[trn[i]], x[:, tst[i]], y[tst[i]]) for i in range(len(trn))])
+
+
+# --------------------------------------------------------------------------- update_model.jl
+def bfgs_hessian(Bi, s, t, rho=None):
+    """bfgs_hessian update_model.jl:50-54 (inverse-Hessian BFGS update)"""
+    rho = 1.0 / float(s @ t) if rho is None else rho
+    n = len(s)
+    Bi = np.eye(n) if Bi is None else Bi
+    C = np.eye(n) - rho * np.outer(s, t)
+    B = C @ Bi @ C.T + rho * np.outer(s, s)
+    return 0.5 * (B + B.T)
+
+
+def bfgs_quad_(theta, JJ, B, gradL, eps, max_iter=100):
+    """bfgs_quad! update_model.jl:64-79: quasi-Newton steps with unit step length; theta, JJ, B updated in place"""
+    it = 0
+    while np.linalg.norm(JJ) > eps and it < max_iter:
+        s = theta.copy()
+        t = JJ.copy()
+        theta -= B @ JJ
+        JJ[...] = gradL(theta)
+        s = theta - s
+        t = JJ - t
+        B[...] = bfgs_hessian(B, s, t)
+        it += 1
+    return it
+
+
+def bfgs_quad(xx, JJ, HH, jac, eps=1e-5, max_iter=100):
+    """bfgs_quad update_model.jl:56-62.  HH: start Hessian (None = identity, the reference passes `I`)."""
+    n = len(xx)
+    x0, J0 = np.array(xx, dtype=np.float64), np.array(JJ, dtype=np.float64)
+    B = np.eye(n) if HH is None else np.linalg.inv(HH)
+    it = bfgs_quad_(x0, J0, B, jac, eps, max_iter)
+    return x0, J0, np.linalg.inv(B), it
+
+
+def hessian_fd(gradL, x, eps=1e-6):
+    """hessian_fd / hessian_fd! update_model.jl:81-94: forward differences of the gradient, column by column"""
+    n = len(x)
+    H = np.empty((n, n))
+    g0 = gradL(x)
+    for i in range(n):
+        xe = np.array(x, dtype=np.float64)
+        xe[i] += eps
+        H[:, i] = (gradL(xe) - g0) / eps
+    return H
+
+
+def update_sample(md, dy, eps_j=1e-3):
+    """update_sample!(md, dy, BFGSQuad(), MarginalLikelihood(), eps_J) update_model.jl:6-48: y += dy, gradient and
+    finite-difference Hessian of the NLML in log space at the current optimum, quasi-Newton re-optimisation.
+    Returns the number of iterations; md.y and md.params are updated in place."""
+    md.y += dy
+    tc = MllGradCache(md)
+    jac = lambda v: log_loss_grad(v, md, tc, want_f=False)[1]
+    hp = np.log(md.params)
+    J = jac(hp)
+    hess = hessian_fd(jac, hp)
+    Binv = np.linalg.inv(0.5 * (hess + hess.T))      # inv(Hermitian(hess)): Hermitian() reads the upper triangle
+    it = bfgs_quad_(hp, J, Binv, jac, eps_j)
+    md.params[...] = np.exp(hp)
+    return it
+
+
+# --------------------------------------------------------------------------- distributions.jl
+def sample_mvn(cov, hp, x, z, mu=None, shift=1e-7, eps=1e-8):
+    """sample(gp(x, theta)) distributions.jl:20-45: Sigma = kernel(cov, theta, x); cholesky(Sigma .+ 1e-7) -- the shift
+    is broadcast over EVERY entry --; s = L z + mu.  z: standard-normal draws (the reference draws them from
+    Xoshiro(1); they are an input here)."""
+    S = (kernel(cov, hp, x, eps=eps) if is_composed(cov) else kernel_single(cov, hp, x, None, True, eps)) + shift
+    L = sl.cholesky(S, lower=True)
+    out = L @ z
+    return out if mu is None else out + mu

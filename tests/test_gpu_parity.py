@@ -484,3 +484,78 @@ def test_mgpu_rank_count_independence_n8192(gpr):
         tc.close()
         assert abs(F - F1) <= 1e-9 * abs(F1), (G, nb)
         assert grad_err(Gd, G1) <= 1e-9, (G, nb, grad_err(Gd, G1))
+
+
+# ------------------------------------------------------------------ (6) SURVEY.md 8f "next" rows on the device
+def test_update_sample_matches_oracle(gpr):
+    """update_sample!(md, dy, BFGSQuad(), MarginalLikelihood(), eps_J) (src/update_model.jl:6-48, test/test_update.jl:50-76):
+    same number of quasi-Newton iterations and the same re-optimised hyper-parameters as the oracle; the P + 1 gradient
+    evaluations of the finite-difference Hessian spread over two caches (ReplicaGradient) give the same result."""
+    import scipy.optimize as so
+    rng = np.random.default_rng(11)
+    D, N = 3, 120
+    x = rng.random((D, N))
+    hp_true = np.concatenate([[1.0], 1.0 + rng.random(D), [0.05]])
+    y0 = o.sample_mvn((o.SE, o.NOISE), hp_true, x, rng.standard_normal(N))
+    mdo = o.GPRModel((o.SE, o.NOISE), np.ones(D + 2), x, y0.copy())
+    tco = o.MllGradCache(mdo)
+    res = so.minimize(lambda v: o.log_loss_grad(v, mdo, tco), np.zeros(D + 2), jac=True, method="L-BFGS-B", options={"gtol": 1e-6, "ftol": 1e-15})
+    hp_opt = np.exp(res.x)
+    dy = 0.01 * y0 ** 2
+    mdo.params[...] = hp_opt
+    it_o = o.update_sample(mdo, dy.copy(), eps_j=1e-3)
+
+    cov = gpr.SquaredExp() + gpr.WhiteNoise()
+    ll = gpr.MarginalLikelihood()
+    md = gpr.GPRModel(cov, hp_opt.copy(), x, y0.copy())
+    it = gpr.update_sample_(md, dy.copy(), gpr.BFGSQuad(), ll, 1e-3)
+    assert it == it_o and it < 10
+    np.testing.assert_allclose(md.params, mdo.params, rtol=1e-6)
+    np.testing.assert_allclose(md.y, y0 + dy)
+    Gl = np.empty(D + 2)
+    tc = gpr.MllGradCache(md)
+    gpr.log_loss_grad_(ll, None, Gl, np.log(md.params), md, tc)
+    assert np.linalg.norm(Gl) < 1e-3
+
+    # low-level form with a second cache as a replica for the Hessian evaluations
+    md2 = gpr.GPRModel(cov, hp_opt.copy(), x, y0.copy())
+    tc2, rep = gpr.MllGradCache(md2), gpr.MllGradCache(md2, ctx=gpr.Context(0))
+    uc = gpr.BFGSQuadCache(md2)
+    it2 = gpr.update_sample_(md2, dy.copy(), ll, uc, tc2, 1e-3, replicas=[rep])
+    assert it2 == it
+    np.testing.assert_allclose(md2.params, md.params, rtol=1e-9)
+    for c in (tc, tc2, rep):
+        c.close()
+
+
+@pytest.mark.parametrize("cost_name", ["MSE", "ChiSq", "Mahalanobis"])
+def test_cv_batch_matches_oracle(gpr, cost_name):
+    """cv_batch / cv_step! (src/crossval.jl:14-50): per fold refit + dense predictive covariance + M-estimator."""
+    rng = np.random.default_rng(21)
+    D, N, k = 2, 150, 10
+    x = rng.random((D, N))
+    y = np.sin(4 * x).sum(0) + 0.05 * rng.standard_normal(N)
+    hp = np.array([1.0, 2.0, 1.5, 0.1])
+    cvset = gpr.kfoldcv(N, k, 5, rng=np.random.default_rng(3))
+    md = gpr.GPRModel(gpr.SquaredExp() + gpr.WhiteNoise(), hp, x, y)
+    lss = gpr.cv_batch(md, getattr(gpr, cost_name)(), x, y, cvset)
+    cost_o = {"MSE": o.loss_mse, "ChiSq": o.loss_chisq, "Mahalanobis": o.loss_mahalanobis}[cost_name]
+    lss_o = o.cv_batch(o.GPRModel((o.SE, o.NOISE), hp, x, y), cost_o, x, y, cvset)
+    np.testing.assert_allclose(lss, lss_o, rtol=1e-7)
+    one = gpr.cv_step(md, getattr(gpr, cost_name)(), x[:, cvset[0][2]], y[cvset[0][2]], x[:, cvset[1][2]], y[cvset[1][2]])
+    assert one == pytest.approx(lss_o[2], rel=1e-7)
+
+
+@pytest.mark.parametrize("cov,D,N", [((o.SE, o.NOISE), 2, 300), ((o.SE, o.SE, o.NOISE), 5, 1000), ((o.SE,), 3, 129)])
+def test_sample_prior_matches_oracle(gpr, cov, D, N):
+    """sample(gp(x, theta)) (src/distributions.jl:20-45) with the same normal draws: Sigma .+ 1e-7 on every entry."""
+    rng = np.random.default_rng(N)
+    x = rng.random((D, N))
+    hp = 0.5 + rng.random(o.dim_hp(cov, D))
+    z = rng.standard_normal(N)
+    covo = cov if len(cov) > 1 else cov[0]
+    gp = gpr.GaussianProcess(lambda col: float(np.sum(col)), to_gpr_cov(gpr, covo))
+    s = gpr.sample(gp, x, hp, z=z)
+    ref = o.sample_mvn(covo, hp, x, z, mu=x.sum(0))
+    cond = np.linalg.cond(o.kernel(cov, hp, x) if len(cov) > 1 else o.kernel_single(cov[0], hp, x, None, True, 1e-8))
+    assert np.abs(s - ref).max() <= ctol(1e-10, cond) * max(1.0, np.abs(ref).max()), (np.abs(s - ref).max(), cond)
