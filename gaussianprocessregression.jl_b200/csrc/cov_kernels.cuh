@@ -504,4 +504,48 @@ __global__ void split_assemble_kernel(double* __restrict__ out, long long ldo, c
   }
 }
 
+// ---------------------------------------------------------------------------
+// Analytic integration of the posterior over a box (noise-free path):
+//   k1[j] = sigma^2 (sqrt(pi)/2)^D prod_i (1/l_i) * prod_i erf(l_i (a_i - x_ij), l_i (b_i - x_ij))
+// (antideriv!, /root/reference/src/integrate.jl:15-31).  erf(x, y) = erf(y) - erf(x) evaluated the way
+// SpecialFunctions.jl does (erfc differences when both arguments lie on the same side, no cancellation).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double erf_between(double x, double y) {
+  const double r = 0.70710678118654752440;
+  if (fabs(x) <= r && fabs(y) <= r) return erf(y) - erf(x);
+  if (x >= 0.0 && y >= 0.0) return erfc(x) - erfc(y);
+  if (x <= 0.0 && y <= 0.0) return erfc(-y) - erfc(-x);
+  return erf(y) - erf(x);
+}
+
+// hp: [sigma, l_1..l_D] (the first D + 1 hyper-parameters of the model, as the reference reads them); k1 has np
+// entries, those >= n are set to zero (padding of the factor).
+__global__ void antideriv_se_kernel(const double* __restrict__ x, int D, long long n, long long np, const double* __restrict__ hp,
+                                    const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ k1) {
+  const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (j >= np) return;
+  if (j >= n) { k1[j] = 0.0; return; }
+  double prefac = hp[0] * hp[0], v = 1.0;
+  for (int i = 0; i < D; ++i) {
+    const double l = hp[1 + i], xij = x[i + j * D];
+    prefac *= 0.88622692545275801365 / l;
+    v *= erf_between(l * (a[i] - xij), l * (b[i] - xij));
+  }
+  k1[j] = v * prefac;
+}
+
+// out[0] = sum_i v[i]^2 over n entries; one CTA, fixed order
+__global__ void __launch_bounds__(1024, 1) sumsq_kernel(const double* __restrict__ v, long long n, double* __restrict__ out) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += v[i] * v[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
 }  // namespace gpr

@@ -1063,6 +1063,59 @@ int gpr_split_predict(gpr_model* m, const double* xe, int64_t ne, const double* 
 }
 
 // ---------------------------------------------------------------------------
+// analytic integration over a box (src/integrate.jl, noise-free path)
+// ---------------------------------------------------------------------------
+int gpr_integrate(gpr_model* m, const double* a, const double* b, double* Iout, double* var_out) {
+  if (!m) return GPR_ERR_ARG;
+  gpr_ctx* ctx = m->ctx;
+  if (!a || !b || !Iout) return fail(ctx, GPR_ERR_ARG, "NULL argument");
+  if (!m->have_factor || m->factor_destroyed) return fail(ctx, GPR_ERR_STATE, "integrate: call gpr_update_cache first");
+  if (m->spec.type[0] == KT_NOISE) return fail(ctx, GPR_ERR_UNSUPPORTED, "integrate: the first component must be a SquaredExp (antideriv!, src/integrate.jl:15)");
+  CK(cudaSetDevice(ctx->device));
+  const int D = m->D;
+  const int64_t N = m->N, Np = m->Np;
+  int rc = ensure(ctx, m->w_part, (size_t)Np + 2 * D + 2 + m->nyp);
+  if (rc) return rc;
+  double* d_k1 = m->w_part.p;
+  double* d_ab = d_k1 + Np;            // a[D], b[D]
+  double* d_sq = d_ab + 2 * D;         // |U^-T k1|^2
+  double* d_I = d_sq + 2;              // nyp
+  CK(cudaMemcpyAsync(d_ab, a, sizeof(double) * D, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ab + D, b, sizeof(double) * D, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_I, 0, sizeof(double) * m->nyp, ctx->stream));
+  antideriv_se_kernel<<<(unsigned)((Np + 255) / 256), 256, 0, ctx->stream>>>(m->d_x, D, N, Np, m->d_hp, d_ab, d_ab + D, d_k1);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CudaBE be{ctx};
+  be.gemv('T', m->nyp, Np, 1.0, m->d_wt, Np, d_k1, d_I);          // Iout = wt' * k1   (mean_integ_impl!, :118-121)
+  std::vector<double> hI((size_t)m->ny);
+  CK(cudaMemcpyAsync(hI.data(), d_I, sizeof(double) * m->ny, cudaMemcpyDeviceToHost, ctx->stream));
+  double hsq = 0.0;
+  if (var_out) {
+    Blocked<CudaBE> blk(be, m->d_dinv);
+    blk.trsv_LUT(m->d_U, Np, Np, 0, d_k1, 1.0);                     // ldiv!(kchol.L, tt), L = U^T   (:133-134)
+    sumsq_kernel<<<1, 1024, 0, ctx->stream>>>(d_k1, Np, d_sq);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&hsq, d_sq, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  rc = check_pending(ctx, "gpr_integrate");
+  if (rc) return rc;
+  for (int e = 0; e < m->ny; ++e) Iout[e] = hI[e];
+  if (var_out) {
+    // antideriv2 (src/integrate.jl:33-41): sigma^2 prod_i erf_integ(l_i, a_i, b_i)
+    double k2 = m->hp_host[0] * m->hp_host[0];
+    for (int i = 0; i < D; ++i) {
+      const double w = m->hp_host[1 + i], d = b[i] - a[i];
+      k2 *= 1.0 / (w * w) * (std::exp(-(w * d) * (w * d)) - 1.0) + 2.0 * (0.88622692545275801365 / w) * d * std::erf(w * d);
+    }
+    var_out[0] = k2 - hsq;
+  }
+  return GPR_OK;
+}
+
+// ---------------------------------------------------------------------------
 // prior sampling (src/distributions.jl)
 // ---------------------------------------------------------------------------
 int gpr_sample_mvn(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, const double* hp, const double* x, int64_t N,

@@ -11,4 +11,5 @@ from .api import (Cmap, ComposedKernel, Diagonal, Euclidean, GPRModel, GPRPredic
                   loss_cache, loss_grad_, loss_grad_cache, predict, predict_, predict_cache, predict_mean,
                   predict_mean_, rm_noise, split, train, update_cache_, MSE, ChiSq, Mahalanobis, m_loss, kfoldcv, cv_step,
                   cv_step_, cv_batch, BFGSQuad, BFGSQuadCache, updater_cache, bfgs_hessian, bfgs_quad, bfgs_quad_,
-                  hessian_fd, hessian_fd_, ReplicaGradient, update_sample_, GaussianProcess, NormalDistribution, sample)
+                  hessian_fd, hessian_fd_, ReplicaGradient, update_sample_, GaussianProcess, NormalDistribution, sample, gauss_integ, erf_integ,
+                  antideriv2, integrate)

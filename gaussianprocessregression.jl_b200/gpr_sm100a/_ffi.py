@@ -55,6 +55,7 @@ _SIGS = {
     "gpr_split_kernel": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _dp, _dp, _i64, _dp, _i64, _dp, _i64, _dp, _dp, _dp]),
     "gpr_split_predict": (C.c_int, [_vp, _dp, _i64, _dp, _i64, _i64, _i64, _dp, _dp]),
     "gpr_timings": (C.c_int, [_vp, _dp, C.c_int]),
+    "gpr_integrate": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
     "gpr_sample_mvn": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _dp, _dp, _i64, C.c_double, _dp, _dp, _dp, C.POINTER(_i64)]),
     "gpr_dbg_dgemm": (C.c_int, [_vp, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _i64, _dp, _i64,
                                 C.c_double, _dp, _i64, C.c_int, C.c_int, _dp]),
@@ -279,6 +280,15 @@ class ModelHandle:
         lo, hi = (1, 0) if var_range is None else (int(var_range[0]), int(var_range[1]))
         self.ctx.check(lib().gpr_split_predict(self.handle, dptr(xe), ne, dptr(xq), nq, lo, hi, dptr(mean), dptr(var)))
         return mean, var
+
+    def integrate(self, a, b, want_var=True):
+        a, b = f64(np.asarray(a, dtype=np.float64).ravel()), f64(np.asarray(b, dtype=np.float64).ravel())
+        if a.size != self.D or b.size != self.D:
+            raise GPRError("integration bounds must have one entry per input dimension")
+        Iout = np.empty(self.ny)
+        var = np.empty(1) if want_var else None
+        self.ctx.check(lib().gpr_integrate(self.handle, dptr(a), dptr(b), dptr(Iout), dptr(var)))
+        return Iout, var
 
     def timings(self):
         ms = np.zeros(T_COUNT)

@@ -873,3 +873,56 @@ def sample(dist_or_gp, *args, rng=None, z=None, ctx=None):
     if z is None:
         z = (rng or np.random.default_rng(1)).standard_normal(n)
     return _ffi.sample_mvn(ctx or get_context(), _types(N.cov), N.x.shape[0], N.θ, N.x, z, N.μ, 1e-7)
+
+
+# --------------------------------------------------------------------------- integrate.jl (noise-free path)
+_RT_PI_BY_2 = 0.5 * np.sqrt(np.pi)
+
+
+def _erf2(x, y):
+    """SpecialFunctions.erf(x, y) = erf(y) - erf(x) without cancellation"""
+    import scipy.special as sp
+    x, y = np.broadcast_arrays(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64))
+    r = 1.0 / np.sqrt(2.0)
+    small = (np.abs(x) <= r) & (np.abs(y) <= r)
+    out = sp.erf(y) - sp.erf(x)
+    out = np.where((x >= 0) & (y >= 0) & ~small, sp.erfc(x) - sp.erfc(y), out)
+    out = np.where((x <= 0) & (y <= 0) & ~small, sp.erfc(-y) - sp.erfc(-x), out)
+    return out
+
+
+def gauss_integ(xs, w, a, b):
+    """gauss_integ(xs, w, a, b)  (src/integrate.jl:4-5)"""
+    return (1.0 / w) * _RT_PI_BY_2 * _erf2(w * (a - xs), w * (b - xs))
+
+
+def erf_integ(w, a, b):
+    """erf_integ(w, a, b)  (src/integrate.jl:6-7)"""
+    import scipy.special as sp
+    return 1.0 / (w ** 2) * (np.exp(-(w * (b - a)) ** 2) - 1.0) + 2.0 * (_RT_PI_BY_2 / w) * (b - a) * sp.erf(w * (b - a))
+
+
+def antideriv2(cov, hp, a, b):
+    """antideriv2(::SquaredExp, hp, a, b)  (src/integrate.jl:33-41)"""
+    dim = len(a)
+    ls = np.asarray(hp[1:dim + 1], dtype=np.float64)
+    return float(np.prod(erf_integ(ls, np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64))) * hp[0] ** 2)
+
+
+def integrate(md, *args, sample_noise=None, ctx=None):
+    """integrate(md, a, b; sample_noise) | integrate(md, hp, a, b; sample_noise)  (src/integrate.jl:45-62):
+    mean and variance of the integral of the posterior over the box [a, b].  Returns (Iout[ny], var_Iout[1]).
+    Only the Cholesky path (sample_noise = nothing) is on the device; the per-sample-noise path of the reference needs a
+    symmetric eigendecomposition (LAPACK syevr, :72-80) and is not built."""
+    if sample_noise is not None:
+        raise GPRError("integrate: the sample_noise (eigendecomposition) path is not built; only sample_noise = nothing")
+    if len(args) == 2:
+        hp, (a, b) = md.params, args
+    else:
+        hp, a, b = args
+    wc = MllLossCache(md, ctx)
+    try:
+        update_cache_(wc, hp, md)
+        return wc.handle.integrate(a, b, want_var=True)
+    finally:
+        wc.close()

@@ -149,6 +149,13 @@ int gpr_split_predict(gpr_model* model, const double* xe, int64_t ne, const doub
 
 int gpr_timings(gpr_model* model, double* ms, int n);
 
+/* integrate!(Iout, var_Iout, md, hp, a, b, nothing, wc, ac): src/integrate.jl:56-62,103-143 (row f-3 of SURVEY.md 8f,
+ * the noise-free path; the per-sample-noise path needs a symmetric eigensolver and is not built).
+ * Requires gpr_update_cache (K factored, wt = K^-1 y for all columns).  a, b: D box bounds.
+ * Iout[e] = wt[:, e]^T k1 (e < ny), k1 = antideriv!(SquaredExp(), x, hp, a, b) (:15-31, reads hp[1..D+1] of the model);
+ * var_out[0] = antideriv2(hp, a, b) - |U^-T k1|^2 (:33-41,131-136). */
+int gpr_integrate(gpr_model* model, const double* a, const double* b, double* Iout, double* var_out);
+
 /* sample(gp(x, theta)) / sample(::NormalDistribution): src/distributions.jl:20-45 (row f-5 of SURVEY.md 8f).
  * Sigma = kernel(cov, theta, x) .+ shift  -- the reference adds 1e-7 to EVERY entry, not to the diagonal --
  * factored as Sigma = L L^T; out = L z + mu.  z: N standard-normal draws supplied by the caller (the Xoshiro

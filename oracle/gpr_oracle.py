@@ -529,3 +529,68 @@ def sample_mvn(cov, hp, x, z, mu=None, shift=1e-7, eps=1e-8):
     L = sl.cholesky(S, lower=True)
     out = L @ z
     return out if mu is None else out + mu
+
+
+# --------------------------------------------------------------------------- integrate.jl
+_RT_PI_BY_2 = math.sqrt(math.pi) * 0.5
+
+
+def erf2(x, y):
+    """SpecialFunctions.erf(x, y) = erf(y) - erf(x), evaluated without cancellation (erfc differences when both
+    arguments lie on the same side), as SpecialFunctions.jl does."""
+    import scipy.special as sp
+    x, y = np.broadcast_arrays(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64))
+    r = 1.0 / math.sqrt(2.0)
+    out = sp.erf(y) - sp.erf(x)
+    pos = (x >= 0) & (y >= 0) & ~((np.abs(x) <= r) & (np.abs(y) <= r))
+    neg = (x <= 0) & (y <= 0) & ~((np.abs(x) <= r) & (np.abs(y) <= r))
+    out = np.where(pos, sp.erfc(x) - sp.erfc(y), out)
+    out = np.where(neg, sp.erfc(-y) - sp.erfc(-x), out)
+    return out
+
+
+def gauss_integ(xs, w, a, b):
+    """gauss_integ(xs, w, a, b) integrate.jl:4-5: integral of exp(-w^2 (x - xs)^2) over [a, b]"""
+    return (1.0 / w) * _RT_PI_BY_2 * erf2(w * (a - xs), w * (b - xs))
+
+
+def erf_integ(w, a, b):
+    """erf_integ integrate.jl:6-7: integral over [a, b] of gauss_integ(x, w, a, b)"""
+    import scipy.special as sp
+    return 1.0 / (w ** 2) * (np.exp(-(w * (b - a)) ** 2) - 1.0) + 2.0 * (_RT_PI_BY_2 / w) * (b - a) * sp.erf(w * (b - a))
+
+
+def antideriv(xs, hp, a, b):
+    """antideriv!(integ, SquaredExp(), xs, hp, a, b) integrate.jl:15-31"""
+    nl = xs.shape[0]
+    ls = np.asarray(hp[1:nl + 1])
+    prefac = hp[0] ** 2 * _RT_PI_BY_2 ** nl * np.prod(1.0 / ls)
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return prefac * np.prod(erf2(ls[:, None] * (a[:, None] - xs), ls[:, None] * (b[:, None] - xs)), axis=0)
+
+
+def antideriv2(hp, a, b):
+    """antideriv2(SquaredExp(), hp, a, b) integrate.jl:33-41"""
+    dim = len(a)
+    ls = np.asarray(hp[1:dim + 1])
+    return float(np.prod(erf_integ(ls, np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64))) * hp[0] ** 2)
+
+
+def integrate(md, hp, a, b, sample_noise=None, eps=1e-8):
+    """integrate(md, hp, a, b; sample_noise) integrate.jl:50-62,103-160.  Returns (Iout[ny], var_Iout).
+    sample_noise None: Cholesky path, var_Iout[0] only (:131-136).  scalar / vector noise: eigen path (:72-80,145-160)."""
+    K = kernel(md.covar, hp, md.x, eps=eps) if is_composed(md.covar) else kernel_single(md.covar, hp, md.x, None, True, eps)
+    Y = md.y.reshape(md.y.shape[0], -1)
+    k1 = antideriv(md.x, hp, a, b)
+    k2 = antideriv2(hp, a, b)
+    if sample_noise is None:
+        U = sl.cholesky(K, lower=False)
+        wt = sl.cho_solve((U, False), Y)
+        tt = sl.solve_triangular(U, k1, trans="T", lower=False)
+        return wt.T @ k1, np.array([k2 - float(tt @ tt)])
+    lam, P = np.linalg.eigh(K)
+    noise = np.atleast_1d(np.asarray(sample_noise, dtype=np.float64))
+    Dm = 1.0 / (lam[:, None] + noise[None, :])                  # inverse_diagonal_update!  (:82-100)
+    wt = P @ (Dm * (P.T @ Y))
+    t2 = (P.T @ k1) ** 2
+    return wt.T @ k1, k2 - (1.0 / (lam[None, :] + noise[:, None])) @ t2

@@ -559,3 +559,40 @@ def test_sample_prior_matches_oracle(gpr, cov, D, N):
     ref = o.sample_mvn(covo, hp, x, z, mu=x.sum(0))
     cond = np.linalg.cond(o.kernel(cov, hp, x) if len(cov) > 1 else o.kernel_single(cov[0], hp, x, None, True, 1e-8))
     assert np.abs(s - ref).max() <= ctol(1e-10, cond) * max(1.0, np.abs(ref).max()), (np.abs(s - ref).max(), cond)
+
+
+@pytest.mark.parametrize("dim,n,ny", [(1, 100, 1), (3, 300, 4), (4, 700, 1)])
+def test_integrate_matches_oracle(gpr, dim, n, ny):
+    """integrate(md, hp, a, b) (src/integrate.jl:45-62,103-136, noise-free path): mean and variance of the box integral."""
+    rng = np.random.default_rng(dim * 1000 + n)
+    x = rng.random((dim, n))
+    y = rng.random((n, ny)) if ny > 1 else rng.random(n)
+    hp = np.concatenate([[1.2], 0.8 + 2.0 * rng.random(dim), [0.05]])
+    a = -0.2 + 0.4 * rng.random(dim)
+    b = a + 0.5 + rng.random(dim)
+    md = gpr.GPRModel(gpr.SquaredExp() + gpr.WhiteNoise(), hp, x, y)
+    mu, var = gpr.integrate(md, hp, a, b)
+    mu_o, var_o = o.integrate(o.GPRModel((o.SE, o.NOISE), hp, x, y), hp, a, b)
+    np.testing.assert_allclose(mu, mu_o, rtol=1e-8, atol=1e-8 * np.abs(mu_o).max())
+    assert abs(var[0] - var_o[0]) <= 1e-8 * o.antideriv2(hp, a, b)
+    with pytest.raises(gpr.GPRError):
+        gpr.integrate(md, a, b, sample_noise=np.zeros(max(ny, 1)))
+
+
+def test_integrate_agrees_with_quadrature_of_the_posterior_mean(gpr):
+    """Property (no oracle): the analytic integral of the posterior mean equals Gauss-Legendre quadrature of
+    predict_mean over the box (cf. test/test_integrate.jl:164-177)."""
+    rng = np.random.default_rng(6)
+    dim, n = 2, 400
+    x = rng.random((dim, n))
+    y = np.sin(x.prod(0)) ** 2
+    hp = np.array([1.0, 1.5, 1.5, 0.01])
+    md = gpr.GPRModel(gpr.SquaredExp() + gpr.WhiteNoise(), hp, x, y)
+    mu, var = gpr.integrate(md, np.zeros(dim), np.ones(dim))
+    xg, wg = np.polynomial.legendre.leggauss(24)
+    xg, wg = 0.5 * (xg + 1), 0.5 * wg
+    grid = np.asfortranarray(np.stack(np.meshgrid(xg, xg, indexing="ij")).reshape(2, -1))
+    W = np.outer(wg, wg).ravel()
+    pm = gpr.predict_mean(md, grid)
+    assert mu[0] == pytest.approx(float(W @ pm), rel=1e-9)
+    assert var[0] >= -1e-10

@@ -135,3 +135,54 @@ def test_oracle_sample_mvn_covariance():
     assert np.allclose(np.triu(Lcols, 1), 0.0)
     mu = rng.random(30)
     np.testing.assert_allclose(o.sample_mvn((o.SE, o.NOISE), hp, x, np.zeros(30), mu), mu)
+
+
+def test_gaussian_integrals_against_quadrature(api):
+    """test/test_integrate.jl:3-21: closed forms vs numerical quadrature (scipy.integrate.quad for QuadGK)."""
+    import scipy.integrate as si
+    rng = np.random.default_rng(8)
+    for _ in range(25):
+        xs, w = 3.0 * rng.random(), 0.05 + 3.0 * rng.random()
+        a, b = -3.0 + 6 * rng.random(), -3.0 + 6 * rng.random()
+        q1 = si.quad(lambda t: np.exp(-w ** 2 * (t - xs) ** 2), a, b, epsrel=1e-10)[0]
+        for gi, ei in ((api.gauss_integ, api.erf_integ), (o.gauss_integ, o.erf_integ)):
+            assert float(gi(xs, w, a, b)) == pytest.approx(q1, rel=1e-8, abs=1e-12)
+            q2 = si.quad(lambda t: float(gi(t, w, a, b)), a, b, epsrel=1e-10)[0]
+            assert float(ei(w, a, b)) == pytest.approx(q2, abs=1e-5)
+
+
+@pytest.mark.parametrize("dim,n", [(2, 100), (3, 300), (5, 500)])
+def test_antiderivative_product_form(dim, n):
+    """test/test_integrate.jl:23-37"""
+    rng = np.random.default_rng(dim * n)
+    xs = rng.random((dim, n))
+    hp = 0.05 + 5.0 * rng.random(dim + 1)
+    a = -2 + 4 * rng.random(dim)
+    b = a + 2.0 * rng.random(dim)
+    w = hp[1:dim + 1]
+    integ = hp[0] ** 2 * np.prod(o.gauss_integ(xs, w[:, None], a[:, None], b[:, None]), axis=0)
+    np.testing.assert_allclose(o.antideriv(xs, hp, a, b), integ, rtol=1e-12)
+
+
+def test_oracle_integration_noise_paths_agree():
+    """test/test_integrate.jl:118-161: zero sample noise reproduces the Cholesky path; vector noise matches per-column
+    refactorization."""
+    rng = np.random.default_rng(4)
+    dim, n, k = 2, 120, 5
+    x = rng.random((dim, n))
+    y = rng.random((n, k))
+    hp = np.array([1.0, 1.5, 0.8])
+    md = o.GPRModel(o.SE, hp, x, y)
+    a, b = np.zeros(dim), np.ones(dim)
+    mu, var = o.integrate(md, hp, a, b, None, eps=1e-6)
+    mu0, var0 = o.integrate(md, hp, a, b, np.zeros(k), eps=1e-6)
+    np.testing.assert_allclose(mu0, mu, rtol=1e-5)
+    np.testing.assert_allclose(var0, var[0], rtol=1e-4, atol=1e-9)
+    noise = 1e-3 * (1 + rng.random(k))
+    mun, varn = o.integrate(md, hp, a, b, noise)
+    K = o.kernel_single(o.SE, hp, x, None, True, 1e-8)
+    k1, k2 = o.antideriv(x, hp, a, b), o.antideriv2(hp, a, b)
+    for i in range(k):
+        Kn = K + noise[i] * np.eye(n)
+        assert mun[i] == pytest.approx(float(np.linalg.solve(Kn, y[:, i]) @ k1), rel=1e-6)
+        assert varn[i] == pytest.approx(k2 - float(k1 @ np.linalg.solve(Kn, k1)), rel=1e-5, abs=1e-10)
