@@ -56,7 +56,7 @@ enum GemmFlags : int {
   // jt of C stands for the GLOBAL tile column gt = col_gtile[jt].
   GEMM_MAP_UPPER = 8,    // only elements with (row_gtile0 + tile row, row in tile) <= (gt, col in tile) exist
   GEMM_MAP_KUPTO = 16,   // the tile column contracts over k < (gt - k_gtile0 + 1) * 128 only
-  GEMM_MAP_BROWS = 32,   // (transB = 'T') the B rows of the tile column start at gt * 128
+  GEMM_MAP_BROWS = 32,   // the op(B) columns of the tile column start at gt * 128 instead of at the local column
 };
 
 struct GemmParams {
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
   const long long m0 = (long long)tile_m * GEMM_BM, n0 = (long long)tile_n * BN;
   const long long bz = blockIdx.z;
   const double* Ap = p.A + bz * p.sA + (A_KC ? m0 * p.lda : m0);
-  const double* Bp = p.B + bz * p.sB + (B_KC ? n0 * p.ldb : ((p.flags & GEMM_MAP_BROWS) ? (long long)gt * 128 + (n0 & 127) : n0));
+  const long long nB = (p.flags & GEMM_MAP_BROWS) ? (long long)gt * 128 + (n0 & 127) : n0;   // first op(B) column of this tile
+  const double* Bp = p.B + bz * p.sB + (B_KC ? nB * p.ldb : nB);
   const int kt0 = (p.flags & GEMM_K_FROM_N) ? blk_n * (128 / GEMM_BK) : 0;   // first k-tile of this tile
 
   double acc[MI][4][2];

@@ -38,7 +38,7 @@
 //        flags: BLK_MAP_UPPER  element (m, n) exists iff (map.row_gtile0 + m/128, m%128) <= (gt(n), n%128),
 //                              gt(n) = map.col_gtile[n / 128]  (global 128-tile column of local tile n/128)
 //               BLK_MAP_KUPTO  column tile contracts over k < (gt(n) - map.k_gtile0 + 1) * 128 only
-//               BLK_MAP_BROWS  (tB = 'T') rows of B for column tile n/128 start at gt(n) * 128 instead of n
+//               BLK_MAP_BROWS  the op(B) columns of column tile n/128 start at gt(n) * 128 instead of n
 //     be.activate()          select the rank's device
 //     be.fork() / be.join()  side queue waits for everything queued on the main queue so far / vice versa
 //     be.side(on)            route the following launches (and the rank's part of collectives) to the side queue
@@ -46,7 +46,8 @@
 //   selects one of the two panel / Ukk buffers):
 //     comm.bcast_diag(k, with_owner, b)   Ukk[b] (nb x nb, ld nb) and dinv blocks k*tpb.. <- owner's diagonal block k
 //     comm.gather_rowpanel(k, b)          panel[b][p + ((J-k-1)*nb + c)*nb] <- U(k*nb + p, J*nb + c), J = k+1 .. nblk-1
-//     comm.bcast_colpanel(k, b)           panel[b][i + c*Np] <- L_owner(i, block k col c), i < (k+1)*nb
+//     comm.bcast_colpanel(k, b)           panel[b][c + i*nb] <- L_owner(i, block k col c), i < (k+1)*nb  (TRANSPOSED: both
+//                                         operands of the lauum update are then contraction-contiguous, the fastest GEMM form)
 //     comm.barrier()                      every rank's main-queue work so far is ordered before every rank's later
 //                                         main-queue work
 //   The collectives themselves do not synchronise: the drivers place a barrier between producing a block on
@@ -244,7 +245,7 @@ struct DistBlocked {
 
   // L(upper) <- W W^T (matrix columns only)
   void lauum() {
-    const int64_t nb = lay.nb, Np = lay.Np;
+    const int64_t nb = lay.nb;
     comm.barrier();
     comm.bcast_colpanel(0, 0);
     for (int64_t k = 0; k < lay.nblk; ++k) {
@@ -264,12 +265,12 @@ struct DistBlocked {
         R.be->activate();
         if (nacc > 0) {
           TileMap map{R.gtile, 0, 0};
-          R.be->gemm_map('N', 'T', Mrows, nacc * nb, nb, 1.0, R.panel[b], Np, R.panel[b], Np, 1.0, R.L, R.ld,
+          R.be->gemm_map('T', 'N', Mrows, nacc * nb, nb, 1.0, R.panel[b], nb, R.panel[b], nb, 1.0, R.L, R.ld,
                          BLK_MAP_UPPER | BLK_MAP_BROWS, map);
         }
         if (R.r == o) {
           TileMap map{R.gtile + (cnt - 1) * lay.tpb(), 0, 0};
-          R.be->gemm_map('N', 'T', Mrows, nb, nb, 1.0, R.panel[b], Np, R.panel[b], Np, 0.0, R.L + (cnt - 1) * nb * R.ld, R.ld,
+          R.be->gemm_map('T', 'N', Mrows, nb, nb, 1.0, R.panel[b], nb, R.panel[b], nb, 0.0, R.L + (cnt - 1) * nb * R.ld, R.ld,
                          BLK_MAP_UPPER | BLK_MAP_BROWS, map);
         }
       }

@@ -110,6 +110,12 @@ struct CudaBE {
     note(cudaGetLastError());
     ctx->launches++;
   }
+  void transpose_inplace(double* A, int64_t ld, int64_t n) {
+    const int64_t nt = n / 32;
+    transpose_inplace_kernel<<<(unsigned)(nt * (nt + 1) / 2), dim3(32, 8), 0, ctx->stream>>>(A, ld, nt);
+    note(cudaGetLastError());
+    ctx->launches++;
+  }
   void copy_dinv_128(double* dst, int64_t ldd, const double* src, int64_t batch, int64_t stride, int64_t dstride,
                      bool full) {
     copy_dinv_128_kernel<<<(unsigned)batch, 256, 0, ctx->stream>>>(dst, ldd, src, stride, dstride, full ? 1 : 0);
@@ -329,7 +335,8 @@ int form_inverse(gpr_model* m) {
     }
     {
       Scope s(m->tm, GPR_T_LAUUM, ctx->stream);
-      blk.lauum_oop(m->d_W, Np, Np, m->d_Kinv, Np);
+      be.transpose_inplace(m->d_W, Np, Np);
+      blk.lauum_oop_t(m->d_W, Np, Np, m->d_Kinv, Np);
     }
   } else {
     {
@@ -1256,7 +1263,8 @@ int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, 
     if (mode == 3 && e == cudaSuccess) {   // out-of-place inverse: W = U^-1 with clean diagonal blocks, C = W W^T, upper(C) -> upper(A)
       e = cudaMemcpyAsync(dW, dA, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, ctx->stream);
       blk.trtri(dW, Np, Np, 0, true);
-      blk.lauum_oop(dW, Np, Np, dC, Np);
+      be.transpose_inplace(dW, Np, Np);
+      blk.lauum_oop_t(dW, Np, Np, dC, Np);
     } else {
       if (mode >= 1) blk.trtri(dA, Np, Np, 0);
       if (mode >= 2) blk.lauum(dA, Np, Np, 0);

@@ -427,4 +427,31 @@ __global__ void pad_copy_kernel(double* __restrict__ dst, long long ldd, long lo
   }
 }
 
+// A <- A^T in place, n x n column major, n % 32 == 0.  One CTA (32 x 8 threads) per pair of 32 x 32 tiles
+// (bi <= bj, linearised over the upper block triangle); HBM-bound: 16 n^2 bytes.
+__global__ void __launch_bounds__(256) transpose_inplace_kernel(double* __restrict__ A, long long ld, long long nt) {
+  __shared__ double t0[32][33], t1[32][33];
+  long long lin = blockIdx.x;
+  long long bj = (long long)((sqrt(8.0 * (double)lin + 1.0) - 1.0) * 0.5);
+  while (bj * (bj + 1) / 2 > lin) --bj;
+  while ((bj + 1) * (bj + 2) / 2 <= lin) ++bj;
+  const long long bi = lin - bj * (bj + 1) / 2;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  double* P = A + bi * 32 + bj * 32 * ld;   // tile (bi, bj)
+  double* Q = A + bj * 32 + bi * 32 * ld;   // tile (bj, bi)
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = ty + 8 * r;
+    t0[c][tx] = P[tx + (long long)c * ld];
+    if (bi != bj) t1[c][tx] = Q[tx + (long long)c * ld];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = ty + 8 * r;
+    Q[tx + (long long)c * ld] = t0[tx][c];
+    if (bi != bj) P[tx + (long long)c * ld] = t1[tx][c];
+  }
+}
+
 }  // namespace gpr

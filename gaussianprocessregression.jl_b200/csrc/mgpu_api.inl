@@ -20,6 +20,25 @@ __global__ void __launch_bounds__(256) copy2d_kernel(double* __restrict__ dst, l
       reinterpret_cast<double2*>(dst + c * ldd)[p] = reinterpret_cast<const double2*>(src + c * lds)[p];
 }
 
+// dst (cols x rows, ldd) <- transpose of src (rows x cols, lds); rows, cols % 32 == 0.  32 x 8 threads per 32 x 32 tile;
+// src may be peer memory (coalesced 256-byte reads over NVLink, local transposed writes).
+__global__ void __launch_bounds__(256) copy2d_transpose_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src,
+                                                               long long lds, long long row_tiles, long long col_tiles) {
+  __shared__ double t[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (long long lin = blockIdx.x; lin < row_tiles * col_tiles; lin += gridDim.x) {
+    const long long br = lin % row_tiles, bc = lin / row_tiles;
+    const double* S = src + br * 32 + bc * 32 * lds;
+    double* D = dst + bc * 32 + br * 32 * ldd;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) t[ty + 8 * r][tx] = S[tx + (long long)(ty + 8 * r) * lds];   // t[c][r]
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) D[tx + (long long)(ty + 8 * r) * ldd] = t[tx][ty + 8 * r];    // dst(c = tx, r = ty + 8r)
+  }
+}
+
 // Row panel k of the block-cyclic factor, gathered in global column order on the calling rank:
 //   dst[p + ((J-k-1)*nb + c)*nb] = L_{owner(J)}[k*nb + p + ((J/G)*nb + c)*ld],  J = k+1+blockIdx.x
 // (owner(J): snake order of DistLayout::owner)
@@ -101,7 +120,7 @@ struct gpr_mgpu {
   int64_t nb = 1024;
   std::vector<MRank> rk;
   std::string err;
-  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr, tot0 = nullptr, tot1 = nullptr;
 };
 
 namespace {
@@ -168,10 +187,18 @@ struct LocalComm {
       R.ctx->launches++;
     }
   }
-  void bcast_colpanel(int64_t k, int b) {
+  void bcast_colpanel(int64_t k, int b) {   // transposed: panel[b] is nb x (k+1)*nb, ld nb
     const MRank& S = mg->rk[lay.owner(k)];
-    for (int r = 0; r < mg->G; ++r)
-      copy2d(r, mg->rk[r].panel[b], lay.Np, S.L + (k / lay.G) * lay.nb * ld, ld, (k + 1) * lay.nb, lay.nb);
+    const int64_t rows = (k + 1) * lay.nb, cols = lay.nb;
+    for (int r = 0; r < mg->G; ++r) {
+      MRank& R = mg->rk[r];
+      act(r);
+      const int64_t tiles = (rows / 32) * (cols / 32);
+      copy2d_transpose_kernel<<<(unsigned)std::min<int64_t>(tiles, 148 * 16), dim3(32, 8), 0, R.ctx->stream>>>(
+          R.panel[b], cols, S.L + (k / lay.G) * lay.nb * ld, ld, rows / 32, cols / 32);
+      R.be.note(cudaGetLastError());
+      R.ctx->launches++;
+    }
   }
 };
 
@@ -256,7 +283,7 @@ struct gpr_mgpu_model {
   int ncomp = 0, D = 0, P = 0, nk = 0, ny = 1, train_axis = 1;
   int64_t N = 0, Np = 0, nyp = 128;
   MDense md;
-  bool have_inverse = false;
+  bool have_inverse = false, have_alpha = false;
   double ms[GPR_T_COUNT] = {0};
 };
 
@@ -303,6 +330,7 @@ int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** out) 
     }
   cudaSetDevice(devices[0]);
   cudaEventCreate(&mg->t0); cudaEventCreate(&mg->t1);
+  cudaEventCreate(&mg->tot0); cudaEventCreate(&mg->tot1);
   *out = mg;
   return GPR_OK;
 }
@@ -318,6 +346,8 @@ int gpr_mgpu_destroy(gpr_mgpu* mg) {
   }
   if (mg->t0) cudaEventDestroy(mg->t0);
   if (mg->t1) cudaEventDestroy(mg->t1);
+  if (mg->tot0) cudaEventDestroy(mg->tot0);
+  if (mg->tot1) cudaEventDestroy(mg->tot1);
   delete mg;
   return GPR_OK;
 }
@@ -402,9 +432,8 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
     m->ms[slot] += t;
     return GPR_OK;
   };
-  cudaEvent_t tot0, tot1;
+  cudaEvent_t tot0 = mg->tot0, tot1 = mg->tot1;
   cudaSetDevice(mg->rk[0].ctx->device);
-  cudaEventCreate(&tot0); cudaEventCreate(&tot1);
   cudaEventRecord(tot0, mg->rk[0].ctx->stream);
 
   // ---- covariance build into the block-cyclic layout (upper triangle, zero below), y columns
@@ -456,19 +485,29 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
   if (info) *info = h_info;
   m->have_inverse = false;
   if (h_info != 0) {
-    cudaEventDestroy(tot0); cudaEventDestroy(tot1);
     char buf[128];
     snprintf(buf, sizeof buf, "matrix is not positive definite; Cholesky failed at pivot %lld", h_info);
     return mfail(mg, GPR_ERR_NOT_POSDEF, buf);
   }
 
-  // ---- trtri (+ back substitution): W = U^-1 in place, y columns = -alpha
-  tick();
-  db.trtri();
-  { int rc = tock(GPR_T_TRTRI); if (rc) return rc; }
-  tick();
-  {
-    const int yo = lay.y_owner();
+  const int yo = lay.y_owner();
+  if (!G) {
+    // loss only: y^T K^-1 y = |z|^2 with z = U^-T y, which the potrf sweep left in the y columns -- no back
+    // substitution and no inverse needed (alpha is not formed: gpr_mgpu_fetch(ALPHA) then reports a state error)
+    tick();
+    MRank& R = mg->rk[yo];
+    MCK(cudaSetDevice(R.ctx->device));
+    sumsq_kernel<<<1, 1024, 0, R.ctx->stream>>>(R.L + (lay.ycol0(yo) + (m->train_axis - 1)) * ld, N, R.scal + 1);
+    R.ctx->launches++;
+    MCK(cudaGetLastError());
+    m->have_alpha = false;
+    { int rc = tock(GPR_T_POTRS); if (rc) return rc; }
+  } else {
+    // ---- trtri (+ back substitution): W = U^-1 in place, y columns = -alpha
+    tick();
+    db.trtri();
+    { int rc = tock(GPR_T_TRTRI); if (rc) return rc; }
+    tick();
     MRank& R = mg->rk[yo];
     MCK(cudaSetDevice(R.ctx->device));
     const double* X = R.L + (lay.ycol0(yo) + (m->train_axis - 1)) * ld;
@@ -478,8 +517,9 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
     comm.barrier();
     for (int r = 0; r < Gn; ++r)
       if (r != yo) comm.copy2d(r, mg->rk[r].alpha, Np, R.alpha, Np, Np, 1);
+    m->have_alpha = true;
+    { int rc = tock(GPR_T_POTRS); if (rc) return rc; }
   }
-  { int rc = tock(GPR_T_POTRS); if (rc) return rc; }
 
   double Fv = 0.0;
   {
@@ -543,7 +583,6 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
   cudaEventRecord(tot1, mg->rk[0].ctx->stream);
   cudaEventSynchronize(tot1);
   { float t = 0.f; cudaEventElapsedTime(&t, tot0, tot1); m->ms[GPR_T_TOTAL] = t; }
-  cudaEventDestroy(tot0); cudaEventDestroy(tot1);
   return msync_all(mg, "nlml_grad", nullptr);
 }
 
@@ -560,6 +599,7 @@ int gpr_mgpu_fetch(gpr_mgpu_model* m, int which, double* out) {
   const DistLayout& lay = m->md.lay;
   const int64_t N = m->N, nb = lay.nb, ld = m->md.ld;
   if (which == GPR_FETCH_ALPHA) {
+    if (!m->have_alpha) return mfail(mg, GPR_ERR_STATE, "fetch alpha: the last evaluation was loss-only (no back substitution)");
     MRank& R = mg->rk[0];
     MCK(cudaSetDevice(R.ctx->device));
     MCK(cudaMemcpyAsync(out, R.alpha, sizeof(double) * N, cudaMemcpyDeviceToHost, R.ctx->stream));

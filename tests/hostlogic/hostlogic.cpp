@@ -31,7 +31,7 @@ struct CpuBE {
       const int64_t gt = map.col_gtile[n / gpr::LEAF];
       int64_t kend = K;
       if (flags & gpr::BLK_MAP_KUPTO) kend = std::min<int64_t>(K, (gt - map.k_gtile0 + 1) * gpr::LEAF);
-      const int64_t brow = (flags & gpr::BLK_MAP_BROWS) ? gt * gpr::LEAF + n % gpr::LEAF : n;
+      const int64_t brow = (flags & gpr::BLK_MAP_BROWS) ? gt * gpr::LEAF + n % gpr::LEAF : n;   // op(B) column
       for (int64_t m = 0; m < M; ++m) {
         if (flags & gpr::BLK_MAP_UPPER) {
           const int64_t rt = map.row_gtile0 + m / gpr::LEAF;
@@ -40,7 +40,7 @@ struct CpuBE {
         double s = 0.0;
         for (int64_t k = 0; k < kend; ++k) {
           const double a = (tA == 'T') ? A[k + m * lda] : A[m + k * lda];
-          const double b = (tB == 'T') ? B[brow + k * ldb] : B[k + n * ldb];
+          const double b = (tB == 'T') ? B[brow + k * ldb] : B[k + brow * ldb];
           s += a * b;
         }
         tmp[m + n * M] = s;
@@ -122,6 +122,10 @@ struct CpuBE {
     }
     for (int m = 0; m < n; ++m) v[m] = tmp[m];
   }
+  void transpose_inplace(double* A, int64_t ld, int64_t n) {
+    for (int64_t j = 0; j < n; ++j)
+      for (int64_t i = 0; i < j; ++i) std::swap(A[i + j * ld], A[j + i * ld]);
+  }
   void copy_dinv_128(double* dst, int64_t ldd, const double* src, int64_t batch, int64_t stride, int64_t dstride,
                      bool full) {
     for (int64_t z = 0; z < batch; ++z)
@@ -164,7 +168,7 @@ struct CpuComm {
     const auto& S = (*ranks)[lay.owner(k)];
     for (auto& R : *ranks)
       for (int64_t c = 0; c < nb; ++c)
-        for (int64_t i = 0; i < (k + 1) * nb; ++i) R.panel[b][i + c * lay.Np] = S.L[i + ((k / lay.G) * nb + c) * S.ld];
+        for (int64_t i = 0; i < (k + 1) * nb; ++i) R.panel[b][c + i * nb] = S.L[i + ((k / lay.G) * nb + c) * S.ld];
   }
 };
 
@@ -226,11 +230,12 @@ long long hl_factor(double* A, int64_t n, int mode, long long* gemm_calls) {
   std::vector<double> dinv((size_t)n * 128);
   gpr::Blocked<CpuBE> blk(be, dinv.data());
   blk.potrf(A, n, n, 0);
-  if (mode == 3) {   // out-of-place inverse: W = copy of U with clean diagonal blocks, C = W W^T written back to A (upper)
+  if (mode == 3 || mode == 4) {   // out-of-place inverse: W = copy of U with clean diagonal blocks, C = W W^T written back to A (upper)
     std::vector<double> W((size_t)n * n), C((size_t)n * n, 0.0);
     memcpy(W.data(), A, sizeof(double) * n * n);
     blk.trtri(W.data(), n, n, 0, true);
-    blk.lauum_oop(W.data(), n, n, C.data(), n);
+    if (mode == 3) blk.lauum_oop(W.data(), n, n, C.data(), n);
+    else { be.transpose_inplace(W.data(), n, n); blk.lauum_oop_t(W.data(), n, n, C.data(), n); }   // the product path
     for (int64_t j = 0; j < n; ++j)
       for (int64_t i = 0; i <= j; ++i) A[i + j * n] = C[i + j * n];
   } else {

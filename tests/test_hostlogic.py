@@ -33,7 +33,7 @@ def spd(n, seed):
 
 
 @pytest.mark.parametrize("n", [128, 256, 384, 640, 1024])
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_blocked_factor(hl, n, mode):
     K = spd(n, n)
     A = np.asfortranarray(K.copy())
@@ -41,7 +41,7 @@ def test_blocked_factor(hl, n, mode):
     info = hl.hl_factor(dp(A), ctypes.c_int64(n), mode, ctypes.byref(calls))
     assert info == 0
     U = sl.cholesky(K, lower=False)
-    ref = [U, np.linalg.inv(U), np.linalg.inv(K), np.linalg.inv(K)][mode]   # mode 3: out-of-place W W^T
+    ref = [U, np.linalg.inv(U), np.linalg.inv(K), np.linalg.inv(K), np.linalg.inv(K)][mode]   # modes 3, 4: out-of-place W W^T
     np.testing.assert_allclose(np.triu(A), np.triu(ref), rtol=0, atol=1e-12 * np.abs(ref).max())
     # dpotrf('U') semantics: the strict lower triangle keeps K (test/test_loss.jl:46)
     assert np.array_equal(np.tril(A, -1), np.tril(K, -1))
