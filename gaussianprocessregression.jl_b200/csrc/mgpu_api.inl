@@ -54,6 +54,20 @@ __global__ void __launch_bounds__(256) gather_rowpanel_kernel(double* __restrict
       reinterpret_cast<double2*>(D + c * nb)[p] = reinterpret_cast<const double2*>(S + c * ld)[p];
 }
 
+// Row panel pulled by the copy engines arrives rank-major in `stage` (source rank s: its blocks J > k in local order at
+// block offset off[s]); put the blocks into global column order: dst block (J - k - 1) <- stage block off[s] + J/G - first[s].
+struct GatherMap { int off[MGPU_MAX_RANKS]; int first[MGPU_MAX_RANKS]; };
+__global__ void __launch_bounds__(256) unpermute_rowpanel_kernel(double* __restrict__ dst, const double* __restrict__ stage,
+                                                                 const GatherMap gm, int G, long long k, long long nb) {
+  const long long J = k + 1 + blockIdx.x;
+  const int pos = (int)(J % G);
+  const int s = ((J / G) & 1) ? G - 1 - pos : pos;
+  const double2* S = reinterpret_cast<const double2*>(stage + ((long long)gm.off[s] + J / G - gm.first[s]) * nb * nb);
+  double2* D = reinterpret_cast<double2*>(dst + (long long)blockIdx.x * nb * nb);
+  const long long n2 = nb * nb / 2;
+  for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.y * blockDim.x) D[i] = S[i];
+}
+
 // out[0] = sum over the local matrix columns of log(L[gcol(c), c]) (the rank's share of log det U); one CTA.
 __global__ void __launch_bounds__(1024, 1) dist_logdiag_kernel(const double* __restrict__ L, long long ld, long long ncols,
                                                                long long nb, int G, int rank, double* __restrict__ out) {
@@ -106,6 +120,7 @@ struct MRank {
   gpr_ctx* ctx = nullptr;
   CudaBE be{nullptr};
   double *L = nullptr, *dinv = nullptr, *Ukk[2] = {nullptr, nullptr}, *panel[2] = {nullptr, nullptr};
+  double* stage = nullptr;   // landing buffer of the copy-engine pulls (Np * nb doubles)
   int* gtile = nullptr;
   // model part
   double *x = nullptr, *y = nullptr, *hp = nullptr, *alpha = nullptr, *gpart = nullptr, *scal = nullptr;   // scal: [logdiag, y.alpha, tot[P+1]...]
@@ -162,6 +177,17 @@ struct LocalComm {
     R.be.note(cudaGetLastError());
     R.ctx->launches++;
   }
+  // A rank that currently issues to its SIDE queue is prefetching while its main queue runs GEMMs that fill every SM
+  // (2 CTAs x 250 registers): an SM-driven pull would have to take CTA slots away from them and hold them for the
+  // length of an NVLink read (measured on 8 x B200: trtri + 300 ms).  Those transfers therefore go through the copy
+  // engines (cudaMemcpy2DAsync between peers) into a staging buffer; only the cheap local re-layout is a kernel.
+  bool on_side(int r) const { return mg->rk[r].ctx->side_stream && mg->rk[r].ctx->stream == mg->rk[r].ctx->side_stream; }
+  void dma2d(int r, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
+    MRank& R = mg->rk[r];
+    act(r);
+    R.be.note(cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * rows, (size_t)cols,
+                                cudaMemcpyDefault, R.ctx->stream));
+  }
   void bcast_diag(int64_t k, bool with_owner, int b) {
     const int o = lay.owner(k);
     const int64_t nb = lay.nb, kb = k / lay.G;
@@ -169,20 +195,42 @@ struct LocalComm {
     const int64_t dl = (int64_t)lay.tpb() * 128 * 128;
     for (int r = 0; r < mg->G; ++r) {
       if (r == o && !with_owner) continue;
-      copy2d(r, mg->rk[r].Ukk[b], nb, S.L + k * nb + kb * nb * ld, ld, nb, nb);
-      if (r != o) copy2d(r, mg->rk[r].dinv + k * dl, dl, S.dinv + k * dl, dl, dl, 1);
+      if (on_side(r)) {
+        dma2d(r, mg->rk[r].Ukk[b], nb, S.L + k * nb + kb * nb * ld, ld, nb, nb);
+        if (r != o) dma2d(r, mg->rk[r].dinv + k * dl, dl, S.dinv + k * dl, dl, dl, 1);
+      } else {
+        copy2d(r, mg->rk[r].Ukk[b], nb, S.L + k * nb + kb * nb * ld, ld, nb, nb);
+        if (r != o) copy2d(r, mg->rk[r].dinv + k * dl, dl, S.dinv + k * dl, dl, dl, 1);
+      }
     }
   }
   void gather_rowpanel(int64_t k, int b) {
     const int64_t nrem = lay.nblk - k - 1;
     if (nrem <= 0) return;
+    const int64_t nb = lay.nb;
     PeerPtrs pp{};
     for (int s = 0; s < mg->G; ++s) pp.p[s] = mg->rk[s].L;
+    GatherMap gm{};
+    int off = 0;
+    for (int s = 0; s < mg->G; ++s) {
+      gm.first[s] = (int)lay.count_le(s, k);
+      gm.off[s] = off;
+      off += (int)(lay.nloc(s) - lay.count_le(s, k));
+    }
     for (int r = 0; r < mg->G; ++r) {
       MRank& R = mg->rk[r];
       act(r);
-      dim3 grid((unsigned)nrem, (unsigned)std::min<int64_t>(lay.nb, std::max<int64_t>(4, 2048 / nrem)));
-      gather_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], pp, mg->G, ld, k, lay.nb);
+      if (on_side(r)) {
+        for (int s = 0; s < mg->G; ++s) {
+          const int64_t cnt = lay.nloc(s) - gm.first[s];
+          if (cnt > 0) dma2d(r, R.stage + (int64_t)gm.off[s] * nb * nb, nb, mg->rk[s].L + k * nb + (int64_t)gm.first[s] * nb * ld, ld, nb, cnt * nb);
+        }
+        dim3 grid((unsigned)nrem, (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, 1024 / nrem)));
+        unpermute_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], R.stage, gm, mg->G, k, nb);
+      } else {
+        dim3 grid((unsigned)nrem, (unsigned)std::min<int64_t>(nb, std::max<int64_t>(4, 2048 / nrem)));
+        gather_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], pp, mg->G, ld, k, nb);
+      }
       R.be.note(cudaGetLastError());
       R.ctx->launches++;
     }
@@ -190,12 +238,19 @@ struct LocalComm {
   void bcast_colpanel(int64_t k, int b) {   // transposed: panel[b] is nb x (k+1)*nb, ld nb
     const MRank& S = mg->rk[lay.owner(k)];
     const int64_t rows = (k + 1) * lay.nb, cols = lay.nb;
+    const double* src = S.L + (k / lay.G) * lay.nb * ld;
     for (int r = 0; r < mg->G; ++r) {
       MRank& R = mg->rk[r];
       act(r);
+      const double* tsrc = src;
+      int64_t tld = ld;
+      if (on_side(r)) {   // copy engine -> staging (rows x cols, ld rows), then a local transpose
+        dma2d(r, R.stage, rows, src, ld, rows, cols);
+        tsrc = R.stage; tld = rows;
+      }
       const int64_t tiles = (rows / 32) * (cols / 32);
       copy2d_transpose_kernel<<<(unsigned)std::min<int64_t>(tiles, 148 * 16), dim3(32, 8), 0, R.ctx->stream>>>(
-          R.panel[b], cols, S.L + (k / lay.G) * lay.nb * ld, ld, rows / 32, cols / 32);
+          R.panel[b], cols, tsrc, tld, rows / 32, cols / 32);
       R.be.note(cudaGetLastError());
       R.ctx->launches++;
     }
@@ -213,7 +268,7 @@ void mdense_free(gpr_mgpu* mg) {
     if (!R.ctx) continue;
     cudaSetDevice(R.ctx->device);
     cudaStreamSynchronize(R.ctx->stream);
-    cudaFree(R.L); cudaFree(R.dinv); cudaFree(R.gtile);
+    cudaFree(R.L); cudaFree(R.dinv); cudaFree(R.gtile); cudaFree(R.stage); R.stage = nullptr;
     for (int b = 0; b < 2; ++b) { cudaFree(R.Ukk[b]); cudaFree(R.panel[b]); R.Ukk[b] = R.panel[b] = nullptr; }
     cudaFree(R.x); cudaFree(R.y); cudaFree(R.hp); cudaFree(R.alpha); cudaFree(R.gpart); cudaFree(R.scal);
     R.L = R.dinv = R.x = R.y = R.hp = R.alpha = R.gpart = R.scal = nullptr;
@@ -235,6 +290,7 @@ int mdense_alloc(gpr_mgpu* mg, MDense& md, int64_t Np, int64_t nyp) {
       MCK(cudaMalloc(&R.Ukk[b], sizeof(double) * lay.nb * lay.nb));
       MCK(cudaMalloc(&R.panel[b], sizeof(double) * Np * lay.nb));
     }
+    MCK(cudaMalloc(&R.stage, sizeof(double) * Np * lay.nb));
     const int64_t lt = std::max<int64_t>(lay.ltiles(r), 1);
     MCK(cudaMalloc(&R.gtile, sizeof(int) * lt));
     std::vector<int> gt((size_t)lt, 0);
