@@ -126,6 +126,7 @@ struct DistBlocked {
   DistLayout lay;
   std::vector<DistRank<BE>>& ranks;
   COMM& comm;
+  bool prefetch_trtri = true, prefetch_lauum = true;   // issue the copies for the next step on the side queue
 
   DistBlocked(const DistLayout& l, std::vector<DistRank<BE>>& rk, COMM& c) : lay(l), ranks(rk), comm(c) {}
 
@@ -210,7 +211,7 @@ struct DistBlocked {
       const int64_t Krem = Np - (k + 1) * nb;
       all_join();       // the copies for step k (side queue of step k+1)
       comm.barrier();   // every rank holds its copies: row panel k and diagonal block k may be overwritten
-      all_side(true);
+      if (prefetch_trtri) all_side(true);
       if (k > 0) {      // copies for step k-1: U is final there, so they only wait for the buffers
         comm.bcast_diag(k - 1, true, b ^ 1);
         comm.gather_rowpanel(k - 1, b ^ 1);
@@ -254,7 +255,7 @@ struct DistBlocked {
       all_join();       // column panel k (side queue of step k-1)
       comm.barrier();   // every rank holds it: the owner may overwrite block column k
       if (k + 1 < lay.nblk) {
-        all_side(true);
+        if (prefetch_lauum) all_side(true);
         comm.bcast_colpanel(k + 1, b ^ 1);   // W is final: only waits for the buffer
         all_side(false);
       }

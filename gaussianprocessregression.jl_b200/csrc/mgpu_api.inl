@@ -136,6 +136,12 @@ struct gpr_mgpu {
   std::vector<MRank> rk;
   std::string err;
   cudaEvent_t t0 = nullptr, t1 = nullptr, tot0 = nullptr, tot1 = nullptr;
+  // how the panels of the NEXT step travel during trtri / lauum: 0 = on the main queue before the step's GEMMs (no
+  // overlap), 1 = side queue, SM-driven peer reads, 2 = side queue, copy engines + local re-layout.
+  // Measured at N = 131072 on 8 x B200 (profiles/README.md), phase time in ms:
+  //   trtri  mode 0: 3482   mode 1: 3779   mode 2: 3688     lauum  mode 1: 3552   mode 2: 3140
+  // (at 2 GPUs the three modes are within 0.5 % of each other), hence the defaults.
+  int prefetch_trtri = 0, prefetch_lauum = 2;
 };
 
 namespace {
@@ -181,7 +187,8 @@ struct LocalComm {
   // (2 CTAs x 250 registers): an SM-driven pull would have to take CTA slots away from them and hold them for the
   // length of an NVLink read (measured on 8 x B200: trtri + 300 ms).  Those transfers therefore go through the copy
   // engines (cudaMemcpy2DAsync between peers) into a staging buffer; only the cheap local re-layout is a kernel.
-  bool on_side(int r) const { return mg->rk[r].ctx->side_stream && mg->rk[r].ctx->stream == mg->rk[r].ctx->side_stream; }
+  int dma_mode = 2;   // 2: transfers issued to a side queue use the copy engines
+  bool on_side(int r) const { return dma_mode == 2 && mg->rk[r].ctx->side_stream && mg->rk[r].ctx->stream == mg->rk[r].ctx->side_stream; }
   void dma2d(int r, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
     MRank& R = mg->rk[r];
     act(r);
@@ -408,6 +415,14 @@ int gpr_mgpu_destroy(gpr_mgpu* mg) {
   return GPR_OK;
 }
 
+int gpr_mgpu_set_option(gpr_mgpu* mg, const char* name, int64_t value) {
+  if (!mg || !name) return GPR_ERR_ARG;
+  if (value < 0 || value > 2) return mfail(mg, GPR_ERR_ARG, "option value must be 0, 1 or 2");
+  if (!strcmp(name, "prefetch_trtri")) { mg->prefetch_trtri = (int)value; return GPR_OK; }
+  if (!strcmp(name, "prefetch_lauum")) { mg->prefetch_lauum = (int)value; return GPR_OK; }
+  return mfail(mg, GPR_ERR_ARG, std::string("unknown option ") + name);
+}
+
 const char* gpr_mgpu_last_error(gpr_mgpu* mg) { return mg ? mg->err.c_str() : g_create_error.c_str(); }
 
 int64_t gpr_mgpu_launch_count(gpr_mgpu* mg) {
@@ -524,6 +539,8 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
   auto ranks = mdense_ranks(mg, m->md);
   LocalComm comm{mg, lay, ld};
   DistBlocked<CudaBE, LocalComm> db(lay, ranks, comm);
+  db.prefetch_trtri = mg->prefetch_trtri != 0;
+  db.prefetch_lauum = mg->prefetch_lauum != 0;
 
   // ---- potrf (+ forward substitution of y), log det
   tick();
@@ -561,6 +578,7 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
   } else {
     // ---- trtri (+ back substitution): W = U^-1 in place, y columns = -alpha
     tick();
+    comm.dma_mode = mg->prefetch_trtri;
     db.trtri();
     { int rc = tock(GPR_T_TRTRI); if (rc) return rc; }
     tick();
@@ -595,6 +613,7 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
   if (G) {
     // ---- K^-1 = W W^T in place, then the fused all-hyper-parameter reduction over the local columns
     tick();
+    comm.dma_mode = mg->prefetch_lauum;
     db.lauum();
     { int rc = tock(GPR_T_LAUUM); if (rc) return rc; }
     m->have_inverse = true;
@@ -719,10 +738,13 @@ int gpr_mgpu_dbg_factor(gpr_mgpu* mg, double* A, int64_t N, double* Y, int ny, i
     auto ranks = mdense_ranks(mg, md);
     LocalComm comm{mg, lay, md.ld};
     DistBlocked<CudaBE, LocalComm> db(lay, ranks, comm);
+    db.prefetch_trtri = mg->prefetch_trtri != 0;
+    db.prefetch_lauum = mg->prefetch_lauum != 0;
     double t[3] = {0, 0, 0};
     for (int ph = 0; ph <= mode && ph < 3; ++ph) {
       cudaSetDevice(mg->rk[0].ctx->device);
       cudaEventRecord(mg->t0, mg->rk[0].ctx->stream);
+      comm.dma_mode = ph == 1 ? mg->prefetch_trtri : mg->prefetch_lauum;
       if (ph == 0) db.potrf(); else if (ph == 1) db.trtri(); else db.lauum();
       for (int r = 0; r < mg->G; ++r) { cudaSetDevice(mg->rk[r].ctx->device); MCK(cudaStreamSynchronize(mg->rk[r].ctx->stream)); }
       cudaSetDevice(mg->rk[0].ctx->device);

@@ -62,6 +62,7 @@ _SIGS = {
     "gpr_dbg_factor": (C.c_int, [_vp, _dp, _i64, C.c_int, C.POINTER(_i64), _dp]),
     "gpr_mgpu_create": (C.c_int, [C.c_int, _ip, _i64, C.POINTER(_vp)]),
     "gpr_mgpu_destroy": (C.c_int, [_vp]),
+    "gpr_mgpu_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "gpr_mgpu_last_error": (C.c_char_p, [_vp]),
     "gpr_mgpu_launch_count": (_i64, [_vp]),
     "gpr_mgpu_model_create": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _i64, _dp, _dp, C.c_int, C.c_int, C.POINTER(_vp)]),
@@ -408,6 +409,9 @@ class MultiContext:
 
     def launch_count(self):
         return int(lib().gpr_mgpu_launch_count(self.handle))
+
+    def set_option(self, name, value):
+        self.check(lib().gpr_mgpu_set_option(self.handle, name.encode(), int(value)))
 
     def dbg_factor(self, A, Y=None, mode=0):
         A = np.array(A, dtype=np.float64, order="F")

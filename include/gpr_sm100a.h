@@ -188,6 +188,10 @@ typedef struct gpr_mgpu_model gpr_mgpu_model;
 
 int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** mg);
 int gpr_mgpu_destroy(gpr_mgpu* mg);
+/* "prefetch_trtri" / "prefetch_lauum": how the panels of the next step travel while the current step computes:
+ * 0 = on the main queue before the step (no overlap), 1 = side queue with SM-driven peer reads, 2 = side queue through
+ * the copy engines.  Defaults (measured on 8 x B200): trtri 0, lauum 2. */
+int gpr_mgpu_set_option(gpr_mgpu* mg, const char* name, int64_t value);
 const char* gpr_mgpu_last_error(gpr_mgpu* mg);     /* mg may be NULL: last error of a failed gpr_mgpu_create */
 int64_t gpr_mgpu_launch_count(gpr_mgpu* mg);
 /* GPRModel(cov, hp, x, y; train_axis): src/models.jl:17-37; x and y are replicated on every rank */

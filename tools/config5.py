@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--gpus", default="8")
     ap.add_argument("--nb", type=int, default=1024)
     ap.add_argument("--evals", type=int, default=1, help="timed evaluations per GPU count (after one warm-up if > 1)")
+    ap.add_argument("--prefetch", default="", help="prefetch_trtri,prefetch_lauum (0 none, 1 SM pulls, 2 copy engines)")
     ap.add_argument("--fd", action="store_true", help="also check the gradient by a central difference of F")
     args = ap.parse_args()
     from gpr_sm100a import _ffi
@@ -53,6 +54,10 @@ def main():
         devs = [r % ndev for r in range(G)]
         t0 = time.perf_counter()
         mc = _ffi.MultiContext(devs, nb=args.nb)
+        if args.prefetch:
+            pt, pl = [int(v) for v in args.prefetch.split(",")]
+            mc.set_option("prefetch_trtri", pt)
+            mc.set_option("prefetch_lauum", pl)
         mm = _ffi.MultiModelHandle(mc, [1, 2], D, x, y)
         t_setup = time.perf_counter() - t0
         if args.evals > 1:
@@ -67,7 +72,7 @@ def main():
         cols = np.random.default_rng(1).choice(N, 32, replace=False)
         Kc = se_noise_columns(x, hp, cols)
         resid = float(np.abs(Kc.T @ alpha - y[cols]).max() / np.abs(y).max())
-        out = {"config": 5, "N": N, "D": D, "P": len(hp), "gpus": G, "devices": devs, "nb": args.nb, "setup_s": round(t_setup, 2),
+        out = {"config": 5, "N": N, "D": D, "P": len(hp), "gpus": G, "devices": devs, "nb": args.nb, "prefetch": args.prefetch or "default (0,2)", "setup_s": round(t_setup, 2),
                "s_per_eval": [round(t, 3) for t in ts], "evals_per_s": 1.0 / min(ts),
                "phase_ms": {k: round(v, 1) for k, v in tms[-1].items() if v > 0},
                "dense_tflops_aggregate": N ** 3 / ((tms[-1]["potrf"] + tms[-1]["trtri"] + tms[-1]["lauum"]) * 1e-3) / 1e12,
