@@ -6,6 +6,7 @@
 //        strided batch: member z uses A + z*sA, B + z*sB, C + z*sC
 //        flags: BLK_UPPER_ONLY (C diagonal-anchored, only row <= col computed/stored),
 //               BLK_K_FROM_N   (tile column block J contracts over k >= 128*J only: the triangular product W W^T)
+//               BLK_SKIP_TILE00 (the 128x128 tile (0,0) of C is left alone)
 //   be.potrf_leaf(A, lda, Dinv_blk, global_row_offset)   128x128 diagonal block:
 //        A(upper) <- chol(A) (U^T U = A) and Dinv_blk <- inv(U) (full 128x128, zeros below the diagonal)
 //   be.transpose_inplace(A, ld, n)   A <- A^T (n x n, in place)
@@ -37,6 +38,7 @@ namespace gpr {
 constexpr int LEAF = 128;
 constexpr int BLK_UPPER_ONLY = 1;   // == GEMM_UPPER_ONLY
 constexpr int BLK_K_FROM_N = 2;     // == GEMM_K_FROM_N
+constexpr int BLK_SKIP_TILE00 = 64; // == GEMM_SKIP_TILE00
 
 template <class BE>
 struct Blocked {
@@ -55,9 +57,16 @@ struct Blocked {
   // launches with fewer tiles than SMs.
   void potrf(double* A, int64_t ld, int64_t n, int64_t b0) { potrf_panel(A, ld, n, 0, b0); }
 
-  void potrf_panel(double* A, int64_t ld, int64_t n, int64_t mr, int64_t b0) {
+  // leaf_lookahead: factor the NEXT 128x128 diagonal block on the backend's side queue as soon as its own tile of
+  // the trailing update is done, while the main queue runs the rest of that update (the 256 single-CTA leaf
+  // factorizations of an N = 32768 problem are otherwise a serial 21 ms chain during which the GPU idles).
+  // Needs be.fork() / be.join() / be.side(on); must stay off when the caller already runs on the side queue.
+  bool leaf_lookahead = false;
+
+  void potrf_panel(double* A, int64_t ld, int64_t n, int64_t mr, int64_t b0, bool first_leaf_done = false) {
     if (n == LEAF) {
-      be.potrf_leaf(A, ld, dinv_blk(b0), b0 * LEAF);
+      if (first_leaf_done) be.join();                   // factored ahead on the side queue
+      else be.potrf_leaf(A, ld, dinv_blk(b0), b0 * LEAF);
       if (mr > 0) {
         double* P = A + (int64_t)LEAF * ld;   // row panel right of the block: 128 x mr
         be.gemm('T', 'N', LEAF, mr, LEAF, 1.0, dinv_blk(b0), LEAF, P, ld, 0.0, P, ld, 0, 1, 0, 0, 0);
@@ -67,9 +76,20 @@ struct Blocked {
     const int64_t n1 = split(n), n2 = n - n1;
     double* A12 = A + n1 * ld;           // n1 x (n2 + mr): rest of the row panel
     double* A22 = A + n1 + n1 * ld;      // (n2) x (n2 + mr), diagonal anchored
-    potrf_panel(A, ld, n1, n2 + mr, b0);
-    be.gemm('T', 'N', n2, n2 + mr, n1, -1.0, A12, ld, A12, ld, 1.0, A22, ld, BLK_UPPER_ONLY, 1, 0, 0, 0);
-    potrf_panel(A22, ld, n2, mr, b0 + n1 / LEAF);
+    potrf_panel(A, ld, n1, n2 + mr, b0, first_leaf_done);
+    if (!leaf_lookahead) {
+      be.gemm('T', 'N', n2, n2 + mr, n1, -1.0, A12, ld, A12, ld, 1.0, A22, ld, BLK_UPPER_ONLY, 1, 0, 0, 0);
+      potrf_panel(A22, ld, n2, mr, b0 + n1 / LEAF);
+      return;
+    }
+    // side queue: tile (0,0) of A22 gets its update and is factored; main queue: the rest of the update
+    be.fork();
+    be.side(true);
+    be.gemm('T', 'N', LEAF, LEAF, n1, -1.0, A12, ld, A12, ld, 1.0, A22, ld, BLK_UPPER_ONLY, 1, 0, 0, 0);
+    be.potrf_leaf(A22, ld, dinv_blk(b0 + n1 / LEAF), (b0 + n1 / LEAF) * LEAF);
+    be.side(false);
+    be.gemm('T', 'N', n2, n2 + mr, n1, -1.0, A12, ld, A12, ld, 1.0, A22, ld, BLK_UPPER_ONLY | BLK_SKIP_TILE00, 1, 0, 0, 0);
+    potrf_panel(A22, ld, n2, mr, b0 + n1 / LEAF, true);
   }
 
   // B (n x m) <- s * T^-T B,   T upper n x n, s = +-1

@@ -56,6 +56,7 @@ enum GemmFlags : int {
   // jt of C stands for the GLOBAL tile column gt = col_gtile[jt].
   GEMM_MAP_UPPER = 8,    // only elements with (row_gtile0 + tile row, row in tile) <= (gt, col in tile) exist
   GEMM_MAP_KUPTO = 16,   // the tile column contracts over k < (gt - k_gtile0 + 1) * 128 only
+  GEMM_SKIP_TILE00 = 64, // the 128x128 tile at (0, 0) of C is neither read nor written (it is produced elsewhere, concurrently)
   GEMM_MAP_BROWS = 32,   // the op(B) columns of the tile column start at gt * 128 instead of at the local column
 };
 
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
   if (p.flags & GEMM_MAP_KUPTO) tile_n = gridDim.y - 1 - tile_n;
   const int blk_n = (tile_n * BN) >> 7;   // 128-block column of this tile (tile_m is already a 128-block row)
   if ((p.flags & GEMM_UPPER_ONLY) && tile_m > blk_n) return;
+  if ((p.flags & GEMM_SKIP_TILE00) && tile_m == 0 && blk_n == 0) return;
   int gt = 0;   // global tile column (mapped forms)
   if (p.flags & (GEMM_MAP_UPPER | GEMM_MAP_KUPTO | GEMM_MAP_BROWS)) {
     gt = p.col_gtile[blk_n];

@@ -42,6 +42,7 @@ struct gpr_ctx {
   int sm_count = 0;
   int64_t predict_tile = 16384;
   int inplace_lauum = 0;   // option "inplace_lauum": force the recursive in-place W W^T (saves one N x N buffer)
+  int leaf_lookahead = 1;  // option "leaf_lookahead": factor the next diagonal leaf on the side queue (csrc/blocked.hpp)
   long long launches = 0;
   long long* d_info = nullptr;
   cudaError_t pending = cudaSuccess;   // first launch error seen by the backend
@@ -272,6 +273,7 @@ int factor_and_solve(gpr_model* m, const double* hp, double eps, int64_t* info) 
   }
   CudaBE be{ctx};
   Blocked<CudaBE> blk(be, m->d_dinv);
+  blk.leaf_lookahead = ctx->leaf_lookahead != 0;
   {
     Scope s(m->tm, GPR_T_POTRF, ctx->stream);
     blk.potrf(m->d_U, Np, Np, 0);
@@ -428,6 +430,11 @@ int gpr_ctx_create(int device, gpr_ctx** out) {
   if (e != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return fail_cuda(nullptr, e, "cudaMalloc", __LINE__); }
   int rc = setup_kernel_attributes(ctx);
   if (rc) { g_create_error = ctx->err; cudaFree(ctx->d_info); cudaStreamDestroy(ctx->stream); delete ctx; return rc; }
+  ctx->main_stream = ctx->stream;
+  e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  if (e != cudaSuccess) { gpr_ctx_destroy(ctx); return fail_cuda(nullptr, e, "side queue", __LINE__); }
   *out = ctx;
   return GPR_OK;
 }
@@ -456,6 +463,7 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
     return GPR_OK;
   }
   if (!strcmp(name, "inplace_lauum")) { ctx->inplace_lauum = value ? 1 : 0; return GPR_OK; }
+  if (!strcmp(name, "leaf_lookahead")) { ctx->leaf_lookahead = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "gemm_cfg")) { gemm_forced_cfg() = (int)value; return GPR_OK; }   // 0 auto, 1..3: see dgemm_sm100.cuh
   return fail(ctx, GPR_ERR_ARG, std::string("unknown option ") + name);
 }
@@ -1253,6 +1261,7 @@ int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, 
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     CudaBE be{ctx};
     Blocked<CudaBE> blk(be, dinv);
+    blk.leaf_lookahead = ctx->leaf_lookahead != 0;
     double *dW = nullptr, *dC = nullptr;
     if (mode == 3) {
       if (e == cudaSuccess) e = cudaMalloc(&dW, sizeof(double) * Np * Np);

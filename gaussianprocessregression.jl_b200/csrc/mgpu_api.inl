@@ -365,14 +365,6 @@ int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** out) 
     int rc = gpr_ctx_create(devices[r], &mg->rk[r].ctx);
     if (rc) { std::string e = g_create_error; gpr_mgpu_destroy(mg); g_create_error = e; return rc; }
     mg->rk[r].be = CudaBE{mg->rk[r].ctx};
-    {
-      gpr_ctx* c = mg->rk[r].ctx;   // gpr_ctx_create left the device current
-      c->main_stream = c->stream;
-      cudaError_t e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
-      if (e != cudaSuccess) { gpr_mgpu_destroy(mg); return mfail(nullptr, GPR_ERR_CUDA, std::string("side queue: ") + cudaGetErrorString(e)); }
-    }
     if (cudaEventCreateWithFlags(&mg->rk[r].ev, cudaEventDisableTiming) != cudaSuccess) {
       gpr_mgpu_destroy(mg);
       return mfail(nullptr, GPR_ERR_CUDA, "cudaEventCreate failed");

@@ -79,6 +79,7 @@ struct CpuBE {
       for (int64_t n = 0; n < N; ++n)
         for (int64_t m = 0; m < M; ++m) {
           if ((flags & gpr::BLK_UPPER_ONLY) && (m / gpr::LEAF > n / gpr::LEAF || (m / gpr::LEAF == n / gpr::LEAF && m > n))) continue;
+          if ((flags & gpr::BLK_SKIP_TILE00) && m < gpr::LEAF && n < gpr::LEAF) continue;
           double r = alpha * tmp[m + n * M];
           if (beta != 0.0) r += beta * C[m + n * ldc];
           C[m + n * ldc] = r;
@@ -229,6 +230,8 @@ long long hl_factor(double* A, int64_t n, int mode, long long* gemm_calls) {
   CpuBE be;
   std::vector<double> dinv((size_t)n * 128);
   gpr::Blocked<CpuBE> blk(be, dinv.data());
+  blk.leaf_lookahead = (mode & 16) != 0;   // the ordering the CUDA product uses (side-queue calls are no-ops here)
+  mode &= 15;
   blk.potrf(A, n, n, 0);
   if (mode == 3 || mode == 4) {   // out-of-place inverse: W = copy of U with clean diagonal blocks, C = W W^T written back to A (upper)
     std::vector<double> W((size_t)n * n), C((size_t)n * n, 0.0);

@@ -33,12 +33,13 @@ def spd(n, seed):
 
 
 @pytest.mark.parametrize("n", [128, 256, 384, 640, 1024])
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 16, 20])
 def test_blocked_factor(hl, n, mode):
     K = spd(n, n)
     A = np.asfortranarray(K.copy())
     calls = ctypes.c_longlong(0)
     info = hl.hl_factor(dp(A), ctypes.c_int64(n), mode, ctypes.byref(calls))
+    mode &= 15                                   # bit 4: leaf look-ahead ordering of the update
     assert info == 0
     U = sl.cholesky(K, lower=False)
     ref = [U, np.linalg.inv(U), np.linalg.inv(K), np.linalg.inv(K), np.linalg.inv(K)][mode]   # modes 3, 4: out-of-place W W^T
