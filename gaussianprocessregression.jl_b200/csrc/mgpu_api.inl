@@ -139,9 +139,9 @@ struct gpr_mgpu {
   // how the panels of the NEXT step travel during trtri / lauum: 0 = on the main queue before the step's GEMMs (no
   // overlap), 1 = side queue, SM-driven peer reads, 2 = side queue, copy engines + local re-layout.
   // Measured at N = 131072 on 8 x B200 (profiles/README.md), phase time in ms:
-  //   trtri  mode 0: 3482   mode 1: 3779   mode 2: 3688     lauum  mode 1: 3552   mode 2: 3140
+  //   trtri  mode 0: 3760   mode 1: 3779   mode 2: 3688     lauum  mode 0: 3735   mode 1: 3552   mode 2: 3140
   // (at 2 GPUs the three modes are within 0.5 % of each other), hence the defaults.
-  int prefetch_trtri = 0, prefetch_lauum = 2;
+  int prefetch_trtri = 2, prefetch_lauum = 2;
 };
 
 namespace {

@@ -190,7 +190,7 @@ int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** mg);
 int gpr_mgpu_destroy(gpr_mgpu* mg);
 /* "prefetch_trtri" / "prefetch_lauum": how the panels of the next step travel while the current step computes:
  * 0 = on the main queue before the step (no overlap), 1 = side queue with SM-driven peer reads, 2 = side queue through
- * the copy engines.  Defaults (measured on 8 x B200): trtri 0, lauum 2. */
+ * the copy engines.  Default 2 for both (measured on 8 x B200, profiles/README.md). */
 int gpr_mgpu_set_option(gpr_mgpu* mg, const char* name, int64_t value);
 const char* gpr_mgpu_last_error(gpr_mgpu* mg);     /* mg may be NULL: last error of a failed gpr_mgpu_create */
 int64_t gpr_mgpu_launch_count(gpr_mgpu* mg);

@@ -72,7 +72,7 @@ def main():
         cols = np.random.default_rng(1).choice(N, 32, replace=False)
         Kc = se_noise_columns(x, hp, cols)
         resid = float(np.abs(Kc.T @ alpha - y[cols]).max() / np.abs(y).max())
-        out = {"config": 5, "N": N, "D": D, "P": len(hp), "gpus": G, "devices": devs, "nb": args.nb, "prefetch": args.prefetch or "default (0,2)", "setup_s": round(t_setup, 2),
+        out = {"config": 5, "N": N, "D": D, "P": len(hp), "gpus": G, "devices": devs, "nb": args.nb, "prefetch": args.prefetch or "default (2,2)", "setup_s": round(t_setup, 2),
                "s_per_eval": [round(t, 3) for t in ts], "evals_per_s": 1.0 / min(ts),
                "phase_ms": {k: round(v, 1) for k, v in tms[-1].items() if v > 0},
                "dense_tflops_aggregate": N ** 3 / ((tms[-1]["potrf"] + tms[-1]["trtri"] + tms[-1]["lauum"]) * 1e-3) / 1e12,
