@@ -596,3 +596,56 @@ def test_integrate_agrees_with_quadrature_of_the_posterior_mean(gpr):
     pm = gpr.predict_mean(md, grid)
     assert mu[0] == pytest.approx(float(W @ pm), rel=1e-9)
     assert var[0] >= -1e-10
+
+
+# ------------------------------------------------------------------ (7) edge sizes
+@pytest.mark.parametrize("N", [1, 2, 3, 127, 128, 129])
+def test_tiny_and_boundary_sizes(gpr, N):
+    """Sizes around the 128-padding boundary and degenerate training sets (the reference has no lower limit on n)."""
+    rng = np.random.default_rng(N)
+    D = 2
+    x = rng.random((D, N))
+    y = rng.random(N)
+    hp = np.array([1.1, 0.9, 1.3, 0.2])
+    cov, covo = gpr.SquaredExp() + gpr.WhiteNoise(), (o.SE, o.NOISE)
+    md, mdo = gpr.GPRModel(cov, hp, x, y), o.GPRModel(covo, hp, x, y)
+    ll = gpr.MarginalLikelihood()
+    tc = gpr.MllGradCache(md)
+    G = np.empty(4)
+    F = gpr.loss_grad_(ll, True, G, hp, md, tc)
+    Fo, Go = o.loss_grad(hp, mdo)
+    assert abs(F - Fo) <= TOL_F * max(abs(Fo), 1.0)
+    assert np.abs(G - Go).max() <= TOL_G * max(np.abs(Go).max(), 1.0)
+    tc.close()
+    xp = rng.random((D, 5))
+    mu, Sig = gpr.predict(md, xp, diagonal_var=True)
+    mu_o, var_o = o.predict(mdo, xp, diagonal_var=True)
+    assert np.abs(mu - mu_o).max() <= TOL_MU * max(np.abs(mu_o).max(), 1.0)
+    assert np.abs(Sig.diag - var_o).max() <= TOL_VAR * o.prior_diag(mdo)
+    tcm = gpr.MultiGPUGradCache(md, devices=_devices(2), nb=128)
+    Gm = np.empty(4)
+    Fm = gpr.loss_grad_(ll, True, Gm, hp, md, tcm)
+    assert abs(Fm - Fo) <= TOL_F * max(abs(Fo), 1.0)
+    assert np.abs(Gm - Go).max() <= TOL_G * max(np.abs(Go).max(), 1.0)
+    tcm.close()
+
+
+def test_mgpu_prefetch_modes_agree(gpr):
+    """The three transports of the prefetched panels (main queue / SM pulls / copy engines) give identical results."""
+    from gpr_sm100a import _ffi
+    rng = np.random.default_rng(9)
+    n = 1536
+    X = rng.standard_normal((n, n))
+    K = X @ X.T / n + np.eye(n)
+    Y0 = rng.standard_normal((n, 2))
+    outs = []
+    for mode in (0, 1, 2):
+        mc = _ffi.MultiContext(_devices(3), nb=256)
+        mc.set_option("prefetch_trtri", mode)
+        mc.set_option("prefetch_lauum", mode)
+        A, Y, _ = mc.dbg_factor(np.triu(K), Y0, 2)
+        mc.close()
+        outs.append((A, Y))
+    for A, Y in outs[1:]:
+        assert np.array_equal(A, outs[0][0]) and np.array_equal(Y, outs[0][1])
+    assert np.abs(np.triu(outs[0][0]) - np.triu(np.linalg.inv(K))).max() <= 1e-11 * np.abs(np.linalg.inv(K)).max()
