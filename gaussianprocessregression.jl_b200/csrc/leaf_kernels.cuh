@@ -454,4 +454,67 @@ __global__ void __launch_bounds__(256) transpose_inplace_kernel(double* __restri
   }
 }
 
+// ---------------------------------------------------------------------------
+// out = A y for a symmetric A of which only the UPPER triangle is stored (the lower part of the buffer is never
+// read): alpha = K^-1 y from the explicit inverse on the gradient path, replacing the two triangular sweeps
+// (ldiv!(alpha, kchol, y), src/cost.jl:89,106) when K^-1 is formed anyway.  Two deterministic passes over the
+// triangle (8 n^2 bytes): strictly-upper column parts (one warp per column) and row parts including the diagonal
+// (a CTA owns 64 rows, its 8 warps split the columns).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) symv_upper_cols_kernel(long long n, const double* __restrict__ A, long long ld,
+                                                              const double* __restrict__ y, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long j = blockIdx.x * 8LL + warp;
+  if (j >= n) return;
+  const double* col = A + j * ld;
+  double s0 = 0.0, s1 = 0.0;
+  const long long jeven = j & ~1LL;                  // rows [0, jeven) in double2 steps, row jeven (< j) separately
+  for (long long i = 2 * lane; i < jeven; i += 64) {
+    const double2 a = *reinterpret_cast<const double2*>(col + i);
+    const double2 v = *reinterpret_cast<const double2*>(y + i);
+    s0 += a.x * v.x; s1 += a.y * v.y;
+  }
+  if (lane == 0 && jeven < j) s0 += col[jeven] * y[jeven];
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) out[j] = s;                          // sum_{i < j} A_ij y_i
+}
+
+// out[i] += sum_{j >= i} A_ij y_j
+__global__ void __launch_bounds__(256) symv_upper_rows_kernel(long long n, const double* __restrict__ A, long long ld,
+                                                              const double* __restrict__ y, double* __restrict__ out) {
+  __shared__ double red[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long r0 = blockIdx.x * 64LL;
+  const long long i0 = r0 + 2 * lane;                 // this lane's two rows
+  double sx = 0.0, sy = 0.0;
+  if (i0 < n) {
+    const double* p = A + i0;
+    // columns r0 .. r0+63 (the diagonal 64-block): element-wise test j >= i
+    for (long long j = r0 + warp; j < r0 + 64 && j < n; j += 8) {
+      const double yj = y[j];
+      if (j >= i0) sx += p[j * ld] * yj;
+      if (j >= i0 + 1 && i0 + 1 < n) sy += p[1 + j * ld] * yj;
+    }
+    // columns right of the diagonal block: both rows valid, 16-byte loads
+    for (long long j = r0 + 64 + warp; j < n; j += 8) {
+      const double2 a = *reinterpret_cast<const double2*>(p + j * ld);
+      const double yj = y[j];
+      sx += a.x * yj; sy += a.y * yj;
+    }
+  }
+  red[warp][2 * lane] = sx; red[warp][2 * lane + 1] = sy;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const long long i = r0 + threadIdx.x;
+    if (i < n) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+      out[i] += s;
+    }
+  }
+}
+
 }  // namespace gpr
