@@ -3,8 +3,11 @@
 //
 // One rank per entry of the device list; a device may appear more than once ("virtual ranks": the whole
 // distributed code path then runs on a single GPU, which is how tests/test_gpu_parity.py covers it on a
-// 1-GPU box).  Cross-rank movement = pull kernels over peer memory (NVLink when the ranks sit on different
-// devices), ordered by CUDA events; the algorithms are csrc/dist_blocked.hpp.
+// 1-GPU box).  The algorithms are csrc/dist_blocked.hpp; three transports move the panels between ranks:
+//   0  LocalComm   all ranks in this process: pull kernels / copy engines over peer memory (NVLink), CUDA events
+//   1  PackedComm  all ranks in this process, but through the pack -> collective -> unpack data path of the NCCL
+//                  transport with plain device copies as the "collective" (1-GPU test of that data path)
+//   2  PackedComm  one rank per PROCESS (torchrun), NCCL broadcast / all-gather / all-reduce (gpr_dist_create)
 namespace {
 
 constexpr int MGPU_MAX_RANKS = 16;
@@ -117,6 +120,7 @@ __global__ void grad_partial_sum_kernel(const double* __restrict__ partial, int 
 }
 
 struct MRank {
+  int rank = 0;              // global rank of this entry (== its index unless transport 2)
   gpr_ctx* ctx = nullptr;
   CudaBE be{nullptr};
   double *L = nullptr, *dinv = nullptr, *Ukk[2] = {nullptr, nullptr}, *panel[2] = {nullptr, nullptr};
@@ -126,14 +130,20 @@ struct MRank {
   double *x = nullptr, *y = nullptr, *hp = nullptr, *alpha = nullptr, *gpart = nullptr, *scal = nullptr;   // scal: [logdiag, y.alpha, tot[P+1]...]
   int gr_blocks = 0;
   cudaEvent_t ev = nullptr;
+  long long* d_flag = nullptr;   // transport 2: all-reduced factorization status
 };
+
+struct NcclApi;
 
 }  // namespace
 
 struct gpr_mgpu {
-  int G = 0;
+  int G = 0;                 // ranks of the distributed factorization (world size)
   int64_t nb = 1024;
-  std::vector<MRank> rk;
+  std::vector<MRank> rk;     // the ranks held by this process: all G (transports 0, 1) or one (transport 2)
+  int transport = 0;
+  NcclApi* nccl = nullptr;
+  void* comm = nullptr;      // ncclComm_t (transport 2)
   std::string err;
   cudaEvent_t t0 = nullptr, t1 = nullptr, tot0 = nullptr, tot1 = nullptr;
   // how the panels of the NEXT step travel during trtri / lauum: 0 = on the main queue before the step's GEMMs (no
@@ -160,13 +170,87 @@ int mfail(gpr_mgpu* mg, int code, const std::string& msg) {
     }                                                                                                      \
   } while (0)
 
-// COMM of csrc/dist_blocked.hpp for ranks that live in this process
-struct LocalComm {
+// COMM interface of csrc/dist_blocked.hpp (virtual: the transport is chosen at run time) plus the two exchanges of the
+// model level: the alpha vector from the y owner to everybody and the sum of a few doubles over the ranks.
+struct CommBase {
+  int dma_mode = 2;
+  virtual ~CommBase() {}
+  virtual void barrier() = 0;
+  virtual void bcast_diag(int64_t k, bool with_owner, int b) = 0;
+  virtual void gather_rowpanel(int64_t k, int b) = 0;
+  virtual void bcast_colpanel(int64_t k, int b) = 0;
+  virtual void bcast_alpha(int root, int64_t count) = 0;                     // MRank::alpha
+  virtual int sum_scal(int64_t off, int64_t count, double* host_out) = 0;    // sum over ranks of MRank::scal[off ..], rank order
+};
+
+// NCCL through dlopen: libgpr_sm100a.so keeps linking the CUDA runtime only; inside a torch process the already loaded
+// libnccl.so.2 (torch's bundled build) is the one that answers.
+}  // namespace
+#include <dlfcn.h>
+#include <nccl.h>
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi* nccl_api(std::string& err) {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) {
+      *(void**)&api.GetUniqueId = dlsym(api.lib, "ncclGetUniqueId");
+      *(void**)&api.CommInitRank = dlsym(api.lib, "ncclCommInitRank");
+      *(void**)&api.CommDestroy = dlsym(api.lib, "ncclCommDestroy");
+      *(void**)&api.Broadcast = dlsym(api.lib, "ncclBroadcast");
+      *(void**)&api.AllGather = dlsym(api.lib, "ncclAllGather");
+      *(void**)&api.AllReduce = dlsym(api.lib, "ncclAllReduce");
+      *(void**)&api.GetErrorString = dlsym(api.lib, "ncclGetErrorString");
+    }
+  }
+  if (!api.lib) { err = "libnccl.so.2 could not be loaded (dlopen)"; return nullptr; }
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast || !api.AllGather || !api.AllReduce) {
+    err = "libnccl.so.2 lacks a required entry point";
+    return nullptr;
+  }
+  return &api;
+}
+
+// sum over the local ranks of MRank::scal[off .. off + count), in rank order (deterministic), on the host
+int host_sum_scal(gpr_mgpu* mg, int64_t off, int64_t count, double* host_out) {
+  std::vector<double> part((size_t)count);
+  for (int64_t i = 0; i < count; ++i) host_out[i] = 0.0;
+  for (auto& R : mg->rk) {
+    MCK(cudaSetDevice(R.ctx->device));
+    MCK(cudaMemcpyAsync(part.data(), R.scal + off, sizeof(double) * count, cudaMemcpyDeviceToHost, R.ctx->stream));
+    MCK(cudaStreamSynchronize(R.ctx->stream));
+    for (int64_t i = 0; i < count; ++i) host_out[i] += part[i];
+  }
+  return GPR_OK;
+}
+
+// COMM for ranks that all live in this process (transport 0)
+struct LocalComm : CommBase {
   gpr_mgpu* mg;
   DistLayout lay;
   int64_t ld;
+  LocalComm(gpr_mgpu* m, const DistLayout& l, int64_t ld_) : mg(m), lay(l), ld(ld_) {}
   void act(int r) { cudaSetDevice(mg->rk[r].ctx->device); }
-  void barrier() {
+  void bcast_alpha(int root, int64_t count) override {
+    barrier();
+    for (int r = 0; r < mg->G; ++r)
+      if (r != root) copy2d(r, mg->rk[r].alpha, count, mg->rk[root].alpha, count, count, 1);
+  }
+  int sum_scal(int64_t off, int64_t count, double* host_out) override { return host_sum_scal(mg, off, count, host_out); }
+  void barrier() override {
     if (mg->G == 1) return;
     for (int r = 0; r < mg->G; ++r) { act(r); mg->rk[r].be.note(cudaEventRecord(mg->rk[r].ev, mg->rk[r].ctx->stream)); }
     for (int r = 0; r < mg->G; ++r) {
@@ -187,7 +271,6 @@ struct LocalComm {
   // (2 CTAs x 250 registers): an SM-driven pull would have to take CTA slots away from them and hold them for the
   // length of an NVLink read (measured on 8 x B200: trtri + 300 ms).  Those transfers therefore go through the copy
   // engines (cudaMemcpy2DAsync between peers) into a staging buffer; only the cheap local re-layout is a kernel.
-  int dma_mode = 2;   // 2: transfers issued to a side queue use the copy engines
   bool on_side(int r) const { return dma_mode == 2 && mg->rk[r].ctx->side_stream && mg->rk[r].ctx->stream == mg->rk[r].ctx->side_stream; }
   void dma2d(int r, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
     MRank& R = mg->rk[r];
@@ -195,7 +278,7 @@ struct LocalComm {
     R.be.note(cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * rows, (size_t)cols,
                                 cudaMemcpyDefault, R.ctx->stream));
   }
-  void bcast_diag(int64_t k, bool with_owner, int b) {
+  void bcast_diag(int64_t k, bool with_owner, int b) override {
     const int o = lay.owner(k);
     const int64_t nb = lay.nb, kb = k / lay.G;
     const MRank& S = mg->rk[o];
@@ -211,7 +294,7 @@ struct LocalComm {
       }
     }
   }
-  void gather_rowpanel(int64_t k, int b) {
+  void gather_rowpanel(int64_t k, int b) override {
     const int64_t nrem = lay.nblk - k - 1;
     if (nrem <= 0) return;
     const int64_t nb = lay.nb;
@@ -242,7 +325,7 @@ struct LocalComm {
       R.ctx->launches++;
     }
   }
-  void bcast_colpanel(int64_t k, int b) {   // transposed: panel[b] is nb x (k+1)*nb, ld nb
+  void bcast_colpanel(int64_t k, int b) override {   // transposed: panel[b] is nb x (k+1)*nb, ld nb
     const MRank& S = mg->rk[lay.owner(k)];
     const int64_t rows = (k + 1) * lay.nb, cols = lay.nb;
     const double* src = S.L + (k / lay.G) * lay.nb * ld;
@@ -264,6 +347,115 @@ struct LocalComm {
   }
 };
 
+// COMM through pack -> collective -> unpack (transports 1 and 2).  Everything is issued on the main queue: NCCL wants
+// one consistent order of collectives per communicator, so the panels are not prefetched here.
+struct PackedComm : CommBase {
+  gpr_mgpu* mg;
+  DistLayout lay;
+  int64_t ld;
+  PackedComm(gpr_mgpu* m, const DistLayout& l, int64_t ld_) : mg(m), lay(l), ld(ld_) {}
+  MRank* local(int rank) { for (auto& R : mg->rk) if (R.rank == rank) return &R; return nullptr; }
+  void sync_all() { for (auto& R : mg->rk) { cudaSetDevice(R.ctx->device); R.be.note(cudaStreamSynchronize(R.ctx->stream)); } }
+  void nccl_note(MRank& R, ncclResult_t rc) { if (rc != ncclSuccess) R.be.note(cudaErrorUnknown); }
+  void copy2d(MRank& R, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
+    cudaSetDevice(R.ctx->device);
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows / 2 + 255) / 256, 64)), (unsigned)std::min<int64_t>(cols, 1024));
+    copy2d_kernel<<<grid, 256, 0, R.ctx->stream>>>(dst, ldd, src, lds, rows, cols);
+    R.be.note(cudaGetLastError());
+    R.ctx->launches++;
+  }
+  // buf(R): the same logical buffer on every rank
+  template <class F> void bcast(int root, F buf, size_t count) {
+    if (mg->transport == 2) {
+      for (auto& R : mg->rk) {
+        cudaSetDevice(R.ctx->device);
+        nccl_note(R, mg->nccl->Broadcast(buf(R), buf(R), count, ncclDouble, root, (ncclComm_t)mg->comm, R.ctx->stream));
+      }
+      return;
+    }
+    sync_all();
+    MRank* S = local(root);
+    for (auto& R : mg->rk)
+      if (&R != S) { cudaSetDevice(R.ctx->device); R.be.note(cudaMemcpyAsync(buf(R), buf(*S), sizeof(double) * count, cudaMemcpyDefault, R.ctx->stream)); }
+    sync_all();
+  }
+  // in place: rank r's contribution sits at stage + r * slot on rank r
+  void allgather_stage(size_t slot) {
+    if (mg->transport == 2) {
+      for (auto& R : mg->rk) {
+        cudaSetDevice(R.ctx->device);
+        nccl_note(R, mg->nccl->AllGather(R.stage + (size_t)R.rank * slot, R.stage, slot, ncclDouble, (ncclComm_t)mg->comm, R.ctx->stream));
+      }
+      return;
+    }
+    sync_all();
+    for (auto& D : mg->rk)
+      for (auto& S : mg->rk)
+        if (&D != &S) {
+          cudaSetDevice(D.ctx->device);
+          D.be.note(cudaMemcpyAsync(D.stage + (size_t)S.rank * slot, S.stage + (size_t)S.rank * slot, sizeof(double) * slot, cudaMemcpyDefault, D.ctx->stream));
+        }
+    sync_all();
+  }
+  void barrier() override {}
+  void bcast_diag(int64_t k, bool, int b) override {
+    const int o = lay.owner(k);
+    const int64_t nb = lay.nb, kb = k / lay.G, dl = (int64_t)lay.tpb() * 128 * 128;
+    if (MRank* S = local(o)) copy2d(*S, S->Ukk[b], nb, S->L + k * nb + kb * nb * ld, ld, nb, nb);   // pack
+    bcast(o, [b](MRank& R) { return R.Ukk[b]; }, (size_t)(nb * nb));
+    bcast(o, [k, dl](MRank& R) { return R.dinv + k * dl; }, (size_t)dl);
+  }
+  void gather_rowpanel(int64_t k, int b) override {
+    const int64_t nrem = lay.nblk - k - 1;
+    if (nrem <= 0) return;
+    const int64_t nb = lay.nb;
+    int64_t maxcnt = 0;
+    GatherMap gm{};
+    for (int s = 0; s < mg->G; ++s) {
+      gm.first[s] = (int)lay.count_le(s, k);
+      maxcnt = std::max<int64_t>(maxcnt, lay.nloc(s) - gm.first[s]);
+    }
+    for (int s = 0; s < mg->G; ++s) gm.off[s] = (int)(s * maxcnt);
+    const size_t slot = (size_t)(maxcnt * nb * nb);
+    for (auto& R : mg->rk) {   // pack this rank's blocks of the row panel
+      const int64_t first = gm.first[R.rank], cnt = lay.nloc(R.rank) - first;
+      if (cnt > 0) copy2d(R, R.stage + (size_t)R.rank * slot, nb, R.L + k * nb + first * nb * ld, ld, nb, cnt * nb);
+    }
+    allgather_stage(slot);
+    for (auto& R : mg->rk) {   // rank-major -> global column order
+      cudaSetDevice(R.ctx->device);
+      dim3 grid((unsigned)nrem, (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, 1024 / nrem)));
+      unpermute_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], R.stage, gm, mg->G, k, nb);
+      R.be.note(cudaGetLastError());
+      R.ctx->launches++;
+    }
+  }
+  void bcast_colpanel(int64_t k, int b) override {
+    const int o = lay.owner(k);
+    const int64_t rows = (k + 1) * lay.nb, cols = lay.nb;
+    if (MRank* S = local(o)) copy2d(*S, S->stage, rows, S->L + (k / lay.G) * lay.nb * ld, ld, rows, cols);   // pack
+    bcast(o, [](MRank& R) { return R.stage; }, (size_t)(rows * cols));
+    for (auto& R : mg->rk) {
+      cudaSetDevice(R.ctx->device);
+      const int64_t tiles = (rows / 32) * (cols / 32);
+      copy2d_transpose_kernel<<<(unsigned)std::min<int64_t>(tiles, 148 * 16), dim3(32, 8), 0, R.ctx->stream>>>(
+          R.panel[b], cols, R.stage, rows, rows / 32, cols / 32);
+      R.be.note(cudaGetLastError());
+      R.ctx->launches++;
+    }
+  }
+  void bcast_alpha(int root, int64_t count) override { bcast(root, [](MRank& R) { return R.alpha; }, (size_t)count); }
+  int sum_scal(int64_t off, int64_t count, double* host_out) override {
+    if (mg->transport == 2) {
+      for (auto& R : mg->rk) {
+        cudaSetDevice(R.ctx->device);
+        nccl_note(R, mg->nccl->AllReduce(R.scal + off, R.scal + off, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)mg->comm, R.ctx->stream));
+      }
+    }
+    return host_sum_scal(mg, off, count, host_out);   // transport 2: one local rank holding the global sum
+  }
+};
+
 // dense state of one distributed factorization
 struct MDense {
   DistLayout lay;
@@ -277,7 +469,7 @@ void mdense_free(gpr_mgpu* mg) {
     cudaStreamSynchronize(R.ctx->stream);
     cudaFree(R.L); cudaFree(R.dinv); cudaFree(R.gtile); cudaFree(R.stage); R.stage = nullptr;
     for (int b = 0; b < 2; ++b) { cudaFree(R.Ukk[b]); cudaFree(R.panel[b]); R.Ukk[b] = R.panel[b] = nullptr; }
-    cudaFree(R.x); cudaFree(R.y); cudaFree(R.hp); cudaFree(R.alpha); cudaFree(R.gpart); cudaFree(R.scal);
+    cudaFree(R.x); cudaFree(R.y); cudaFree(R.hp); cudaFree(R.alpha); cudaFree(R.gpart); cudaFree(R.scal); cudaFree(R.d_flag); R.d_flag = nullptr;
     R.L = R.dinv = R.x = R.y = R.hp = R.alpha = R.gpart = R.scal = nullptr;
     R.gtile = nullptr;
   }
@@ -287,8 +479,8 @@ int mdense_alloc(gpr_mgpu* mg, MDense& md, int64_t Np, int64_t nyp) {
   DistLayout& lay = md.lay;
   lay.G = mg->G; lay.nb = mg->nb; lay.Np = Np; lay.nblk = Np / mg->nb; lay.nyp = nyp;
   md.ld = Np;
-  for (int r = 0; r < mg->G; ++r) {
-    MRank& R = mg->rk[r];
+  for (auto& R : mg->rk) {
+    const int r = R.rank;
     MCK(cudaSetDevice(R.ctx->device));
     const int64_t lc = std::max<int64_t>(lay.lcols(r), 128);
     MCK(cudaMalloc(&R.L, sizeof(double) * Np * lc));
@@ -297,7 +489,8 @@ int mdense_alloc(gpr_mgpu* mg, MDense& md, int64_t Np, int64_t nyp) {
       MCK(cudaMalloc(&R.Ukk[b], sizeof(double) * lay.nb * lay.nb));
       MCK(cudaMalloc(&R.panel[b], sizeof(double) * Np * lay.nb));
     }
-    MCK(cudaMalloc(&R.stage, sizeof(double) * Np * lay.nb));
+    MCK(cudaMalloc(&R.stage, sizeof(double) * (Np + (int64_t)mg->G * lay.nb) * lay.nb));   // + one block per rank: padded all-gather slots
+    MCK(cudaMalloc(&R.d_flag, sizeof(long long)));
     const int64_t lt = std::max<int64_t>(lay.ltiles(r), 1);
     MCK(cudaMalloc(&R.gtile, sizeof(int) * lt));
     std::vector<int> gt((size_t)lt, 0);
@@ -310,18 +503,15 @@ int mdense_alloc(gpr_mgpu* mg, MDense& md, int64_t Np, int64_t nyp) {
 }
 
 std::vector<DistRank<CudaBE>> mdense_ranks(gpr_mgpu* mg, const MDense& md) {
-  std::vector<DistRank<CudaBE>> v((size_t)mg->G);
-  for (int r = 0; r < mg->G; ++r) {
-    MRank& R = mg->rk[r];
-    v[r] = DistRank<CudaBE>{r, &R.be, R.L, md.ld, R.dinv, {R.Ukk[0], R.Ukk[1]}, {R.panel[0], R.panel[1]}, R.gtile};
-  }
+  std::vector<DistRank<CudaBE>> v;
+  for (auto& R : mg->rk)
+    v.push_back(DistRank<CudaBE>{R.rank, &R.be, R.L, md.ld, R.dinv, {R.Ukk[0], R.Ukk[1]}, {R.panel[0], R.panel[1]}, R.gtile});
   return v;
 }
 
 int msync_all(gpr_mgpu* mg, const char* where, long long* info) {
   long long first = 0;
-  for (int r = 0; r < mg->G; ++r) {
-    MRank& R = mg->rk[r];
+  for (auto& R : mg->rk) {
     MCK(cudaSetDevice(R.ctx->device));
     long long h = 0;
     MCK(cudaMemcpyAsync(&h, R.ctx->d_info, sizeof h, cudaMemcpyDeviceToHost, R.ctx->stream));
@@ -329,13 +519,30 @@ int msync_all(gpr_mgpu* mg, const char* where, long long* info) {
     if (R.ctx->pending != cudaSuccess) {
       cudaError_t e = R.ctx->pending; R.ctx->pending = cudaSuccess;
       char b[256];
-      snprintf(b, sizeof b, "CUDA error %d (%s) in %s on rank %d", (int)e, cudaGetErrorString(e), where, r);
+      snprintf(b, sizeof b, "CUDA / NCCL error %d (%s) in %s on rank %d", (int)e, cudaGetErrorString(e), where, R.rank);
       return mfail(mg, GPR_ERR_CUDA, b);
     }
     if (h && (!first || h < first)) first = h;
   }
+  if (mg->transport == 2 && info) {
+    // every process must take the same branch on a failed factorization: smallest failing pivot over all ranks
+    // (max of 2^62 - pivot; 0 = no failure)
+    MRank& R = mg->rk[0];
+    long long enc = first ? (1LL << 62) - first : 0;
+    MCK(cudaMemcpyAsync(R.d_flag, &enc, sizeof enc, cudaMemcpyHostToDevice, R.ctx->stream));
+    if (mg->nccl->AllReduce(R.d_flag, R.d_flag, 1, ncclInt64, ncclMax, (ncclComm_t)mg->comm, R.ctx->stream) != ncclSuccess)
+      return mfail(mg, GPR_ERR_CUDA, "ncclAllReduce(status) failed");
+    MCK(cudaMemcpyAsync(&enc, R.d_flag, sizeof enc, cudaMemcpyDeviceToHost, R.ctx->stream));
+    MCK(cudaStreamSynchronize(R.ctx->stream));
+    first = enc ? (1LL << 62) - enc : 0;
+  }
   if (info) *info = first;
   return GPR_OK;
+}
+
+std::unique_ptr<CommBase> make_comm(gpr_mgpu* mg, const DistLayout& lay, int64_t ld) {
+  if (mg->transport == 0) return std::unique_ptr<CommBase>(new LocalComm(mg, lay, ld));
+  return std::unique_ptr<CommBase>(new PackedComm(mg, lay, ld));
 }
 
 }  // namespace
@@ -365,6 +572,7 @@ int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** out) 
     int rc = gpr_ctx_create(devices[r], &mg->rk[r].ctx);
     if (rc) { std::string e = g_create_error; gpr_mgpu_destroy(mg); g_create_error = e; return rc; }
     mg->rk[r].be = CudaBE{mg->rk[r].ctx};
+    mg->rk[r].rank = r;
     if (cudaEventCreateWithFlags(&mg->rk[r].ev, cudaEventDisableTiming) != cudaSuccess) {
       gpr_mgpu_destroy(mg);
       return mfail(nullptr, GPR_ERR_CUDA, "cudaEventCreate failed");
@@ -390,9 +598,55 @@ int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** out) 
   return GPR_OK;
 }
 
+int gpr_dist_unique_id(void* id128) {
+  if (!id128) return GPR_ERR_ARG;
+  std::string err;
+  NcclApi* api = nccl_api(err);
+  if (!api) return mfail(nullptr, GPR_ERR_UNSUPPORTED, err);
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (api->GetUniqueId(&id) != ncclSuccess) return mfail(nullptr, GPR_ERR_CUDA, "ncclGetUniqueId failed");
+  memcpy(id128, &id, sizeof id);
+  return GPR_OK;
+}
+
+int gpr_dist_create(int device, int rank, int world, const void* id128, int64_t nb, gpr_mgpu** out) {
+  if (!out || !id128) return mfail(nullptr, GPR_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (world < 1 || world > MGPU_MAX_RANKS || rank < 0 || rank >= world) return mfail(nullptr, GPR_ERR_ARG, "rank / world out of range (world <= 16)");
+  if (nb < 128 || nb % 128) return mfail(nullptr, GPR_ERR_ARG, "panel width nb must be a positive multiple of 128");
+  std::string err;
+  NcclApi* api = nccl_api(err);
+  if (!api) return mfail(nullptr, GPR_ERR_UNSUPPORTED, err);
+  gpr_mgpu* mg = new gpr_mgpu();
+  mg->G = world; mg->nb = nb; mg->transport = 2; mg->nccl = api;
+  mg->prefetch_trtri = mg->prefetch_lauum = 0;
+  mg->rk.resize(1);
+  int rc = gpr_ctx_create(device, &mg->rk[0].ctx);
+  if (rc) { std::string e = g_create_error; gpr_mgpu_destroy(mg); g_create_error = e; return rc; }
+  mg->rk[0].be = CudaBE{mg->rk[0].ctx};
+  mg->rk[0].rank = rank;
+  cudaEventCreateWithFlags(&mg->rk[0].ev, cudaEventDisableTiming);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ncclComm_t comm = nullptr;
+  ncclResult_t nr = api->CommInitRank(&comm, world, id, rank);
+  if (nr != ncclSuccess) {
+    std::string e = std::string("ncclCommInitRank failed: ") + (api->GetErrorString ? api->GetErrorString(nr) : "?");
+    gpr_mgpu_destroy(mg);
+    return mfail(nullptr, GPR_ERR_CUDA, e);
+  }
+  mg->comm = comm;
+  cudaEventCreate(&mg->t0); cudaEventCreate(&mg->t1);
+  cudaEventCreate(&mg->tot0); cudaEventCreate(&mg->tot1);
+  *out = mg;
+  return GPR_OK;
+}
+
 int gpr_mgpu_destroy(gpr_mgpu* mg) {
   if (!mg) return GPR_OK;
   mdense_free(mg);
+  if (mg->comm && mg->nccl) { cudaSetDevice(mg->rk[0].ctx->device); mg->nccl->CommDestroy((ncclComm_t)mg->comm); mg->comm = nullptr; }
   for (auto& R : mg->rk) {
     if (!R.ctx) continue;
     cudaSetDevice(R.ctx->device);
@@ -410,6 +664,14 @@ int gpr_mgpu_destroy(gpr_mgpu* mg) {
 int gpr_mgpu_set_option(gpr_mgpu* mg, const char* name, int64_t value) {
   if (!mg || !name) return GPR_ERR_ARG;
   if (value < 0 || value > 2) return mfail(mg, GPR_ERR_ARG, "option value must be 0, 1 or 2");
+  if (!strcmp(name, "transport")) {
+    if (mg->transport == 2 || value == 2) return mfail(mg, GPR_ERR_ARG, "transport 2 (NCCL, one process per rank) is chosen by gpr_dist_create only");
+    if (mg->rk[0].L) return mfail(mg, GPR_ERR_STATE, "set the transport before creating a model");
+    mg->transport = (int)value;
+    if (value != 0) mg->prefetch_trtri = mg->prefetch_lauum = 0;
+    return GPR_OK;
+  }
+  if (mg->transport != 0 && value != 0) return mfail(mg, GPR_ERR_UNSUPPORTED, "the packed transports issue every collective on the main queue (no prefetch)");
   if (!strcmp(name, "prefetch_trtri")) { mg->prefetch_trtri = (int)value; return GPR_OK; }
   if (!strcmp(name, "prefetch_lauum")) { mg->prefetch_lauum = (int)value; return GPR_OK; }
   return mfail(mg, GPR_ERR_ARG, std::string("unknown option ") + name);
@@ -419,7 +681,7 @@ const char* gpr_mgpu_last_error(gpr_mgpu* mg) { return mg ? mg->err.c_str() : g_
 
 int64_t gpr_mgpu_launch_count(gpr_mgpu* mg) {
   int64_t n = 0;
-  if (mg) for (auto& R : mg->rk) n += R.ctx->launches;
+  if (mg) for (auto& R : mg->rk) if (R.ctx) n += R.ctx->launches;
   return n;
 }
 
@@ -440,8 +702,7 @@ int gpr_mgpu_model_create(gpr_mgpu* mg, const int* comp_types, int ncomp, int D,
   m->Np = round_up(N, mg->nb); m->nyp = round_up(ny, 128);
   rc = mdense_alloc(mg, m->md, m->Np, m->nyp);
   if (rc) { mdense_free(mg); delete m; return rc; }
-  for (int r = 0; r < mg->G; ++r) {
-    MRank& R = mg->rk[r];
+  for (auto& R : mg->rk) {
     cudaError_t e = cudaSetDevice(R.ctx->device);
     auto A = [&](double** p, size_t elems) { if (e == cudaSuccess) e = cudaMalloc(p, elems * sizeof(double)); };
     A(&R.x, (size_t)D * N);
@@ -487,7 +748,7 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
   auto tick = [&]() { cudaSetDevice(mg->rk[0].ctx->device); cudaEventRecord(mg->t0, mg->rk[0].ctx->stream); };
   auto tock = [&](int slot) -> int {
     // phase time = rank 0's stream from tick to the point where every rank has finished the phase
-    for (int r = 0; r < Gn; ++r) { cudaSetDevice(mg->rk[r].ctx->device); MCK(cudaStreamSynchronize(mg->rk[r].ctx->stream)); }
+    for (auto& R : mg->rk) { cudaSetDevice(R.ctx->device); MCK(cudaStreamSynchronize(R.ctx->stream)); }
     cudaSetDevice(mg->rk[0].ctx->device);
     MCK(cudaEventRecord(mg->t1, mg->rk[0].ctx->stream));
     MCK(cudaEventSynchronize(mg->t1));
@@ -501,12 +762,13 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
 
   // ---- covariance build into the block-cyclic layout (upper triangle, zero below), y columns
   tick();
-  for (int r = 0; r < Gn; ++r) {
-    MRank& R = mg->rk[r];
+  for (auto& R : mg->rk) {
+    const int r = R.rank;
     gpr_ctx* ctx = R.ctx;
     MCK(cudaSetDevice(ctx->device));
     MCK(cudaMemcpyAsync(R.hp, hp.data(), sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
     MCK(cudaMemsetAsync(ctx->d_info, 0, sizeof(long long), ctx->stream));
+    MCK(cudaMemsetAsync(R.scal, 0, sizeof(double) * (P + 3), ctx->stream));
     for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
       const int64_t J = lay.gblock(r, lb);
       const int64_t cvalid = std::max<int64_t>(0, std::min<int64_t>(nb, N - J * nb));
@@ -529,16 +791,17 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
   { int rc = tock(GPR_T_KBUILD); if (rc) return rc; }
 
   auto ranks = mdense_ranks(mg, m->md);
-  LocalComm comm{mg, lay, ld};
-  DistBlocked<CudaBE, LocalComm> db(lay, ranks, comm);
+  std::unique_ptr<CommBase> comm_p = make_comm(mg, lay, ld);
+  CommBase& comm = *comm_p;
+  DistBlocked<CudaBE, CommBase> db(lay, ranks, comm);
   db.prefetch_trtri = mg->prefetch_trtri != 0;
   db.prefetch_lauum = mg->prefetch_lauum != 0;
 
   // ---- potrf (+ forward substitution of y), log det
   tick();
   db.potrf();
-  for (int r = 0; r < Gn; ++r) {
-    MRank& R = mg->rk[r];
+  for (auto& R : mg->rk) {
+    const int r = R.rank;
     MCK(cudaSetDevice(R.ctx->device));
     dist_logdiag_kernel<<<1, 1024, 0, R.ctx->stream>>>(R.L, ld, lay.nloc(r) * nb, nb, Gn, r, R.scal);
     R.ctx->launches++;
@@ -556,15 +819,18 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
   }
 
   const int yo = lay.y_owner();
+  MRank* Ry = nullptr;                       // the local rank that owns the y columns (if it lives in this process)
+  for (auto& R : mg->rk) if (R.rank == yo) Ry = &R;
   if (!G) {
     // loss only: y^T K^-1 y = |z|^2 with z = U^-T y, which the potrf sweep left in the y columns -- no back
     // substitution and no inverse needed (alpha is not formed: gpr_mgpu_fetch(ALPHA) then reports a state error)
     tick();
-    MRank& R = mg->rk[yo];
-    MCK(cudaSetDevice(R.ctx->device));
-    sumsq_kernel<<<1, 1024, 0, R.ctx->stream>>>(R.L + (lay.ycol0(yo) + (m->train_axis - 1)) * ld, N, R.scal + 1);
-    R.ctx->launches++;
-    MCK(cudaGetLastError());
+    if (Ry) {
+      MCK(cudaSetDevice(Ry->ctx->device));
+      sumsq_kernel<<<1, 1024, 0, Ry->ctx->stream>>>(Ry->L + (lay.ycol0(yo) + (m->train_axis - 1)) * ld, N, Ry->scal + 1);
+      Ry->ctx->launches++;
+      MCK(cudaGetLastError());
+    }
     m->have_alpha = false;
     { int rc = tock(GPR_T_POTRS); if (rc) return rc; }
   } else {
@@ -574,32 +840,24 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
     db.trtri();
     { int rc = tock(GPR_T_TRTRI); if (rc) return rc; }
     tick();
-    MRank& R = mg->rk[yo];
-    MCK(cudaSetDevice(R.ctx->device));
-    const double* X = R.L + (lay.ycol0(yo) + (m->train_axis - 1)) * ld;
-    dist_alpha_kernel<<<1, 1024, 0, R.ctx->stream>>>(X, R.y + (int64_t)(m->train_axis - 1) * N, N, Np, R.alpha, R.scal);
-    R.ctx->launches++;
-    MCK(cudaGetLastError());
-    comm.barrier();
-    for (int r = 0; r < Gn; ++r)
-      if (r != yo) comm.copy2d(r, mg->rk[r].alpha, Np, R.alpha, Np, Np, 1);
+    if (Ry) {
+      MCK(cudaSetDevice(Ry->ctx->device));
+      const double* X = Ry->L + (lay.ycol0(yo) + (m->train_axis - 1)) * ld;
+      dist_alpha_kernel<<<1, 1024, 0, Ry->ctx->stream>>>(X, Ry->y + (int64_t)(m->train_axis - 1) * N, N, Np, Ry->alpha, Ry->scal);
+      Ry->ctx->launches++;
+      MCK(cudaGetLastError());
+    }
+    comm.bcast_alpha(yo, Np);
     m->have_alpha = true;
     { int rc = tock(GPR_T_POTRS); if (rc) return rc; }
   }
 
   double Fv = 0.0;
   {
-    double logdiag = 0.0, ya = 0.0;
-    for (int r = 0; r < Gn; ++r) {
-      MRank& R = mg->rk[r];
-      double sc[2];
-      MCK(cudaSetDevice(R.ctx->device));
-      MCK(cudaMemcpyAsync(sc, R.scal, sizeof sc, cudaMemcpyDeviceToHost, R.ctx->stream));
-      MCK(cudaStreamSynchronize(R.ctx->stream));
-      logdiag += sc[0];
-      if (r == lay.y_owner()) ya = sc[1];
-    }
-    Fv = 0.5 * (ya + 2.0 * logdiag + (double)N * std::log(2.0 * M_PI));   // src/loss_grad.jl:40
+    double sc[2];   // [sum of the ranks' log-diagonal shares, y . alpha (non-zero on the y owner only)]
+    int rc = comm.sum_scal(0, 2, sc);
+    if (rc) return rc;
+    Fv = 0.5 * (sc[1] + 2.0 * sc[0] + (double)N * std::log(2.0 * M_PI));   // src/loss_grad.jl:40
   }
 
   if (G) {
@@ -610,9 +868,9 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
     { int rc = tock(GPR_T_LAUUM); if (rc) return rc; }
     m->have_inverse = true;
     tick();
-    std::vector<double> tot((size_t)P + 1, 0.0), part((size_t)P + 1);
-    for (int r = 0; r < Gn; ++r) {
-      MRank& R = mg->rk[r];
+    std::vector<double> tot((size_t)P + 1, 0.0);
+    for (auto& R : mg->rk) {
+      const int r = R.rank;
       gpr_ctx* ctx = R.ctx;
       MCK(cudaSetDevice(ctx->device));
       GradArgs a{};
@@ -626,13 +884,7 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
       ctx->launches++;
       MCK(cudaGetLastError());
     }
-    for (int r = 0; r < Gn; ++r) {   // fixed rank order: deterministic
-      MRank& R = mg->rk[r];
-      MCK(cudaSetDevice(R.ctx->device));
-      MCK(cudaMemcpyAsync(part.data(), R.scal + 2, sizeof(double) * (P + 1), cudaMemcpyDeviceToHost, R.ctx->stream));
-      MCK(cudaStreamSynchronize(R.ctx->stream));
-      for (int s = 0; s <= P; ++s) tot[s] += part[s];
-    }
+    { int rc = comm.sum_scal(2, P + 1, tot.data()); if (rc) return rc; }   // fixed rank order (or NCCL's fixed tree): deterministic
     // sigma: -acc/|sigma| ; l_d: +l_d * acc ; noise: -sigma_n * acc_diag  (loss_grad.jl:43-52, deriv_covar.jl:23,26,31)
     for (int c = 0; c < m->spec.ncomp; ++c) {
       const int off = m->spec.hp_off[c];
@@ -665,6 +917,8 @@ int gpr_mgpu_fetch(gpr_mgpu_model* m, int which, double* out) {
   gpr_mgpu* mg = m->mg;
   const DistLayout& lay = m->md.lay;
   const int64_t N = m->N, nb = lay.nb, ld = m->md.ld;
+  if (which == GPR_FETCH_KINV && mg->transport == 2)
+    return mfail(mg, GPR_ERR_UNSUPPORTED, "fetch K^-1: with one process per rank every process holds its own block columns only");
   if (which == GPR_FETCH_ALPHA) {
     if (!m->have_alpha) return mfail(mg, GPR_ERR_STATE, "fetch alpha: the last evaluation was loss-only (no back substitution)");
     MRank& R = mg->rk[0];
@@ -675,8 +929,8 @@ int gpr_mgpu_fetch(gpr_mgpu_model* m, int which, double* out) {
   }
   if (which != GPR_FETCH_KINV) return mfail(mg, GPR_ERR_ARG, "unknown fetch selector");
   if (!m->have_inverse) return mfail(mg, GPR_ERR_STATE, "fetch K^-1: cache holds no inverse");
-  for (int r = 0; r < mg->G; ++r) {
-    MRank& R = mg->rk[r];
+  for (auto& R : mg->rk) {
+    const int r = R.rank;
     MCK(cudaSetDevice(R.ctx->device));
     for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
       const int64_t J = lay.gblock(r, lb);
@@ -706,8 +960,8 @@ int gpr_mgpu_dbg_factor(gpr_mgpu* mg, double* A, int64_t N, double* Y, int ny, i
   const DistLayout& lay = md.lay;
   std::vector<double> col((size_t)Np * nb);
   auto body = [&]() -> int {
-    for (int r = 0; r < mg->G; ++r) {
-      MRank& R = mg->rk[r];
+    for (auto& R : mg->rk) {
+      const int r = R.rank;
       MCK(cudaSetDevice(R.ctx->device));
       for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
         const int64_t J = lay.gblock(r, lb);
@@ -728,8 +982,9 @@ int gpr_mgpu_dbg_factor(gpr_mgpu* mg, double* A, int64_t N, double* Y, int ny, i
       }
     }
     auto ranks = mdense_ranks(mg, md);
-    LocalComm comm{mg, lay, md.ld};
-    DistBlocked<CudaBE, LocalComm> db(lay, ranks, comm);
+    std::unique_ptr<CommBase> comm_p = make_comm(mg, lay, md.ld);
+    CommBase& comm = *comm_p;
+    DistBlocked<CudaBE, CommBase> db(lay, ranks, comm);
     db.prefetch_trtri = mg->prefetch_trtri != 0;
     db.prefetch_lauum = mg->prefetch_lauum != 0;
     double t[3] = {0, 0, 0};
@@ -738,7 +993,7 @@ int gpr_mgpu_dbg_factor(gpr_mgpu* mg, double* A, int64_t N, double* Y, int ny, i
       cudaEventRecord(mg->t0, mg->rk[0].ctx->stream);
       comm.dma_mode = ph == 1 ? mg->prefetch_trtri : mg->prefetch_lauum;
       if (ph == 0) db.potrf(); else if (ph == 1) db.trtri(); else db.lauum();
-      for (int r = 0; r < mg->G; ++r) { cudaSetDevice(mg->rk[r].ctx->device); MCK(cudaStreamSynchronize(mg->rk[r].ctx->stream)); }
+      for (auto& R : mg->rk) { cudaSetDevice(R.ctx->device); MCK(cudaStreamSynchronize(R.ctx->stream)); }
       cudaSetDevice(mg->rk[0].ctx->device);
       cudaEventRecord(mg->t1, mg->rk[0].ctx->stream);
       MCK(cudaEventSynchronize(mg->t1));
@@ -750,8 +1005,8 @@ int gpr_mgpu_dbg_factor(gpr_mgpu* mg, double* A, int64_t N, double* Y, int ny, i
     int rc2 = msync_all(mg, "dbg_factor", &h_info);
     if (rc2) return rc2;
     if (info) *info = h_info;
-    for (int r = 0; r < mg->G; ++r) {
-      MRank& R = mg->rk[r];
+    for (auto& R : mg->rk) {
+      const int r = R.rank;
       MCK(cudaSetDevice(R.ctx->device));
       for (int64_t lb = 0; lb < lay.nloc(r); ++lb) {
         const int64_t J = lay.gblock(r, lb);

@@ -2,7 +2,7 @@
 predict API.  All arithmetic runs in libgpr_sm100a.so (hand-written CUDA, C ABI in include/gpr_sm100a.h);
 there is no CPU fallback."""
 from . import _ffi  # noqa: F401
-from ._ffi import Context, GPRError, ModelHandle, MultiContext, MultiModelHandle, PosDefException, get_context  # noqa: F401
+from ._ffi import Context, GPRError, ModelHandle, MultiContext, MultiModelHandle, DistContext, PosDefException, get_context  # noqa: F401
 from .api import *  # noqa: F401,F403
 from .api import (Cmap, ComposedKernel, Diagonal, Euclidean, GPRModel, GPRPredictCache, GPRSplitPredictCache,  # noqa: F401
                   LogScale, MarginalLikelihood, Matern52, MllGradCache, MllLossCache, MultiGPUGradCache, NoLogScale, SplitKernel,

@@ -61,6 +61,8 @@ _SIGS = {
                                 C.c_double, _dp, _i64, C.c_int, C.c_int, _dp]),
     "gpr_dbg_factor": (C.c_int, [_vp, _dp, _i64, C.c_int, C.POINTER(_i64), _dp]),
     "gpr_mgpu_create": (C.c_int, [C.c_int, _ip, _i64, C.POINTER(_vp)]),
+    "gpr_dist_unique_id": (C.c_int, [_vp]),
+    "gpr_dist_create": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _i64, C.POINTER(_vp)]),
     "gpr_mgpu_destroy": (C.c_int, [_vp]),
     "gpr_mgpu_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "gpr_mgpu_last_error": (C.c_char_p, [_vp]),
@@ -382,7 +384,7 @@ class MultiContext:
     """gpr_mgpu: one process driving several ranks (one per entry of `devices`; a device may repeat) for the
     block-cyclic multi-GPU NLML + gradient (BASELINE.json config 5)."""
 
-    def __init__(self, devices, nb=1024):
+    def __init__(self, devices, nb=1024, transport=0):
         self.devices = [int(d) for d in devices]
         self.nb = int(nb)
         self._h = _vp()
@@ -392,6 +394,8 @@ class MultiContext:
             msg = lib().gpr_mgpu_last_error(None)
             self._h = None
             raise GPRError(f"gpr_mgpu_create(devices={self.devices}) failed ({rc}): {msg.decode() if msg else ''}")
+        if transport:
+            self.set_option("transport", transport)
 
     @property
     def handle(self):
@@ -433,6 +437,31 @@ class MultiContext:
             self.close()
         except Exception:
             pass
+
+
+def dist_unique_id():
+    """128-byte NCCL unique id (call on rank 0, ship the bytes to the other processes)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().gpr_dist_unique_id(C.cast(buf, _vp))
+    if rc != 0:
+        msg = lib().gpr_mgpu_last_error(None)
+        raise GPRError(f"gpr_dist_unique_id failed ({rc}): {msg.decode() if msg else ''}")
+    return buf.raw
+
+
+class DistContext(MultiContext):
+    """One rank of a block-cyclic factorization that spans `world` PROCESSES (one GPU each, torchrun-style launch);
+    panels travel over NCCL.  Same use as MultiContext afterwards (MultiModelHandle, nlml_grad on every rank)."""
+
+    def __init__(self, device, rank, world, unique_id, nb=1024):
+        self.devices, self.nb, self.rank, self.world = [int(device)], int(nb), int(rank), int(world)
+        self._h = _vp()
+        idbuf = C.create_string_buffer(bytes(unique_id), 128)
+        rc = lib().gpr_dist_create(int(device), int(rank), int(world), C.cast(idbuf, _vp), self.nb, C.byref(self._h))
+        if rc != 0:
+            msg = lib().gpr_mgpu_last_error(None)
+            self._h = None
+            raise GPRError(f"gpr_dist_create(rank={rank}/{world}) failed ({rc}): {msg.decode() if msg else ''}")
 
 
 class MultiModelHandle:

@@ -83,3 +83,17 @@ def replicated_nlml_grad(eval_fn, hp_sets, group=None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)   # disjoint supports: a gather expressed as a sum
         local = t.cpu().numpy()
     return local[:, 0], local[:, 1:]
+
+
+def dist_context(device=None, nb=1024, group=None):
+    """DistContext for this torch.distributed rank: rank 0 draws the NCCL unique id of the library's own communicator
+    and broadcasts it through the already initialised process group (any backend)."""
+    import torch
+    from . import _ffi
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ids = [_ffi.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0, group=group)
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    return _ffi.DistContext(device, rank, world, ids[0], nb=nb)

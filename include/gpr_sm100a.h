@@ -188,7 +188,18 @@ typedef struct gpr_mgpu_model gpr_mgpu_model;
 
 int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** mg);
 int gpr_mgpu_destroy(gpr_mgpu* mg);
-/* "prefetch_trtri" / "prefetch_lauum": how the panels of the next step travel while the current step computes:
+/* One rank per PROCESS (torchrun / MPI-style launch) for the same factorization: rank 0 obtains a 128-byte NCCL
+ * unique id, ships it to the other processes by whatever means the host has (torch.distributed, MPI, a file), and every
+ * process calls gpr_dist_create with it.  The handle is then used with gpr_mgpu_model_create / gpr_mgpu_nlml_grad /
+ * gpr_mgpu_fetch(ALPHA) / gpr_mgpu_timings exactly like a single-process one: every process passes the same x, y, hp and
+ * receives the same F and G.  Panels travel by ncclBroadcast / ncclAllGather, the P + 3 partial sums by ncclAllReduce.
+ * NCCL is loaded with dlopen("libnccl.so.2") on first use; the library itself links the CUDA runtime only. */
+int gpr_dist_unique_id(void* id128);
+int gpr_dist_create(int device, int rank, int world, const void* id128, int64_t nb, gpr_mgpu** mg);
+
+/* "transport": 0 (default) peer-memory pulls, 1 = the pack / collective / unpack data path of the NCCL transport with
+ * in-process copies (test of that path on one GPU); set before creating a model.
+ * "prefetch_trtri" / "prefetch_lauum": how the panels of the next step travel while the current step computes:
  * 0 = on the main queue before the step (no overlap), 1 = side queue with SM-driven peer reads, 2 = side queue through
  * the copy engines.  Default 2 for both (measured on 8 x B200, profiles/README.md). */
 int gpr_mgpu_set_option(gpr_mgpu* mg, const char* name, int64_t value);

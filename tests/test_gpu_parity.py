@@ -649,3 +649,34 @@ def test_mgpu_prefetch_modes_agree(gpr):
     for A, Y in outs[1:]:
         assert np.array_equal(A, outs[0][0]) and np.array_equal(Y, outs[0][1])
     assert np.abs(np.triu(outs[0][0]) - np.triu(np.linalg.inv(K))).max() <= 1e-11 * np.abs(np.linalg.inv(K)).max()
+
+
+def test_mgpu_packed_transport_matches_peer_transport(gpr):
+    """Transport 1 runs the pack -> collective -> unpack data path of the NCCL transport (gpr_dist_create) with in-process
+    copies as the collective: same arithmetic, so the results must equal the peer-memory transport bit for bit."""
+    from gpr_sm100a import _ffi
+    rng = np.random.default_rng(31)
+    n = 1280
+    X = rng.standard_normal((n, n))
+    K = X @ X.T / n + np.eye(n)
+    Y0 = rng.standard_normal((n, 2))
+    res = []
+    for transport in (0, 1):
+        mc = _ffi.MultiContext(_devices(3), nb=256, transport=transport)
+        A, Y, _ = mc.dbg_factor(np.triu(K), Y0, 2)
+        mc.close()
+        res.append((A, Y))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    # model level: F, G, alpha through the packed transport vs the oracle
+    D, N = 4, 900
+    x = rng.random((D, N))
+    y = np.sin(3 * x).sum(0) + 0.1 * rng.standard_normal(N)
+    hp = np.concatenate([[1.0], 0.6 * np.ones(D), [0.1]])
+    Fo, Go = o.loss_grad(hp, o.GPRModel((o.SE, o.NOISE), hp, x, y))
+    mc = _ffi.MultiContext(_devices(4), nb=128, transport=1)
+    mm = _ffi.MultiModelHandle(mc, [1, 2], D, x, y)
+    F, G = mm.nlml_grad(hp)
+    Fl, _ = mm.nlml_grad(hp, want_g=False)
+    assert abs(F - Fo) <= TOL_F * abs(Fo) and abs(Fl - Fo) <= TOL_F * abs(Fo)
+    assert grad_err(G, Go) <= TOL_G
+    mm.close(); mc.close()
