@@ -1,7 +1,7 @@
 """Config 5 with ONE PROCESS PER GPU (torchrun) and NCCL as the transport of the block-cyclic factorization:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P \
-        tools/config5_dist.py [--n N] [--nb 1024] [--check]
+        tools/config5_dist.py [N [NB [check]]]          (positional: torchrun would try to parse --n... itself)
 
 Every rank evaluates NLML + gradient of the same model; rank 0 prints one JSON line.  --check also runs the
 single-process path (gpr_mgpu_*, peer-memory transport, ranks cycled over the visible devices) on rank 0 and compares."""
@@ -20,11 +20,12 @@ sys.path.insert(0, os.path.join(ROOT, "gaussianprocessregression.jl_b200"))
 from gpr_sm100a import _ffi, shard  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=32768)
-ap.add_argument("--d", type=int, default=16)
-ap.add_argument("--nb", type=int, default=1024)
-ap.add_argument("--check", action="store_true")
+ap.add_argument("n", type=int, nargs="?", default=32768)
+ap.add_argument("nb", type=int, nargs="?", default=1024)
+ap.add_argument("check", nargs="?", default="")
 args = ap.parse_args()
+args.d = 16
+args.check = args.check == "check"
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
