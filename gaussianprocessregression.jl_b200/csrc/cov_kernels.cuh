@@ -51,6 +51,7 @@ struct KBuildArgs {
   const double* mean_w;
   double* mean_partial;
   double all_shift;      // added to EVERY valid entry (prior sampling: `Sigma .+ 1e-7`, src/distributions.jl:25)
+  int lower_only;        // write only the entries strictly below the diagonal (fills in what a zero_lower build left out)
 };
 
 constexpr int KB_TILE = 64;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_kernel(const KBuildArgs a) 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const long long r0 = (long long)blockIdx.x * KB_TILE, c0 = (long long)blockIdx.y * KB_TILE;
 
+  if (a.lower_only && r0 + (KB_TILE - 1) <= c0 + a.diag_shift) return;   // tile entirely on / above the diagonal
   if (a.zero_lower && r0 > c0 + a.diag_shift + (KB_TILE - 1)) {   // tile entirely below the diagonal
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_kernel(const KBuildArgs a) 
     for (int i = 0; i < 4; ++i) {
       const long long r = r0 + tx + 16 * i;
       if (r >= a.Rp || c >= a.Cp) continue;
+      if (a.lower_only && r <= c + a.diag_shift) continue;
       double v;
       if (r < a.R && c < a.C) {
         v = sum[i][j];

@@ -203,6 +203,7 @@ struct gpr_model {
   bool kinv_alias = false;
   // state
   bool have_factor = false, have_inverse = false, factor_destroyed = false, kinv_symmetric = false;
+  bool lower_is_k = false;   // strict lower triangle of d_U holds K (filled on demand by gpr_fetch(U))
   std::vector<double> hp_host;
   double eps_host = 0.0;
   int64_t info_host = 0;
@@ -270,6 +271,10 @@ int factor_and_solve(gpr_model* m, const double* hp, double eps, int64_t* info, 
     a.out = m->d_U; a.ldo = Np; a.R = N; a.C = N; a.Rp = Np; a.Cp = Np;
     a.x1 = m->d_x; a.x2 = m->d_x; a.D = m->D; a.hp = m->d_hp; a.spec = m->spec;
     a.eps = eps; a.same = 1; a.add_noise = 1; a.pad_identity = 1; a.sigma_one = 0; a.row_scale = nullptr; a.diag_shift = 0;
+    // nothing on the path reads the strict lower triangle; it is only part of the reference's cache contents
+    // (kchol_base keeps K there, test/test_loss.jl:46), so it is filled in lazily by gpr_fetch(U)
+    a.zero_lower = 1;
+    m->lower_is_k = false;
     int rc = launch_kbuild(ctx, DM_EUCLID, a);
     if (rc) return rc;
   }
@@ -727,6 +732,15 @@ int gpr_fetch(gpr_model* m, int which, double* out) {
   const int64_t N = m->N, Np = m->Np;
   if (which == GPR_FETCH_U) {
     if (!m->have_factor || m->factor_destroyed) return fail(ctx, GPR_ERR_STATE, "fetch U: no factorization in the cache");
+    if (!m->lower_is_k) {   // strict lower = K, exactly what dpotrf('U') leaves in tc.kchol_base
+      KBuildArgs a{};
+      a.out = m->d_U; a.ldo = Np; a.R = N; a.C = N; a.Rp = Np; a.Cp = Np;
+      a.x1 = m->d_x; a.x2 = m->d_x; a.D = m->D; a.hp = m->d_hp; a.spec = m->spec;
+      a.eps = m->eps_host; a.same = 1; a.add_noise = 1; a.pad_identity = 1; a.lower_only = 1;
+      int rc = launch_kbuild(ctx, DM_EUCLID, a);
+      if (rc) return rc;
+      m->lower_is_k = true;
+    }
     CK(cudaMemcpy2DAsync(out, sizeof(double) * N, m->d_U, sizeof(double) * Np, sizeof(double) * N, N, cudaMemcpyDeviceToHost, ctx->stream));
   } else if (which == GPR_FETCH_ALPHA) {
     if (!m->have_factor) return fail(ctx, GPR_ERR_STATE, "fetch alpha: no factorization in the cache");
