@@ -10,6 +10,7 @@
 //   be.potrf_leaf(A, lda, Dinv_blk, global_row_offset)   128x128 diagonal block:
 //        A(upper) <- chol(A) (U^T U = A) and Dinv_blk <- inv(U) (full 128x128, zeros below the diagonal)
 //   be.transpose_inplace(A, ld, n)   A <- A^T (n x n, in place)
+//   be.copy_dinv_128_t(dst, ldd, src128, batch, stride, dstride)   the same with the TRANSPOSED Dinv block, full block
 //   be.copy_dinv_128(dst, ldd, src128, batch, stride, dstride, full)
 //        dst (128 block; member z at dst + z*stride) <- Dinv block (src + z*dstride); upper part only, or the
 //        full block incl. the explicit zeros below the diagonal when full
@@ -168,6 +169,33 @@ struct Blocked {
       trtri_batched(W, ld, n1, b0, bt, stride, dstride, full_diag);
       trtri_batched(W22, ld, n2, b0 + n1 / LEAF, bt, stride, dstride, full_diag);
     }
+  }
+
+  // Z(lower) <- U^-T = (U^-1)^T, out of place: U is only read (upper blocks + Dinv leaves), Z's lower triangle incl. full
+  // diagonal 128-blocks is written, its upper part is never touched.  Bottom-up over the halving tree,
+  //     Z = [ Z11 0 ; Z21 Z22 ],   Z21 = -U22^-T (U12^T Z11),
+  // so every product has BOTH operands contraction-contiguous (T,N form, the fastest one of the DMMA kernel; the
+  // top-down trtri above runs in the N,N form), the triangular factor Z11 costs half a GEMM (BLK_K_FROM_N), and the
+  // result is already the transposed factor lauum_oop_t wants: no copy of U, no transpose pass.
+  // Level-synchronous like trtri_batched: all nodes of one depth form one strided batch.
+  void trtri_t(const double* U, int64_t ldu, double* Z, int64_t ldz, int64_t n, int64_t b0) {
+    trtri_t_batched(U, ldu, Z, ldz, n, b0, 1, 0, 0, 0);
+  }
+  void trtri_t_batched(const double* U, int64_t ldu, double* Z, int64_t ldz, int64_t n, int64_t b0, int64_t bt, int64_t sU,
+                       int64_t sZ, int64_t dstride) {
+    if (n == LEAF) { be.copy_dinv_128_t(Z, ldz, dinv_blk(b0), bt, sZ, dstride); return; }
+    const int64_t n1 = split(n), n2 = n - n1;
+    if (n1 == n2 && (bt == 1 || (sU == 2 * n1 * (ldu + 1) && sZ == 2 * n1 * (ldz + 1)))) {
+      trtri_t_batched(U, ldu, Z, ldz, n1, b0, 2 * bt, n1 * (ldu + 1), n1 * (ldz + 1), (n1 / LEAF) * (int64_t)(LEAF * LEAF));
+    } else {
+      trtri_t_batched(U, ldu, Z, ldz, n1, b0, bt, sU, sZ, dstride);
+      trtri_t_batched(U + n1 * (ldu + 1), ldu, Z + n1 * (ldz + 1), ldz, n2, b0 + n1 / LEAF, bt, sU, sZ, dstride);
+    }
+    const double* U12 = U + n1 * ldu;            // n1 x n2
+    const double* U22 = U + n1 * (ldu + 1);
+    double* Z21 = Z + n1;                        // n2 x n1
+    be.gemm('T', 'N', n2, n1, n1, 1.0, U12, ldu, Z, ldz, 0.0, Z21, ldz, BLK_K_FROM_N, bt, sU, sZ, sZ);     // U12^T Z11
+    trsm_LUT(U22, ldu, n2, b0 + n1 / LEAF, Z21, ldz, n1, -1.0, bt, sU, sZ, dstride);                         // -U22^-T (.)
   }
 
   // C(upper) <- W W^T out of place, W upper triangular with clean diagonal blocks (trtri(..., full_diag = true)):

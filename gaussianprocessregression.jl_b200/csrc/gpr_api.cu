@@ -119,6 +119,11 @@ struct CudaBE {
     note(cudaGetLastError());
     ctx->launches++;
   }
+  void copy_dinv_128_t(double* dst, int64_t ldd, const double* src, int64_t batch, int64_t stride, int64_t dstride) {
+    copy_dinv_128_t_kernel<<<(unsigned)batch, 256, 0, ctx->stream>>>(dst, ldd, src, stride, dstride);
+    note(cudaGetLastError());
+    ctx->launches++;
+  }
   void copy_dinv_128(double* dst, int64_t ldd, const double* src, int64_t batch, int64_t stride, int64_t dstride,
                      bool full) {
     copy_dinv_128_kernel<<<(unsigned)batch, 256, 0, ctx->stream>>>(dst, ldd, src, stride, dstride, full ? 1 : 0);
@@ -341,13 +346,11 @@ int form_inverse(gpr_model* m) {
   if (m->d_W) {
     {
       Scope s(m->tm, GPR_T_TRTRI, ctx->stream);
-      CK(cudaMemcpyAsync(m->d_W, m->d_U, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, ctx->stream));
-      blk.trtri(m->d_W, Np, Np, 0, true);
+      blk.trtri_t(m->d_U, Np, m->d_W, Np, Np, 0);      // lower(W) = U^-T, all products in the T,N form
     }
     {
       Scope s(m->tm, GPR_T_LAUUM, ctx->stream);
-      be.transpose_inplace(m->d_W, Np, Np);
-      blk.lauum_oop_t(m->d_W, Np, Np, m->d_Kinv, Np);
+      blk.lauum_oop_t(m->d_W, Np, Np, m->d_Kinv, Np);  // K^-1 = (U^-T)^T U^-T
     }
   } else {
     {
@@ -1327,9 +1330,7 @@ int gpr_dbg_factor(gpr_ctx* ctx, double* A, int64_t N, int mode, int64_t* info, 
     cudaEventRecord(e0, ctx->stream);
     blk.potrf(dA, Np, Np, 0);
     if (mode == 3 && e == cudaSuccess) {   // out-of-place inverse: W = U^-1 with clean diagonal blocks, C = W W^T, upper(C) -> upper(A)
-      e = cudaMemcpyAsync(dW, dA, sizeof(double) * Np * Np, cudaMemcpyDeviceToDevice, ctx->stream);
-      blk.trtri(dW, Np, Np, 0, true);
-      be.transpose_inplace(dW, Np, Np);
+      blk.trtri_t(dA, Np, dW, Np, Np, 0);
       blk.lauum_oop_t(dW, Np, Np, dC, Np);
     } else {
       if (mode >= 1) blk.trtri(dA, Np, Np, 0);

@@ -365,6 +365,25 @@ __global__ void copy_dinv_128_kernel(double* __restrict__ dst, long long ldd, co
   }
 }
 
+// dst (128x128 block, ldd; batch member blockIdx.x at dst + z*stride) <- TRANSPOSE of the Dinv block (src + z*dstride):
+// the whole block, i.e. inv(U_leaf)^T in the lower part and explicit zeros above the diagonal.
+__global__ void copy_dinv_128_t_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src,
+                                       long long stride, long long dstride) {
+  __shared__ double t[32][33];
+  dst += (long long)blockIdx.x * stride;
+  src += (long long)blockIdx.x * dstride;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 256 threads = 32 x 8
+  for (int tile = 0; tile < 16; ++tile) {
+    const int br = tile & 3, bc = tile >> 2;                 // source tile (rows br, cols bc)
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t[ty + 8 * q][tx] = src[(br * 32 + tx) + (bc * 32 + ty + 8 * q) * LEAF_N];   // t[c][r]
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[(bc * 32 + tx) + (long long)(br * 32 + ty + 8 * q) * ldd] = t[tx][ty + 8 * q];   // dst(c, r) = src(r, c)
+  }
+}
+
 // dst(upper) <- src(upper), n x n column major (32 x 8 threads per 32 x 32 tile)
 __global__ void copy_upper_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src, long long lds,
                                   long long n) {

@@ -127,6 +127,11 @@ struct CpuBE {
     for (int64_t j = 0; j < n; ++j)
       for (int64_t i = 0; i < j; ++i) std::swap(A[i + j * ld], A[j + i * ld]);
   }
+  void copy_dinv_128_t(double* dst, int64_t ldd, const double* src, int64_t batch, int64_t stride, int64_t dstride) {
+    for (int64_t z = 0; z < batch; ++z)
+      for (int c = 0; c < gpr::LEAF; ++c)
+        for (int r = 0; r < gpr::LEAF; ++r) dst[z * stride + c + (int64_t)r * ldd] = src[z * dstride + r + c * gpr::LEAF];
+  }
   void copy_dinv_128(double* dst, int64_t ldd, const double* src, int64_t batch, int64_t stride, int64_t dstride,
                      bool full) {
     for (int64_t z = 0; z < batch; ++z)
@@ -233,7 +238,13 @@ long long hl_factor(double* A, int64_t n, int mode, long long* gemm_calls) {
   blk.leaf_lookahead = (mode & 16) != 0;   // the ordering the CUDA product uses (side-queue calls are no-ops here)
   mode &= 15;
   blk.potrf(A, n, n, 0);
-  if (mode == 3 || mode == 4) {   // out-of-place inverse: W = copy of U with clean diagonal blocks, C = W W^T written back to A (upper)
+  if (mode == 5) {   // the product path: lower(Z) = U^-T bottom-up (T,N products), C = Z^T Z; Z's upper part stays poisoned
+    std::vector<double> Z((size_t)n * n, std::nan("")), C((size_t)n * n, 0.0);
+    blk.trtri_t(A, n, Z.data(), n, n, 0);
+    blk.lauum_oop_t(Z.data(), n, n, C.data(), n);
+    for (int64_t j = 0; j < n; ++j)
+      for (int64_t i = 0; i <= j; ++i) A[i + j * n] = C[i + j * n];
+  } else if (mode == 3 || mode == 4) {   // out-of-place inverse: W = copy of U with clean diagonal blocks, C = W W^T written back to A (upper)
     std::vector<double> W((size_t)n * n), C((size_t)n * n, 0.0);
     memcpy(W.data(), A, sizeof(double) * n * n);
     blk.trtri(W.data(), n, n, 0, true);

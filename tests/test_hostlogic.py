@@ -33,7 +33,7 @@ def spd(n, seed):
 
 
 @pytest.mark.parametrize("n", [128, 256, 384, 640, 1024])
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 16, 20])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 16, 20, 21])
 def test_blocked_factor(hl, n, mode):
     K = spd(n, n)
     A = np.asfortranarray(K.copy())
@@ -42,7 +42,7 @@ def test_blocked_factor(hl, n, mode):
     mode &= 15                                   # bit 4: leaf look-ahead ordering of the update
     assert info == 0
     U = sl.cholesky(K, lower=False)
-    ref = [U, np.linalg.inv(U), np.linalg.inv(K), np.linalg.inv(K), np.linalg.inv(K)][mode]   # modes 3, 4: out-of-place W W^T
+    ref = [U, np.linalg.inv(U), np.linalg.inv(K), np.linalg.inv(K), np.linalg.inv(K), np.linalg.inv(K)][mode]   # modes 3-5: out-of-place inverse
     np.testing.assert_allclose(np.triu(A), np.triu(ref), rtol=0, atol=1e-12 * np.abs(ref).max())
     # dpotrf('U') semantics: the strict lower triangle keeps K (test/test_loss.jl:46)
     assert np.array_equal(np.tril(A, -1), np.tril(K, -1))
