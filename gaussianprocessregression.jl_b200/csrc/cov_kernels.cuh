@@ -50,6 +50,9 @@ struct KBuildArgs {
   // (mean-only prediction: K* is not stored at all).
   const double* mean_w;
   double* mean_partial;
+  // The same for the TRANSPOSED layout out = K(x, xp) (rows = training points): mean_w_rows != nullptr makes every CTA
+  // write mean_partial[blockIdx.x * Cp + c] = sum over its 64 rows of out(r, c) * mean_w_rows[r].
+  const double* mean_w_rows;
   double all_shift;      // added to EVERY valid entry (prior sampling: `Sigma .+ 1e-7`, src/distributions.jl:25)
   int lower_only;        // write only the entries strictly below the diagonal (fills in what a zero_lower build left out)
 };
@@ -151,7 +154,12 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_kernel(const KBuildArgs a) 
     for (int c = 0; c < a.spec.ncomp; ++c)
       if (a.spec.type[c] == KT_NOISE) { const double s = a.hp[a.spec.hp_off[c]]; noise2 = s * s; break; }   // findfirst: compose_covar.jl:65
   }
-  double msum[4] = {0.0, 0.0, 0.0, 0.0};
+  double msum[4] = {0.0, 0.0, 0.0, 0.0};   // per row (mean_w) or per column (mean_w_rows) of this thread's 4 x 4 patch
+  double wr[4] = {0.0, 0.0, 0.0, 0.0};
+  if (a.mean_w_rows) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const long long r = r0 + tx + 16 * i; wr[i] = (r < a.R) ? a.mean_w_rows[r] : 0.0; }
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const long long c = c0 + ty + 16 * j;
@@ -172,8 +180,24 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_kernel(const KBuildArgs a) 
       }
       if (a.zero_lower && r > c + a.diag_shift) v = 0.0;
       if (a.out) a.out[r + c * a.ldo] = v;
-      msum[i] += v * wc;
+      if (a.mean_w_rows) msum[j] += v * wr[i]; else msum[i] += v * wc;
     }
+  }
+  if (a.mean_w_rows) {
+    // 16 threads (tx = 0..15) hold partial sums of the same column: reduce through shared memory in a fixed order
+    __syncthreads();
+    double* red = kb_smem;                 // [16][64]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[tx * KB_TILE + ty + 16 * j] = msum[j];
+    __syncthreads();
+    if (tid < KB_TILE) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) sacc += red[q * KB_TILE + tid];
+      const long long c = c0 + tid;
+      if (c < a.Cp) a.mean_partial[(long long)blockIdx.x * a.Cp + c] = sacc;
+    }
+    return;
   }
   if (a.mean_w) {
     // 16 threads (ty = 0..15) hold partial sums of the same row: reduce through shared memory in a fixed order
@@ -420,49 +444,8 @@ __global__ void grad_finalize_kernel(const double* __restrict__ partial, int nbl
 }
 
 // ---------------------------------------------------------------------------
-// Streaming row reductions over a column-major (rows x cols) matrix K with the
-// row index fastest (K* = K(xp, x) has the test index fastest: predict.jl:3,37).
-//   MODE 0: partial[split][r] = sum_{c in split} K[r,c] * w[c]      (mean, predict.jl:73-76)
-//   MODE 1: partial[split][r] = sum_{c in split} K[r,c]^2           (row norms of V, predict.jl:91-93)
-// One thread owns two adjacent rows (16-byte loads), a CTA of 64 threads owns
-// 128 rows, blockIdx.y selects the column split.  HBM-bound: 8*rows*cols bytes.
+// Streaming reductions of the prediction path.
 // ---------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(64) rowreduce_kernel(const double* __restrict__ K, long long ld, long long rows,
-                                                       long long cols, long long cols_per_split,
-                                                       const double* __restrict__ w, double* __restrict__ partial) {
-  extern __shared__ __align__(16) double rr_w[];   // MODE 0: the split's slice of w (cols_per_split doubles)
-  const long long cbeg = (long long)blockIdx.y * cols_per_split;
-  long long cend = cbeg + cols_per_split; if (cend > cols) cend = cols;
-  if (MODE == 0) {
-    for (long long c = cbeg + threadIdx.x; c < cend; c += 64) rr_w[c - cbeg] = w[c];
-    __syncthreads();
-  }
-  const long long r = ((long long)blockIdx.x * 64 + threadIdx.x) * 2;
-  if (r >= rows) return;
-  double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0};
-  const double* p = K + r;
-  long long c = cbeg;
-  for (; c + 8 <= cend; c += 8) {
-    double2 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const double2*>(p + (c + u) * ld));
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (MODE == 0) { const double ww = rr_w[c - cbeg + u]; ax[u & 3] += v[u].x * ww; ay[u & 3] += v[u].y * ww; }
-      else { ax[u & 3] += v[u].x * v[u].x; ay[u & 3] += v[u].y * v[u].y; }
-    }
-  }
-  for (; c < cend; ++c) {
-    const double2 v = __ldcs(reinterpret_cast<const double2*>(p + c * ld));
-    if (MODE == 0) { const double ww = rr_w[c - cbeg]; ax[0] += v.x * ww; ay[0] += v.y * ww; }
-    else { ax[0] += v.x * v.x; ay[0] += v.y * v.y; }
-  }
-  double* o = partial + (size_t)blockIdx.y * rows + r;
-  o[0] = (ax[0] + ax[1]) + (ax[2] + ax[3]);
-  o[1] = (ay[0] + ay[1]) + (ay[2] + ay[3]);
-}
-
 // out[r*ostride] = base - sign * sum_split partial[split][r]  (r < rows_valid)
 __global__ void rowreduce_finalize_kernel(const double* __restrict__ partial, int nsplit, long long rows_pad,
                                           long long rows_valid, double base, double sign, double* __restrict__ out) {
@@ -471,6 +454,31 @@ __global__ void rowreduce_finalize_kernel(const double* __restrict__ partial, in
   double s = 0.0;
   for (int q = 0; q < nsplit; ++q) s += partial[(size_t)q * rows_pad + r];
   out[r] = base + sign * s;
+}
+
+// out[c] = base - sum_r V[r + c*ld]^2 for the columns of an (rows x cols) column-major matrix (V^T = U^-T K*^T: the
+// posterior variance of test point c, predict.jl:91-93).  One CTA per column, 16-byte streaming loads, fixed order.
+__global__ void __launch_bounds__(256) colsumsq_kernel(const double* __restrict__ V, long long ld, long long rows,
+                                                       long long cols_valid, double base, double* __restrict__ out) {
+  __shared__ double red[256];
+  const long long c = blockIdx.x;
+  if (c >= cols_valid) return;
+  const double2* p = reinterpret_cast<const double2*>(V + c * ld);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const long long n2 = rows >> 1;
+  long long i = threadIdx.x;
+  for (; i + 768 < n2; i += 1024) {
+    const double2 a = __ldcs(p + i), b = __ldcs(p + i + 256), cc = __ldcs(p + i + 512), d = __ldcs(p + i + 768);
+    s0 += a.x * a.x + a.y * a.y; s1 += b.x * b.x + b.y * b.y; s2 += cc.x * cc.x + cc.y * cc.y; s3 += d.x * d.x + d.y * d.y;
+  }
+  for (; i < n2; i += 256) { const double2 a = __ldcs(p + i); s0 += a.x * a.x + a.y * a.y; }
+  red[threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[c] = base - red[0];
 }
 
 // mu[r + c*ldm] += A[r + c*lda] * T[r + c*ldt]   (split mean: BCw .*= A ; mu .+= BCw, split_predict.jl:15-16)
@@ -504,6 +512,29 @@ __global__ void split_assemble_kernel(double* __restrict__ out, long long ldo, c
              Ct[q + s * nqp + (long long)k * nqp * Np];
     }
     out[r + s * ldo] = v;
+  }
+}
+
+// The same block TRANSPOSED (training index fastest), which is what the T,N triangular solve wants:
+//   out[s + ((e - e0)*nqp + q)*ldo] = sum_k A[e,q,k] * Bt[s,e,k] * Cu[s,q,k]
+// Bt: Np x nep x k (B transposed), Cu: Np x nqp x k (C, not scaled by wt).  All three reads and the write are coalesced in s.
+__global__ void split_assemble_t_kernel(double* __restrict__ out, long long ldo, const double* __restrict__ A,
+                                        const double* __restrict__ Bt, const double* __restrict__ Cu, long long nep,
+                                        long long nqp, long long Np, int nk, long long e0, long long ecount,
+                                        long long ne_valid, long long nq_valid, long long N_valid) {
+  const long long rows = ecount * nqp;
+  const long long total = rows * Np;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long s = idx % Np, r = idx / Np;
+    const long long q = r % nqp, e = e0 + r / nqp;
+    double v = 0.0;
+    if (e < ne_valid && q < nq_valid && s < N_valid) {
+      for (int k = 0; k < nk; ++k)
+        v += A[e + q * nep + (long long)k * nep * nqp] * Bt[s + e * Np + (long long)k * Np * nep] *
+             Cu[s + q * Np + (long long)k * Np * nqp];
+    }
+    out[s + r * ldo] = v;
   }
 }
 

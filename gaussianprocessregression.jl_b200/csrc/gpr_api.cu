@@ -168,7 +168,7 @@ int launch_kbuild(gpr_ctx* ctx, int mode, const KBuildArgs& a) {
   int nk = 0;
   for (int c = 0; c < a.spec.ncomp; ++c) if (a.spec.type[c] != KT_NOISE) nk++;
   size_t smem = (size_t)2 * nk * a.D * KB_TILE * sizeof(double);
-  if (a.mean_w) smem = std::max(smem, (size_t)16 * KB_TILE * sizeof(double));
+  if (a.mean_w || a.mean_w_rows) smem = std::max(smem, (size_t)16 * KB_TILE * sizeof(double));
   if (smem > 200 * 1024) return fail(ctx, GPR_ERR_UNSUPPORTED, "covariance build: (#components x D) too large for shared memory");
   dim3 grid((unsigned)((a.Rp + KB_TILE - 1) / KB_TILE), (unsigned)((a.Cp + KB_TILE - 1) / KB_TILE));
   if (grid.y > 65535) return fail(ctx, GPR_ERR_UNSUPPORTED, "covariance build: too many column tiles");
@@ -792,33 +792,14 @@ double prior_diag(const gpr_model* m) {
   return s;
 }
 
-// Launch the streaming row reduction of K (rows_pad x cols, ld) into out[0..rows_valid)
-int row_reduce(gpr_model* m, int mode, const double* K, int64_t ld, int64_t rows_pad, int64_t rows_valid, int64_t cols,
-               const double* w, double base, double sign, double* out) {
-  gpr_ctx* ctx = m->ctx;
-  const int64_t row_ctas = rows_pad / 128;
-  int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 16 / std::max<int64_t>(row_ctas, 1), cols / 64));
-  if (nsplit < 1) nsplit = 1;
-  if (mode == 0 && (cols + nsplit - 1) / nsplit > 4096) nsplit = (int)((cols + 4095) / 4096);   // w slice in shared memory (<= 32 KB)
-  const int64_t cps = (cols + nsplit - 1) / nsplit;
-  nsplit = (int)((cols + cps - 1) / cps);
-  int rc = ensure(ctx, m->w_part, (size_t)nsplit * rows_pad);
-  if (rc) return rc;
-  dim3 grid((unsigned)row_ctas, (unsigned)nsplit);
-  if (mode == 0) rowreduce_kernel<0><<<grid, 64, (size_t)cps * sizeof(double), ctx->stream>>>(K, ld, rows_pad, cols, cps, w, m->w_part.p);
-  else rowreduce_kernel<1><<<grid, 64, 0, ctx->stream>>>(K, ld, rows_pad, cols, cps, w, m->w_part.p);
-  ctx->launches++;
-  CK(cudaGetLastError());
-  rowreduce_finalize_kernel<<<(unsigned)((rows_valid + 255) / 256), 256, 0, ctx->stream>>>(m->w_part.p, nsplit, rows_pad, rows_valid, base, sign, out);
-  ctx->launches++;
-  CK(cudaGetLastError());
-  return GPR_OK;
-}
-
 // One tile of test points resident on the device: d_xp is D x mt (mt valid points, global index m0..m0+mt).
 // Writes mean (mt x ny, column stride ldmean) and var (mt) to device memory.
 int predict_tile(gpr_model* m, const double* d_xp, int64_t mt, int64_t m0, int same_x, double* d_mean, int64_t ldmean,
                  double* d_var) {
+  // The tile is held TRANSPOSED: Kt = K(x, xp) is Np x mtp with the training index fastest (the reference keeps
+  // Kxp = K(xp, x), src/predict.jl:37).  V^T = U^-T Kt is then a LEFT solve with U^T whose products are all of the T,N
+  // form -- the same instantiation of the DMMA kernel as potrf / trtri / lauum (DMMA pipe 92.9 % active against 90.1 %
+  // for the N,N products of the right solve Kxp U^-1) -- and the row norms of V become contiguous column sums.
   gpr_ctx* ctx = m->ctx;
   const int64_t Np = m->Np, N = m->N;
   const int64_t mtp = round_up(mt, 128);
@@ -827,50 +808,53 @@ int predict_tile(gpr_model* m, const double* d_xp, int64_t mt, int64_t m0, int s
     rc = ensure(ctx, m->w_kxp, (size_t)mtp * Np);
     if (rc) return rc;
   }
-  double* Kxp = m->w_kxp.p;
+  double* Kt = m->w_kxp.p;
+  CudaBE be{ctx};
   {
     Scope s(m->tm, GPR_T_PRED_KSTAR, ctx->stream);
     KBuildArgs a{};
-    a.out = Kxp; a.ldo = mtp; a.R = mt; a.C = N; a.Rp = mtp; a.Cp = Np;
-    a.x1 = d_xp; a.x2 = m->d_x; a.D = m->D; a.hp = m->d_hp; a.spec = m->spec;
+    a.out = Kt; a.ldo = Np; a.R = N; a.C = mt; a.Rp = Np; a.Cp = mtp;
+    a.x1 = m->d_x; a.x2 = d_xp; a.D = m->D; a.hp = m->d_hp; a.spec = m->spec;
     a.eps = m->eps_host; a.same = same_x; a.add_noise = 0; a.pad_identity = 0; a.sigma_one = 0; a.row_scale = nullptr;
-    a.diag_shift = -m0;
-    // vector y: mu = K* wt is reduced inside the build (per-CTA partial sums over 64 columns), so the K* tile is not
-    // re-read; without a variance request K* is not even stored
+    a.diag_shift = m0;          // training point r is test point c of this tile when r == m0 + c (xp === md.x)
+    // vector y: mu = K* wt is reduced inside the build (per-CTA partial sums over 64 training points), so the tile is
+    // not re-read; without a variance request it is not even stored
     const bool fuse_mean = (m->ny == 1);
-    int64_t ncol_tiles = (Np + KB_TILE - 1) / KB_TILE;
+    const int64_t nrow_tiles = (Np + KB_TILE - 1) / KB_TILE;
     if (fuse_mean) {
-      rc = ensure(ctx, m->w_part, (size_t)ncol_tiles * mtp);
+      rc = ensure(ctx, m->w_part, (size_t)nrow_tiles * mtp);
       if (rc) return rc;
-      a.mean_w = m->d_wt; a.mean_partial = m->w_part.p;
+      a.mean_w_rows = m->d_wt; a.mean_partial = m->w_part.p;
       if (!d_var) a.out = nullptr;
     }
     rc = launch_kbuild(ctx, DM_EUCLID, a);
     if (rc) return rc;
     if (fuse_mean) {
-      rowreduce_finalize_kernel<<<(unsigned)((mt + 255) / 256), 256, 0, ctx->stream>>>(m->w_part.p, (int)ncol_tiles, mtp, mt, 0.0, 1.0, d_mean);
+      rowreduce_finalize_kernel<<<(unsigned)((mt + 255) / 256), 256, 0, ctx->stream>>>(m->w_part.p, (int)nrow_tiles, mtp, mt, 0.0, 1.0, d_mean);
       ctx->launches++;
       CK(cudaGetLastError());
     }
   }
   if (m->ny > 1) {
+    // matrix y: mu = Kt^T wt for all columns at once, one T,N GEMM on the zero-padded weights (mtp x nyp)
     Scope s(m->tm, GPR_T_PRED_MEAN, ctx->stream);
-    for (int e = 0; e < m->ny; ++e) {
-      rc = row_reduce(m, 0, Kxp, mtp, mtp, mt, N, m->d_wt + (int64_t)e * Np, 0.0, 1.0, d_mean + (int64_t)e * ldmean);
-      if (rc) return rc;
-    }
+    rc = ensure(ctx, m->w_part, (size_t)mtp * m->nyp);
+    if (rc) return rc;
+    be.gemm('T', 'N', mtp, m->nyp, Np, 1.0, Kt, Np, m->d_wt, Np, 0.0, m->w_part.p, mtp, 0);
+    CK(cudaMemcpy2DAsync(d_mean, sizeof(double) * ldmean, m->w_part.p, sizeof(double) * mtp, sizeof(double) * mt, m->ny,
+                         cudaMemcpyDeviceToDevice, ctx->stream));
   }
   if (d_var) {
-    CudaBE be{ctx};
     Blocked<CudaBE> blk(be, m->d_dinv);
     {
       Scope s(m->tm, GPR_T_PRED_TRSM, ctx->stream);
-      blk.trsm_RUN(m->d_U, Np, Np, 0, Kxp, mtp, mtp, 1.0);   // Kxp <- Kxp U^-1  (rdiv!, src/predict.jl:90)
+      blk.trsm_LUT(m->d_U, Np, Np, 0, Kt, Np, mtp, 1.0);   // Kt <- U^-T Kt = (Kxp U^-1)^T  (rdiv!, src/predict.jl:90)
     }
     {
       Scope s(m->tm, GPR_T_PRED_ROWNORM, ctx->stream);
-      rc = row_reduce(m, 1, Kxp, mtp, mtp, mt, Np, nullptr, prior_diag(m), -1.0, d_var);
-      if (rc) return rc;
+      colsumsq_kernel<<<(unsigned)mt, 256, 0, ctx->stream>>>(Kt, Np, Np, mt, prior_diag(m), d_var);   // predict.jl:91-93
+      ctx->launches++;
+      CK(cudaGetLastError());
     }
   }
   return check_pending(ctx, "predict_tile");
@@ -919,7 +903,7 @@ int gpr_predict(gpr_model* m, const double* xp, int64_t M, int same_x, double* m
     CK(cudaMalloc(&d_sigma, sizeof(double) * Mp * Mp));
     cudaError_t e = cudaMemcpyAsync(m->w_xp.p, xp, sizeof(double) * D * M, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) { cudaFree(d_sigma); return fail_cuda(ctx, e, "upload xp", __LINE__); }
-    rc = predict_tile(m, m->w_xp.p, M, 0, same_x, m->w_mean.p, Mp, m->w_var.p);   // leaves V in w_kxp (Mp x Np)
+    rc = predict_tile(m, m->w_xp.p, M, 0, same_x, m->w_mean.p, Mp, m->w_var.p);   // leaves V^T in w_kxp (Np x Mp)
     if (!rc) {
       KBuildArgs a{};
       a.out = d_sigma; a.ldo = Mp; a.R = M; a.C = M; a.Rp = Mp; a.Cp = Mp;
@@ -929,7 +913,7 @@ int gpr_predict(gpr_model* m, const double* xp, int64_t M, int same_x, double* m
     }
     if (!rc) {
       CudaBE be{ctx};
-      be.gemm('N', 'T', Mp, Mp, Np, -1.0, m->w_kxp.p, Mp, m->w_kxp.p, Mp, 1.0, d_sigma, Mp, 0);   // Sigma -= V V^T
+      be.gemm('T', 'N', Mp, Mp, Np, -1.0, m->w_kxp.p, Np, m->w_kxp.p, Np, 1.0, d_sigma, Mp, 0);   // Sigma -= V V^T = (V^T)^T V^T
       rc = check_pending(ctx, "predict cov");
     }
     if (!rc) {
@@ -969,14 +953,19 @@ int gpr_predict(gpr_model* m, const double* xp, int64_t M, int same_x, double* m
 namespace {
 
 struct SplitBufs {
-  double *A = nullptr, *B = nullptr, *C = nullptr, *Ct = nullptr;   // per non-noise component slices
+  double *A = nullptr, *B = nullptr, *C = nullptr;   // per non-noise component slices
+  double *Bt = nullptr, *Cu = nullptr;               // variance path: B transposed (Np x nep x k), C unscaled (Np x nqp x k)
   double *d_xe = nullptr, *d_xq = nullptr;
   int64_t nep = 0, nqp = 0;
-  void release() { cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(Ct); cudaFree(d_xe); cudaFree(d_xq); A = B = C = Ct = d_xe = d_xq = nullptr; }
+  void release() {
+    cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(Bt); cudaFree(Cu); cudaFree(d_xe); cudaFree(d_xq);
+    A = B = C = Bt = Cu = d_xe = d_xq = nullptr;
+  }
 };
 
 // Builds A (nep x nqp x k), B (nep x Np x k) and, per request, C (Np x nqp x k; optionally row-scaled by wt)
-// and Ct (nqp x Np x k).  d_hp: device global hp.  x: D x N device.
+// and, for the variance, Bt (Np x nep x k) and the unscaled Cu (Np x nqp x k): the training index fastest, the layout the
+// transposed tile assembly reads coalesced.  d_hp: device global hp.  x: D x N device.
 int split_build(gpr_ctx* ctx, const KSpec& spec, int D, const double* d_hp, const double* d_xe, int64_t ne,
                 const double* d_xq, int64_t nq, const double* d_x, int64_t N, int64_t Np, double eps, SplitBufs& sb,
                 bool want_C, const double* c_row_scale, bool want_Ct) {
@@ -1004,9 +993,12 @@ int split_build(gpr_ctx* ctx, const KSpec& spec, int D, const double* d_hp, cons
       rc = launch_kbuild(ctx, DM_SPLIT_C, a); if (rc) return rc;
     }
     if (want_Ct) {
-      a.out = sb.Ct + (int64_t)k * nqp * Np; a.ldo = nqp; a.R = nq; a.C = N; a.Rp = nqp; a.Cp = Np;
-      a.x1 = d_xq; a.x2 = d_x; a.sigma_one = 0; a.row_scale = nullptr;
+      a.out = sb.Cu + (int64_t)k * Np * nqp; a.ldo = Np; a.R = N; a.C = nq; a.Rp = Np; a.Cp = nqp;
+      a.x1 = d_x; a.x2 = d_xq; a.sigma_one = 0; a.row_scale = nullptr;
       rc = launch_kbuild(ctx, DM_SPLIT_C, a); if (rc) return rc;
+      a.out = sb.Bt + (int64_t)k * Np * nep; a.ldo = Np; a.R = N; a.C = ne; a.Rp = Np; a.Cp = nep;
+      a.x1 = d_x; a.x2 = d_xe; a.sigma_one = 1; a.row_scale = nullptr;
+      rc = launch_kbuild(ctx, DM_EUCLID, a); if (rc) return rc;   // B is symmetric in its two point sets: Bt[s, e] = B[e, s]
     }
     ++k;
   }
@@ -1073,7 +1065,8 @@ int gpr_split_predict(gpr_model* m, const double* xe, int64_t ne, const double* 
   cudaError_t e = cudaMalloc(&sb.A, sizeof(double) * nep * nqp * nk);
   if (e == cudaSuccess) e = cudaMalloc(&sb.B, sizeof(double) * nep * Np * nk);
   if (e == cudaSuccess) e = cudaMalloc(&sb.C, sizeof(double) * Np * nqp * nk);
-  if (e == cudaSuccess && var) e = cudaMalloc(&sb.Ct, sizeof(double) * nqp * Np * nk);
+  if (e == cudaSuccess && var) e = cudaMalloc(&sb.Cu, sizeof(double) * nqp * Np * nk);
+  if (e == cudaSuccess && var) e = cudaMalloc(&sb.Bt, sizeof(double) * nep * Np * nk);
   if (e == cudaSuccess) e = cudaMalloc(&sb.d_xe, sizeof(double) * D * ne);
   if (e == cudaSuccess) e = cudaMalloc(&sb.d_xq, sizeof(double) * D * nq);
   if (e == cudaSuccess) e = cudaMalloc(&d_bcw, sizeof(double) * nep * nqp);
@@ -1112,17 +1105,19 @@ int gpr_split_predict(gpr_model* m, const double* xe, int64_t ne, const double* 
       const int64_t rows = ec * nqp;
       {
         Scope s(m->tm, GPR_T_PRED_KSTAR, ctx->stream);
-        split_assemble_kernel<<<(unsigned)std::min<int64_t>((rows * Np + 255) / 256, (int64_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(
-            m->w_kxp.p, rows, sb.A, sb.B, sb.Ct, nep, nqp, Np, nk, e0, ec, ne, nq, N);
+        // Kxq^T for the rows e0 .. e0+ec-1, training index fastest (split_predict.jl:44-47, transposed)
+        split_assemble_t_kernel<<<(unsigned)std::min<int64_t>((rows * Np + 255) / 256, (int64_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(
+            m->w_kxp.p, Np, sb.A, sb.Bt, sb.Cu, nep, nqp, Np, nk, e0, ec, ne, nq, N);
         ctx->launches++;
       }
       {
         Scope s(m->tm, GPR_T_PRED_TRSM, ctx->stream);
-        blk.trsm_RUN(m->d_U, Np, Np, 0, m->w_kxp.p, rows, rows, 1.0);
+        blk.trsm_LUT(m->d_U, Np, Np, 0, m->w_kxp.p, Np, rows, 1.0);     // V^T = U^-T Kxq^T, T,N products
       }
       {
         Scope s(m->tm, GPR_T_PRED_ROWNORM, ctx->stream);
-        rc = row_reduce(m, 1, m->w_kxp.p, rows, rows, rows, Np, nullptr, prior, -1.0, d_var);
+        colsumsq_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(m->w_kxp.p, Np, Np, rows, prior, d_var);
+        ctx->launches++;
       }
       if (rc) break;
       rc = check_pending(ctx, "split variance");
