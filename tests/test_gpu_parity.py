@@ -575,8 +575,17 @@ def test_integrate_matches_oracle(gpr, dim, n, ny):
     mu_o, var_o = o.integrate(o.GPRModel((o.SE, o.NOISE), hp, x, y), hp, a, b)
     np.testing.assert_allclose(mu, mu_o, rtol=1e-8, atol=1e-8 * np.abs(mu_o).max())
     assert abs(var[0] - var_o[0]) <= 1e-8 * o.antideriv2(hp, a, b)
-    with pytest.raises(gpr.GPRError):
-        gpr.integrate(md, a, b, sample_noise=np.zeros(max(ny, 1)))
+    # per-sample-noise branch (src/integrate.jl:72-100,145-160): the oracle follows the reference's eigendecomposition,
+    # the device takes one shifted Cholesky per noise level -- same quantities
+    noise = 1e-3 * (1.0 + rng.random(max(ny, 1)))
+    mu_n, var_n = gpr.integrate(md, hp, a, b, sample_noise=noise)
+    mu_no, var_no = o.integrate(o.GPRModel((o.SE, o.NOISE), hp, x, y), hp, a, b, noise)
+    np.testing.assert_allclose(mu_n, mu_no, rtol=1e-7, atol=1e-8 * np.abs(mu_no).max())
+    np.testing.assert_allclose(var_n, var_no, rtol=0, atol=1e-7 * o.antideriv2(hp, a, b))
+    mu_s, var_s = gpr.integrate(md, hp, a, b, sample_noise=2e-3)
+    mu_so, var_so = o.integrate(o.GPRModel((o.SE, o.NOISE), hp, x, y), hp, a, b, 2e-3)
+    np.testing.assert_allclose(mu_s, mu_so, rtol=1e-7, atol=1e-8 * np.abs(mu_so).max())
+    np.testing.assert_allclose(var_s, np.broadcast_to(var_so, var_s.shape), rtol=0, atol=1e-7 * o.antideriv2(hp, a, b))
 
 
 def test_integrate_agrees_with_quadrature_of_the_posterior_mean(gpr):
