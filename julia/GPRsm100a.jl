@@ -214,4 +214,37 @@ function sample_sm100(cov, θ::Vector{Float64}, x::Matrix{Float64}, μ::Vector{F
     out
 end
 
+# ---------------------------------------------------------------------------------------------------------
+# integrate(md, hp, a, b; sample_noise) on the device (src/integrate.jl:45-62,103-160).  sample_noise === nothing: one
+# factorization.  Scalar / vector noise: the same mu_i, var_i from one shifted factorization per distinct noise level
+# (the shift rides in the jitter argument of gpr_update_cache, divided by the number of non-noise components because
+# every such component adds its own jitter, src/compose_covar.jl:53-55) instead of the eigendecomposition of :72-80.
+# ---------------------------------------------------------------------------------------------------------
+function _integrate_once(h::Handle, hp::Vector{Float64}, a::Vector{Float64}, b::Vector{Float64}, eps::Float64, ny::Int)
+    info = Ref{Int64}(0)
+    check(h.c, ccall((:gpr_update_cache, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cdouble, Cint, Ref{Int64}),
+        h.h, hp, length(hp), eps, 0, info), info[])
+    Iout = Vector{Float64}(undef, ny); v = Vector{Float64}(undef, 1)
+    check(h.c, ccall((:gpr_integrate, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        h.h, a, b, Iout, v))
+    Iout, v[1]
+end
+function integrate_sm100(md::GPRModel, hp, a, b; sample_noise = nothing)
+    h = Handle(md)                       # device model (x, y uploaded once), freed by its finalizer
+    ny = size(md.y, 2)
+    nk = count(k -> !(k isa WhiteNoise), md.covar isa ComposedKernel ? md.covar.kernels : (md.covar,))
+    hpv, av, bv = Vector{Float64}(hp), Vector{Float64}(a), Vector{Float64}(b)
+    sample_noise === nothing && (r = _integrate_once(h, hpv, av, bv, 1e-8, ny); return r[1], [r[2]])
+    if sample_noise isa Real
+        I, v = _integrate_once(h, hpv, av, bv, 1e-8 + sample_noise / nk, ny)
+        return I, fill(v, ny)
+    end
+    Iout = Vector{Float64}(undef, ny); var = similar(Iout)
+    for (i, e) in enumerate(sample_noise)
+        I, v = _integrate_once(h, hpv, av, bv, 1e-8 + e / nk, ny)
+        Iout[i] = I[i]; var[i] = v
+    end
+    Iout, var
+end
+
 end # module
