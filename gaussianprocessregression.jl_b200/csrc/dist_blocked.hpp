@@ -46,6 +46,8 @@
 //   selects one of the two panel / Ukk buffers):
 //     comm.bcast_diag(k, with_owner, b)   Ukk[b] (nb x nb, ld nb) and dinv blocks k*tpb.. <- owner's diagonal block k
 //     comm.gather_rowpanel(k, b)          panel[b][p + ((J-k-1)*nb + c)*nb] <- U(k*nb + p, J*nb + c), J = k+1 .. nblk-1
+//     comm.gather_rowpanel_t(k, b)        the same panel TRANSPOSED: panel[b][((J-k-1)*nb + c) + p*Krem], Krem = Np - (k+1)*nb
+//                                         (trtri contracts over the panel's columns: transposed, the product is T,N)
 //     comm.bcast_colpanel(k, b)           panel[b][c + i*nb] <- L_owner(i, block k col c), i < (k+1)*nb  (TRANSPOSED: both
 //                                         operands of the lauum update are then contraction-contiguous, the fastest GEMM form)
 //     comm.barrier()                      every rank's main-queue work so far is ordered before every rank's later
@@ -214,7 +216,7 @@ struct DistBlocked {
       if (prefetch_trtri) all_side(true);
       if (k > 0) {      // copies for step k-1: U is final there, so they only wait for the buffers
         comm.bcast_diag(k - 1, true, b ^ 1);
-        comm.gather_rowpanel(k - 1, b ^ 1);
+        comm.gather_rowpanel_t(k - 1, b ^ 1);
       }
       for (auto& R : ranks)
         if (R.r == o) {
@@ -231,10 +233,10 @@ struct DistBlocked {
         const double* below = R.L + (k + 1) * nb + c0 * R.ld;
         if (Krem > 0 && mreg > 0) {
           TileMap map{R.gtile + c0 / LEAF, 0, (int)((k + 1) * tpb)};
-          R.be->gemm_map('N', 'N', nb, mreg, Krem, 1.0, R.panel[b], nb, below, R.ld, 0.0, rowp, R.ld, BLK_MAP_KUPTO, map);
+          R.be->gemm_map('T', 'N', nb, mreg, Krem, 1.0, R.panel[b], Krem, below, R.ld, 0.0, rowp, R.ld, BLK_MAP_KUPTO, map);
         }
         if (Krem > 0 && m > mreg)
-          R.be->gemm('N', 'N', nb, m - mreg, Krem, 1.0, R.panel[b], nb, below + mreg * R.ld, R.ld, 1.0, rowp + mreg * R.ld, R.ld, 0, 1, 0, 0, 0);
+          R.be->gemm('T', 'N', nb, m - mreg, Krem, 1.0, R.panel[b], Krem, below + mreg * R.ld, R.ld, 1.0, rowp + mreg * R.ld, R.ld, 0, 1, 0, 0, 0);
         if (m > 0) {
           Blocked<BE> blk(*R.be, R.dinv);
           blk.trsm_LUN(R.Ukk[b], nb, nb, k * tpb, rowp, R.ld, m, -1.0);

@@ -70,6 +70,28 @@ __global__ void __launch_bounds__(256) unpermute_rowpanel_kernel(double* __restr
   const long long n2 = nb * nb / 2;
   for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.y * blockDim.x) D[i] = S[i];
 }
+// The same with every nb x nb block TRANSPOSED into a (Krem x nb, ld = ldt) panel: dst[(J-k-1)*nb + c + p*ldt] = block(p, c).
+// Block blockIdx.x; 32 x 32 tiles over blockIdx.y (32 x 8 threads).
+__global__ void __launch_bounds__(256) unpermute_rowpanel_t_kernel(double* __restrict__ dst, long long ldt, const double* __restrict__ stage,
+                                                                   const GatherMap gm, int G, long long k, long long nb) {
+  __shared__ double t[32][33];
+  const long long J = k + 1 + blockIdx.x;
+  const int pos = (int)(J % G);
+  const int s = ((J / G) & 1) ? G - 1 - pos : pos;
+  const double* S = stage + ((long long)gm.off[s] + J / G - gm.first[s]) * nb * nb;   // (p, c) at S[p + c*nb]
+  double* D = dst + (long long)blockIdx.x * nb;                                          // (c, p) at D[c + p*ldt]
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long nt = nb / 32;
+  for (long long tile = blockIdx.y; tile < nt * nt; tile += gridDim.y) {
+    const long long bp = tile % nt, bc = tile / nt;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t[ty + 8 * q][tx] = S[(bp * 32 + tx) + (bc * 32 + ty + 8 * q) * nb];     // t[c][p]
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) D[(bc * 32 + tx) + (bp * 32 + ty + 8 * q) * ldt] = t[tx][ty + 8 * q];   // dst(c = tx, p = ty + 8q)
+  }
+}
 
 // out[0] = sum over the local matrix columns of log(L[gcol(c), c]) (the rank's share of log det U); one CTA.
 __global__ void __launch_bounds__(1024, 1) dist_logdiag_kernel(const double* __restrict__ L, long long ld, long long ncols,
@@ -178,6 +200,7 @@ struct CommBase {
   virtual void barrier() = 0;
   virtual void bcast_diag(int64_t k, bool with_owner, int b) = 0;
   virtual void gather_rowpanel(int64_t k, int b) = 0;
+  virtual void gather_rowpanel_t(int64_t k, int b) = 0;
   virtual void bcast_colpanel(int64_t k, int b) = 0;
   virtual void bcast_alpha(int root, int64_t count) = 0;                     // MRank::alpha
   virtual int sum_scal(int64_t off, int64_t count, double* host_out) = 0;    // sum over ranks of MRank::scal[off ..], rank order
@@ -294,10 +317,12 @@ struct LocalComm : CommBase {
       }
     }
   }
-  void gather_rowpanel(int64_t k, int b) override {
+  void gather_rowpanel(int64_t k, int b) override { gather_impl(k, b, false); }
+  void gather_rowpanel_t(int64_t k, int b) override { gather_impl(k, b, true); }
+  void gather_impl(int64_t k, int b, bool transposed) {
     const int64_t nrem = lay.nblk - k - 1;
     if (nrem <= 0) return;
-    const int64_t nb = lay.nb;
+    const int64_t nb = lay.nb, Krem = nrem * nb;
     PeerPtrs pp{};
     for (int s = 0; s < mg->G; ++s) pp.p[s] = mg->rk[s].L;
     GatherMap gm{};
@@ -310,16 +335,28 @@ struct LocalComm : CommBase {
     for (int r = 0; r < mg->G; ++r) {
       MRank& R = mg->rk[r];
       act(r);
-      if (on_side(r)) {
+      if (on_side(r)) {   // copy engines -> staging (rank-major), then a local re-layout
         for (int s = 0; s < mg->G; ++s) {
           const int64_t cnt = lay.nloc(s) - gm.first[s];
           if (cnt > 0) dma2d(r, R.stage + (int64_t)gm.off[s] * nb * nb, nb, mg->rk[s].L + k * nb + (int64_t)gm.first[s] * nb * ld, ld, nb, cnt * nb);
         }
-        dim3 grid((unsigned)nrem, (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, 1024 / nrem)));
-        unpermute_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], R.stage, gm, mg->G, k, nb);
-      } else {
+        if (transposed) {
+          dim3 grid((unsigned)nrem, (unsigned)std::max<int64_t>(1, std::min<int64_t>((nb / 32) * (nb / 32), 2048 / nrem)));
+          unpermute_rowpanel_t_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], Krem, R.stage, gm, mg->G, k, nb);
+        } else {
+          dim3 grid((unsigned)nrem, (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, 1024 / nrem)));
+          unpermute_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], R.stage, gm, mg->G, k, nb);
+        }
+      } else {            // SM-driven peer reads straight into global column order (+ a local transpose)
         dim3 grid((unsigned)nrem, (unsigned)std::min<int64_t>(nb, std::max<int64_t>(4, 2048 / nrem)));
-        gather_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], pp, mg->G, ld, k, nb);
+        gather_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(transposed ? R.stage : R.panel[b], pp, mg->G, ld, k, nb);
+        if (transposed) {
+          R.be.note(cudaGetLastError());
+          R.ctx->launches++;
+          const int64_t tiles = (nb / 32) * (Krem / 32);
+          copy2d_transpose_kernel<<<(unsigned)std::min<int64_t>(tiles, 148 * 16), dim3(32, 8), 0, R.ctx->stream>>>(
+              R.panel[b], Krem, R.stage, nb, nb / 32, Krem / 32);
+        }
       }
       R.be.note(cudaGetLastError());
       R.ctx->launches++;
@@ -405,7 +442,9 @@ struct PackedComm : CommBase {
     bcast(o, [b](MRank& R) { return R.Ukk[b]; }, (size_t)(nb * nb));
     bcast(o, [k, dl](MRank& R) { return R.dinv + k * dl; }, (size_t)dl);
   }
-  void gather_rowpanel(int64_t k, int b) override {
+  void gather_rowpanel(int64_t k, int b) override { gather_impl(k, b, false); }
+  void gather_rowpanel_t(int64_t k, int b) override { gather_impl(k, b, true); }
+  void gather_impl(int64_t k, int b, bool transposed) {
     const int64_t nrem = lay.nblk - k - 1;
     if (nrem <= 0) return;
     const int64_t nb = lay.nb;
@@ -422,10 +461,15 @@ struct PackedComm : CommBase {
       if (cnt > 0) copy2d(R, R.stage + (size_t)R.rank * slot, nb, R.L + k * nb + first * nb * ld, ld, nb, cnt * nb);
     }
     allgather_stage(slot);
-    for (auto& R : mg->rk) {   // rank-major -> global column order
+    for (auto& R : mg->rk) {   // rank-major -> global column order (optionally transposed)
       cudaSetDevice(R.ctx->device);
-      dim3 grid((unsigned)nrem, (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, 1024 / nrem)));
-      unpermute_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], R.stage, gm, mg->G, k, nb);
+      if (transposed) {
+        dim3 grid((unsigned)nrem, (unsigned)std::max<int64_t>(1, std::min<int64_t>((nb / 32) * (nb / 32), 2048 / nrem)));
+        unpermute_rowpanel_t_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], nrem * nb, R.stage, gm, mg->G, k, nb);
+      } else {
+        dim3 grid((unsigned)nrem, (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, 1024 / nrem)));
+        unpermute_rowpanel_kernel<<<grid, 256, 0, R.ctx->stream>>>(R.panel[b], R.stage, gm, mg->G, k, nb);
+      }
       R.be.note(cudaGetLastError());
       R.ctx->launches++;
     }

@@ -169,6 +169,16 @@ struct CpuComm {
             R.panel[b][p + ((J - k - 1) * nb + c) * nb] = S.L[k * nb + p + ((J / lay.G) * nb + c) * S.ld];
       }
   }
+  void gather_rowpanel_t(int64_t k, int b) {
+    const int64_t nb = lay.nb, Krem = lay.Np - (k + 1) * nb;
+    for (auto& R : *ranks)
+      for (int64_t J = k + 1; J < lay.nblk; ++J) {
+        const auto& S = (*ranks)[lay.owner(J)];
+        for (int64_t c = 0; c < nb; ++c)
+          for (int64_t p = 0; p < nb; ++p)
+            R.panel[b][((J - k - 1) * nb + c) + p * Krem] = S.L[k * nb + p + ((J / lay.G) * nb + c) * S.ld];
+      }
+  }
   void bcast_colpanel(int64_t k, int b) {
     const int64_t nb = lay.nb;
     const auto& S = (*ranks)[lay.owner(k)];
