@@ -186,14 +186,14 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_kernel(const KBuildArgs a) 
   if (a.mean_w_rows) {
     // 16 threads (tx = 0..15) hold partial sums of the same column: reduce through shared memory in a fixed order
     __syncthreads();
-    double* red = kb_smem;                 // [16][64]
+    double* red = kb_smem;                 // [16][65]: the 16 writers of one column differ in tx -> odd row stride, no bank conflict
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[tx * KB_TILE + ty + 16 * j] = msum[j];
+    for (int j = 0; j < 4; ++j) red[tx * (KB_TILE + 1) + ty + 16 * j] = msum[j];
     __syncthreads();
     if (tid < KB_TILE) {
       double sacc = 0.0;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) sacc += red[q * KB_TILE + tid];
+      for (int q = 0; q < 16; ++q) sacc += red[q * (KB_TILE + 1) + tid];
       const long long c = c0 + tid;
       if (c < a.Cp) a.mean_partial[(long long)blockIdx.x * a.Cp + c] = sacc;
     }

@@ -168,7 +168,7 @@ int launch_kbuild(gpr_ctx* ctx, int mode, const KBuildArgs& a) {
   int nk = 0;
   for (int c = 0; c < a.spec.ncomp; ++c) if (a.spec.type[c] != KT_NOISE) nk++;
   size_t smem = (size_t)2 * nk * a.D * KB_TILE * sizeof(double);
-  if (a.mean_w || a.mean_w_rows) smem = std::max(smem, (size_t)16 * KB_TILE * sizeof(double));
+  if (a.mean_w || a.mean_w_rows) smem = std::max(smem, (size_t)16 * (KB_TILE + 1) * sizeof(double));
   if (smem > 200 * 1024) return fail(ctx, GPR_ERR_UNSUPPORTED, "covariance build: (#components x D) too large for shared memory");
   dim3 grid((unsigned)((a.Rp + KB_TILE - 1) / KB_TILE), (unsigned)((a.Cp + KB_TILE - 1) / KB_TILE));
   if (grid.y > 65535) return fail(ctx, GPR_ERR_UNSUPPORTED, "covariance build: too many column tiles");
