@@ -9,10 +9,15 @@ next point of a fixed hyper-parameter trajectory (so nothing can be cached betwe
   value : evaluations/s with x, y resident in HBM (only hp goes in and F, G come out per step)
   e2e   : the same through the C ABI with HOST buffers: every step re-uploads x, y from pinned host memory
           (gpr_model_set_x/_y), evaluates, and reads F, G back
-  N > 1 : replicas only: every rank evaluates its own hyper-parameter set; no data-path collective
-  --impl reference : the reference-shaped CPU path (oracle/gpr_oracle.py: materialised K per component, dpotrf,
-          dpotrs on the identity, per-hyper-parameter dK + dgemv + ddot) on the host cores, on a bounded sample
-          (smaller N, scaled by N^3 to the metric's configuration; flagged in cpu_baseline.sample)
+  N > 1 : the headline metric is replicas only: every rank evaluates its own hyper-parameter set, no
+          data-path collective.  The SHARDED paths are measured in the same run and reported under `extra`:
+            extra.config4 : split predict on the 4096 x 4096 sum-grid (16.8 M points), `e` rows sharded over the ranks
+            extra.config5 : ONE factorization distributed block-cyclically over all ranks (one process per GPU, panels
+                            over NCCL): N = 65536 for 1-2 GPUs, N = 131072 for 4-8 GPUs (strong scaling of one evaluation)
+  --impl reference : the reference-shaped CPU path (oracle/gpr_oracle_big.reference_shaped_eval: materialised K per
+          component, dpotrf, dpotrs on the identity, per-hyper-parameter dK + dgemv + ddot) on the host cores: one
+          calibration evaluation at N = 16384 (scale <= 8 to the metric's N) + the requested steps at the largest N
+          that fits the time budget; ms_per_step is the time actually spent per executed step
 """
 import argparse
 import json
@@ -90,64 +95,175 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle; checker/baseline only)
-def cpu_eval_seconds(N, D, hp0, steps, warmup, threads):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import gpr_oracle as o
-    x, y, _ = make_problem(N, D)
-    md = o.GPRModel((o.SE, o.SE, o.NOISE), hp0, x, y)
-    tc = o.MllGradCache(md)
-    ts = []
-    for s in range(warmup + steps):
+COV_REF = ("SquaredExp", "SquaredExp", "WhiteNoise")
+CALIBRATION = os.path.join(ROOT, "profiles", "cpu_calibration_r2.json")
+
+
+def host_info():
+    info = {"cores": os.cpu_count() or 1, "ram_gb": None, "blas": None, "blas_threads": None}
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                info["ram_gb"] = round(int(line.split()[1]) / 2 ** 20, 1)
+    except Exception:
+        pass
+    try:
+        import threadpoolctl
+        for lib in threadpoolctl.threadpool_info():
+            if lib.get("user_api") == "blas" and "scipy" in lib.get("filepath", ""):
+                info["blas"], info["blas_threads"] = f"{lib.get('internal_api')} {lib.get('version')}", lib.get("num_threads")
+    except Exception:
+        pass
+    return info
+
+
+class RefArm:
+    """The reference's evaluation AS IT EXECUTES IT (oracle/gpr_oracle_big.reference_shaped_eval; src/cost.jl:60-70,
+    96-127): one materialised N x N matrix per component, dpotrf, dpotrs, dpotrs on a materialised identity, then per
+    hyper-parameter a materialised dK + dgemv + 2 ddot.  BLAS/LAPACK calls use every host thread; the numpy
+    element-wise sweeps (covariance build, dK) are single-threaded, as Julia's broadcasts are."""
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import gpr_oracle_big as ob
+        self.ob = ob
+        self.ws = {}
+
+    def run(self, N, step):
+        x, y, hp0 = make_problem(N, D_FULL)
         t0 = time.perf_counter()
-        o.log_loss_grad(np.log(hp_at(hp0, s)), md, tc)
+        F, G, st, ws = self.ob.reference_shaped_eval(COV_REF, np.log(hp_at(hp0, step)), x, y, ws=self.ws.get(N))
         dt = time.perf_counter() - t0
-        if s >= warmup:
+        self.ws = {N: ws}                       # keep one workspace (MllGradCache) alive, like the reference's train loop
+        return dt, st, F
+
+    def drop(self):
+        self.ws = {}
+
+
+def fit_cost_model(sizes, times):
+    """t(N) = a N^3 + b N^2 (factor / solves vs the N^2 sweeps), least squares in relative error, a, b >= 0."""
+    n = np.asarray(sizes, dtype=np.float64)
+    t = np.asarray(times, dtype=np.float64)
+    A = np.stack([n ** 3 / t, n ** 2 / t], axis=1)
+    coef, *_ = np.linalg.lstsq(A, np.ones_like(t), rcond=None)
+    a, b = float(coef[0]), float(coef[1])
+    if a <= 0 or b < 0:
+        a, b = float(np.mean(t / n ** 3)), 0.0
+    return a, b
+
+
+def reference_measurement(steps, warmup, budget_s, n_cal_max=16384, log=None):
+    """Times the reference-shaped CPU evaluation.  (1) probes at N = 2048 and 4096; (2) ONE calibration evaluation at the
+    largest N <= n_cal_max whose predicted time fits a third of the budget and whose (nk + 3) N^2 workspace fits the
+    host RAM -- the value reported for N = 32768 is that measurement scaled by the fitted model, scale <= 8 when
+    N_cal = 16384; (3) `warmup` + `steps` real evaluations at the largest N whose predicted total fits the rest of the
+    budget: ms_per_step is their mean wall time, exactly what was executed."""
+    say = log or (lambda *a: None)
+    arm = RefArm()
+    hi = host_info()
+    t_start = time.perf_counter()
+    meas = {}
+    arm.run(1024, 0)                                        # spin up the BLAS thread pool
+    for n in (2048, 4096):
+        meas[n] = arm.run(n, 0)[0]
+        say(f"probe N={n}: {meas[n]:.2f} s")
+    a, b = fit_cost_model(list(meas), list(meas.values()))
+    pred = lambda n: a * n ** 3 + b * n ** 2
+    ram = hi["ram_gb"] or 16.0
+    n_cal, cal_stages = None, None
+    for cand in (32768, 16384, 12288, 8192):
+        if cand <= n_cal_max and 5 * 8 * cand ** 2 / 2 ** 30 <= 0.8 * ram and pred(cand) <= budget_s / 3:
+            n_cal = cand
+            break
+    if n_cal:
+        dt, cal_stages, _ = arm.run(n_cal, 0)
+        meas[n_cal] = dt
+        say(f"calibration N={n_cal}: {dt:.1f} s {cal_stages}")
+        a, b = fit_cost_model(list(meas), list(meas.values()))
+    arm.drop()
+    left = budget_s - (time.perf_counter() - t_start)
+    n_step = 2048
+    for cand in (16384, 12288, 8192, 6144, 4096, 3072):
+        if (cand in meas or 5 * 8 * cand ** 2 / 2 ** 30 <= 0.8 * ram) and (steps + warmup) * (meas.get(cand) or pred(cand)) <= left:
+            n_step = cand
+            break
+    ts, F = [], None
+    for sidx in range(warmup + steps):
+        dt, st, F = arm.run(n_step, sidx)
+        if sidx >= warmup:
             ts.append(dt)
-    return ts
+    t_step = float(np.mean(ts))
+    meas_all = dict(meas)
+    meas_all[n_step] = t_step if n_step not in meas else 0.5 * (meas[n_step] + t_step)
+    a, b = fit_cost_model(list(meas_all), list(meas_all.values()))
+    n_base = max(meas_all)                                  # largest size that actually ran
+    scale = (a * N_FULL ** 3 + b * N_FULL ** 2) / (a * n_base ** 3 + b * n_base ** 2)
+    t_full = meas_all[n_base] * scale
+    return {"t_full": t_full, "n_base": n_base, "t_base": meas_all[n_base], "scale": scale, "n_step": n_step, "t_step": t_step,
+            "measured": {str(k): round(v, 3) for k, v in sorted(meas_all.items())}, "fit": {"a_N3": a, "b_N2": b},
+            "calibration_stages_s": {k: round(v, 2) for k, v in (cal_stages or {}).items()}, "host": hi, "F_last": F}
 
 
-def cpu_baseline(hp0, budget_s=25.0, steps=1, warmup=0):
-    """Reference-shaped CPU path timed on the host cores on a bounded sample and extrapolated to N = 32768 with the
-    cost model t(N) = a N^3 + b N^2 (factor / inverse vs the P per-hyper-parameter sweeps), a and b fitted to the
-    measured times at N/2 and N of the sample (plain N^3 scaling would overstate the CPU time: at sample sizes the
-    N^2 P term is a large share)."""
-    cores = os.cpu_count() or 1
-    t_probe = cpu_eval_seconds(2048, D_FULL, hp0, 1, 1, cores)[0]
-    Ns = 4096
-    for cand in (8192,):
-        if t_probe * (cand / 2048) ** 3 * (steps + warmup) <= budget_s:
-            Ns = cand
-    ts = cpu_eval_seconds(Ns, D_FULL, hp0, steps, warmup, cores)
-    t = float(np.mean(ts))
-    t_half = t_probe if Ns == 4096 else float(np.mean(cpu_eval_seconds(Ns // 2, D_FULL, hp0, 1, 0, cores)))
-    n = Ns / 2.0
-    a = (t - 4.0 * t_half) / (4.0 * n ** 3)
-    b = (t_half - a * n ** 3) / n ** 2
-    if a <= 0 or b < 0:                      # noisy fit: fall back to pure N^3 scaling
-        a, b = t / Ns ** 3, 0.0
-    t_full = a * N_FULL ** 3 + b * N_FULL ** 2
-    scale = t_full / t
-    return {"value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle (numpy+scipy OpenBLAS, {cores} threads) log_loss_grad at N={Ns}, D=8, P=19: {t:.2f} s/eval measured "
-                      f"({t_half:.2f} s at N={Ns // 2}); extrapolated to N=32768 with t = a N^3 + b N^2 fitted to the two sizes "
-                      f"(x{scale:.0f}) -- extrapolated",
-            "seconds_per_eval_sample": t, "sample_N": Ns, "scale": scale}, ts, Ns
+def describe(m):
+    h = m["host"]
+    return (f"reference-shaped CPU path (oracle/gpr_oracle_big.reference_shaped_eval: per-component K, dpotrf, dpotrs on the identity, "
+            f"per-hp dK + dgemv + ddot) on {h['cores']} host cores, {h['blas']} with {h['blas_threads']} threads for BLAS/LAPACK "
+            f"(numpy element-wise sweeps single-threaded), {h['ram_gb']} GB RAM available; measured s/eval {m['measured']}; "
+            f"value = measured {m['t_base']:.1f} s at N={m['n_base']} x {m['scale']:.2f} (t = a N^3 + b N^2 fitted to the measured sizes) "
+            f"= {m['t_full']:.0f} s per evaluation at N=32768" + (" -- scaled, not run at full size" if m["n_base"] != N_FULL else ""))
+
+
+def cpu_baseline(budget_s=30.0):
+    """cpu_baseline leg of the default run: a bounded sample (one evaluation at the largest N that fits ~budget_s),
+    scaled with the a N^3 + b N^2 model; when profiles/cpu_calibration_r2.json (a full --impl reference run with an
+    N = 16384 / 32768 calibration on this pool's host) is present its measured figure is quoted beside it."""
+    arm = RefArm()
+    hi = host_info()
+    arm.run(1024, 0)
+    meas = {2048: arm.run(2048, 0)[0]}
+    meas[4096] = arm.run(4096, 0)[0]
+    a, b = fit_cost_model(list(meas), list(meas.values()))
+    if a * 8192 ** 3 + b * 8192 ** 2 <= budget_s:
+        meas[8192] = arm.run(8192, 0)[0]
+        a, b = fit_cost_model(list(meas), list(meas.values()))
+    n_base = max(meas)
+    scale = (a * N_FULL ** 3 + b * N_FULL ** 2) / (a * n_base ** 3 + b * n_base ** 2)
+    t_full = meas[n_base] * scale
+    cal = None
+    try:
+        cal = json.load(open(CALIBRATION))
+    except Exception:
+        pass
+    sample = (f"reference-shaped CPU path (oracle/gpr_oracle_big.reference_shaped_eval) on {hi['cores']} host cores ({hi['blas']}, "
+              f"{hi['blas_threads']} BLAS threads), measured s/eval {({k: round(v, 2) for k, v in meas.items()})}; scaled x{scale:.0f} "
+              f"from N={n_base} with t = a N^3 + b N^2 -- extrapolated")
+    out = {"value": 1.0 / t_full, "unit": UNIT, "cores": hi["cores"], "kind": "port", "sample": sample, "sample_N": n_base, "scale": scale}
+    if cal:
+        out["calibrated"] = {"value": cal.get("value"), "sample_N": cal.get("sample_N"), "scale": cal.get("scale"),
+                             "source": "profiles/cpu_calibration_r2.json (bench.py --impl reference on this pool's host, committed)"}
+    return out
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    _, _, hp0 = make_problem(16, D_FULL)
-    budget = 150.0
-    base, ts, Ns = cpu_baseline(hp0, budget_s=budget, steps=args.steps, warmup=args.warmup)
-    t = float(np.mean(ts))
-    scale = base["scale"]
-    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * scale * 1e3, "higher_is_better": True,
+    budget = float(os.environ.get("GPR_REF_BUDGET_S", "1200"))
+    n_cal_max = int(os.environ.get("GPR_REF_NCAL", "16384"))
+    m = reference_measurement(args.steps, args.warmup, budget, n_cal_max, log=lambda s: print("[reference]", s, file=sys.stderr, flush=True))
+    value = 1.0 / m["t_full"]
+    base = {"value": value, "unit": UNIT, "cores": m["host"]["cores"], "kind": "port", "sample": describe(m),
+            "sample_N": m["n_base"], "scale": m["scale"]}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["t_step"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "timing": f"host wall clock; each step is a bounded sample at N={Ns}, extrapolated with t = a N^3 + b N^2"},
-            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": {"workload": WORKLOAD,
+                       "timing": f"host wall clock; ms_per_step = mean wall time of the {args.steps} executed steps, each one real evaluation at "
+                                 f"N={m['n_step']} (the largest size at which warmup+steps fit the time budget); value = the largest measured size "
+                                 f"(N={m['n_base']}, {m['t_base']:.1f} s) scaled x{m['scale']:.2f} to N=32768",
+                       "step_N": m["n_step"], "sample_N": m["n_base"], "scale": m["scale"], "same_config": m["n_base"] == N_FULL},
+            "cpu_baseline": base, "reference_detail": {k: m[k] for k in ("measured", "fit", "calibration_stages_s", "host", "n_step", "t_step")},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -176,6 +292,184 @@ def measure_fp64_peak(torch, n=8192):
     del a, b
     torch.cuda.empty_cache()
     return 2 * n ** 3 / best / 1e9, 2 * n ** 3 / sustained / 1e9
+
+
+def predict_extras(args, mh, hp0, N, D):
+    """Secondary metric of BASELINE.json: predictive points/s (general test points, mean + diagonal variance and mean only)."""
+    extra = {}
+    M = 16384
+    xp = np.asfortranarray(np.random.default_rng(4004).random((D, M)))
+    mh.update_cache(hp0)
+    mh.predict(xp, want_var=True)
+    t0 = time.perf_counter()
+    mu, var, _ = mh.predict(xp, want_var=True)
+    dt = time.perf_counter() - t0
+    tp = mh.timings()
+    extra["predict_points_per_s"] = M / dt
+    extra["predict_var_tflops"] = M * float(N) ** 2 / dt / 1e12
+    extra["predict_stage_ms"] = {k: round(v, 3) for k, v in tp.items() if k.startswith("pred")}
+    # the two streaming kernels (K* . wt and row norms of V) read 8*M*N bytes each
+    hbm = 6478.9
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    # streams of the prediction: the K* tile is written once (8*M*N bytes) and V = K* U^-1 is read once for the row
+    # norms; mu = K* wt is reduced inside the K* build (no separate stream since round 1c)
+    extra["predict_stream_gbs"] = {"kstar_build_write": 8.0 * M * N / tp["pred_kstar"] / 1e6, "rownorm_v": 8.0 * M * N / tp["pred_rownorm"] / 1e6,
+                                   "mean": "fused into the K* build", "hbm_peak_gbs": hbm}
+    mh.predict(xp, want_var=False)
+    t0 = time.perf_counter()
+    mh.predict(xp, want_var=False)
+    extra["predict_mean_only_points_per_s"] = M / (time.perf_counter() - t0)
+    extra["predict_config"] = f"mean+diag variance, M={M} general test points, host in/out, N={N}"
+    return extra
+
+
+def config4_split_predict(torch, dist, _ffi, ctx, rank, world, nvar_rows=64):
+    """BASELINE.json config 4: posterior mean for all ne x nq = 16.8 M sum-grid points and the variance of
+    `nvar_rows` e rows per rank through gpr_split_predict (src/split_predict.jl:10-53), N = 32768 training points, the `e`
+    rows in contiguous blocks per rank (independent units: no data-path collective).  Timed on the device side of each
+    call (barrier + synchronize on both sides, max over ranks)."""
+    from gpr_sm100a import shard
+    N, D, ne, nq = N_FULL, D_FULL, 4096, 4096
+    x, y, hp = make_problem(N, D)
+    rng = np.random.default_rng(4004)
+    xe, xq = np.asfortranarray(0.5 * rng.random((D, ne))), np.asfortranarray(0.5 * rng.random((D, nq)))
+    mh = _ffi.ModelHandle(ctx, [1, 1, 2], D, x, y)
+    mh.update_cache(hp)
+    lo, hi = shard.block_range(ne, rank, world)
+    xe_blk = np.asfortranarray(xe[:, lo:hi])
+    nv = min(nvar_rows, hi - lo)
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    mh.split_predict(xe_blk[:, :128], xq, var_range=None, want_var=False)       # warm-up (workspaces)
+    sync()
+    t0 = time.perf_counter()
+    mean, _ = mh.split_predict(xe_blk, xq, var_range=None, want_var=False)
+    sync()
+    t_mean = time.perf_counter() - t0
+    tm = mh.timings()
+    t0 = time.perf_counter()
+    _, var = mh.split_predict(xe_blk[:, :nv], xq, var_range=(1, nv), want_var=True)
+    sync()
+    t_var = time.perf_counter() - t0
+    tv = mh.timings()
+    if dist is not None:
+        tt = torch.tensor([t_mean, t_var], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_mean, t_var = float(tt[0]), float(tt[1])
+    out = None
+    if rank == 0:
+        worst_mu = worst_var = 0.0
+        for e in (0, nv // 2, nv - 1):             # split path vs the dense path of the library on explicit points
+            pts = np.asfortranarray(xe_blk[:, e:e + 1] + xq[:, :512])
+            mu_d, var_d, _ = mh.predict(pts, want_var=True)
+            worst_mu = max(worst_mu, float(np.abs(mu_d[:, 0] - mean[e, :512]).max()))
+            worst_var = max(worst_var, float(np.abs(var_d - var[e * nq:e * nq + 512]).max()))
+        M = ne * nq
+        nvp = world * nv * nq
+        out = {"workload": f"split predict, N={N}, ne=nq={ne} (M={M}), e rows sharded over {world} rank(s); variance of {nv} e rows per rank",
+               "mean_ms_all_points": t_mean * 1e3, "mean_points_per_s": M / t_mean, "mean_tflops": 2.0 * 2 * ne * nq * N / t_mean / 1e12,
+               "mean_stage_ms_rank0": {k: round(v, 2) for k, v in tm.items() if k.startswith("split") and v > 0},
+               "var_points": nvp, "var_s": t_var, "var_points_per_s": nvp / t_var, "var_tflops_aggregate": nvp * float(N) ** 2 / t_var / 1e12,
+               "var_stage_ms_rank0": {k: round(v, 2) for k, v in tv.items() if k.startswith("pred") and v > 0},
+               "parity_split_vs_dense": {"max_abs_mean_diff": worst_mu, "max_abs_var_diff": worst_var, "rows": 3, "points_per_row": 512},
+               "timing": "host clock around each C-ABI call (host xe/xq in, mean/var out), barrier + synchronize on both sides, max over ranks"}
+    mh.close()
+    return out
+
+
+def config5_distributed(torch, dist, _ffi, rank, world, local_rank, n_override=None, evals=1):
+    """BASELINE.json config 5: ONE NLML + gradient evaluation of SquaredExp()+WhiteNoise(), D = 16,
+    with K / U / K^-1 block-cyclic over all ranks (csrc/dist_blocked.hpp; one process per GPU, panels travel by
+    ncclBroadcast / ncclAllGather, the P + 3 partial sums by ncclAllReduce).  N = 65536 on 1-2 GPUs, 131072 on 4-8
+    (the 137 GB covariance of the full configuration needs >= 4 GPUs next to the out-of-place workspaces).
+    Reports per-phase milliseconds, TFLOP/s per GPU, |K alpha - y| on sampled columns; reference: src/cost.jl:96-127."""
+    from gpr_sm100a import shard
+    N = n_override or (65536 if world <= 2 else 131072)
+    D = 16
+    rng = np.random.default_rng(5005)
+    x = np.asfortranarray(rng.random((D, N)))
+    y = np.sin(3 * x).sum(0) + 0.1 * rng.standard_normal(N)
+    hp = np.concatenate([[1.0], 0.4 * np.ones(D), [0.1]])
+    mc = shard.dist_context(device=local_rank, nb=1024) if world > 1 else _ffi.MultiContext([local_rank], nb=1024)
+    mm = _ffi.MultiModelHandle(mc, [1, 2], D, x, y)
+    mm.nlml_grad(hp * 0.99)                                     # warm-up evaluation
+    ts, F, G, tm = [], None, None, None
+    for _ in range(evals):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        F, G = mm.nlml_grad(hp)
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+        tm = mm.timings()
+    t = min(ts)
+    if dist is not None:
+        tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+    alpha = mm.fetch(_ffi.FETCH_ALPHA)
+    out = None
+    if rank == 0:
+        cols = np.random.default_rng(1).choice(N, 32, replace=False)
+        sig, ell, sn = hp[0], hp[1:-1], hp[-1]
+        xs = x * ell[:, None]
+        Kc = sig * sig * np.exp(-((xs[:, :, None] - xs[:, None, cols]) ** 2).sum(0))
+        Kc[cols, np.arange(32)] += 1e-8 + sn * sn
+        resid = float(np.abs(Kc.T @ alpha - y[cols]).max() / np.abs(y).max())
+        dense_ms = tm["potrf"] + tm["trtri"] + tm["lauum"]
+        out = {"workload": f"one NLML+gradient, SquaredExp()+WhiteNoise() P=18, N={N}, D=16, block-cyclic over {world} rank(s), nb=1024",
+               "transport": "NCCL (one process per GPU)" if world > 1 else "single rank",
+               "s_per_eval": t, "evals_per_s": 1.0 / t, "phase_ms": {k: round(v, 1) for k, v in tm.items() if v > 0 and not k.startswith("pred")},
+               "dense_tflops_aggregate": float(N) ** 3 / (dense_ms * 1e-3) / 1e12, "dense_tflops_per_gpu": float(N) ** 3 / (dense_ms * 1e-3) / 1e12 / world,
+               "phase_tflops_per_gpu": {k: float(N) ** 3 / 3 / (tm[k] * 1e-3) / 1e12 / world for k in ("potrf", "trtri", "lauum")},
+               "limiter": max(("potrf", "trtri", "lauum"), key=lambda k: tm[k]),
+               "F": F, "G_norm": float(np.linalg.norm(G)), "resid_K_alpha_minus_y": resid,
+               "timing": "host clock around gpr_mgpu_nlml_grad after a barrier, max over ranks; phases: CUDA events of rank 0"}
+    mm.close()
+    mc.close()
+    return out
+
+
+def config3_ext_and_training(_ffi, ctx, steps=2):
+    """Config 3 as BASELINE.json words it: SquaredExp()+Matern52()+WhiteNoise() (3-ext; Matern-5/2 is an extension, parity
+    unpinned) evaluations/s, and a free-running L-BFGS training run of 3-ref at N = 32768 (src/train.jl:47-56: log-space
+    fg! closure over one cache, host optimiser)."""
+    import scipy.optimize as so
+    x, y, hp0 = make_problem(N_FULL, D_FULL)
+    out = {}
+    mh = _ffi.ModelHandle(ctx, [1, 3, 2], D_FULL, x, y)
+    mh.nlml_grad(np.log(hp0), log_scale=True)
+    ev = 0.0
+    for sidx in range(steps):
+        mh.nlml_grad(np.log(hp_at(hp0, sidx + 1)), log_scale=True)
+        ev += mh.timings()["eval"]
+    out["config3_ext"] = {"workload": "SquaredExp()+Matern52()+WhiteNoise() P=19, N=32768, D=8 (extension: parity vs own oracle only)",
+                          "evals_per_s": steps / (ev * 1e-3), "ms_per_eval": ev / steps}
+    mh.close()
+    mh = _ffi.ModelHandle(ctx, [1, 1, 2], D_FULL, x, y)
+    trace = []
+
+    def fg(v):
+        F, G = mh.nlml_grad(v, log_scale=True)
+        trace.append(F)
+        return F, G
+
+    t0 = time.perf_counter()
+    res = so.minimize(fg, np.log(hp0), jac=True, method="L-BFGS-B", options={"maxiter": 4, "maxfun": 8})
+    dt = time.perf_counter() - t0
+    out["train_free_running"] = {"workload": "L-BFGS-B from the benchmark hp, 3-ref, N=32768 (src/train.jl:47-56), maxiter 4",
+                                 "iterations": int(res.nit), "evaluations": len(trace), "seconds": dt, "evals_per_s": len(trace) / dt,
+                                 "F_start": trace[0], "F_end": float(res.fun)}
+    mh.close()
+    return out
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -260,6 +554,23 @@ def run_gpu(args, rank, world, local_rank):
         t_e = float(tt.item())
     e2e = {"value": world * args.steps / t_e, "unit": UNIT, "h2d_bytes_per_step": 8 * (D * N + N + P), "d2h_bytes_per_step": 8 * (P + 1)}
 
+    # secondary single-GPU numbers that need the headline model (rank 0 only), then free it for the sharded extras
+    pred_extra = predict_extras(args, mh, hp0, N, D) if (rank == 0 and not args.no_predict) else {}
+    gemm_ms = None
+    if rank == 0:
+        rng = np.random.default_rng(0)
+        A = np.asfortranarray(rng.standard_normal((4096, 4096)))
+        _, gemm_ms = _ffi.dbg_dgemm(ctx, "T", "N", 1.0, A, A, 0.0, np.zeros((4096, 4096), order="F"), reps=6)
+    mh.close()
+    sharded = {}
+    if not args.no_sharded:
+        sharded["config4"] = config4_split_predict(torch, dist, _ffi, ctx, rank, world)
+        sharded["config5"] = config5_distributed(torch, dist, _ffi, rank, world, local_rank, n_override=args.config5_n)
+        if args.config5_base and world == 1:
+            sharded["config5_base_1gpu_n131072"] = config5_distributed(torch, dist, _ffi, rank, world, local_rank, n_override=131072)
+        if rank == 0 and world == 1 and N == N_FULL:
+            sharded.update(config3_ext_and_training(_ffi, ctx))
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -271,42 +582,13 @@ def run_gpu(args, rank, world, local_rank):
     flops_factor_inverse = float(N) ** 3                                # N^3/3 potrf + 2N^3/3 trtri+lauum
     t_dense = (ms["potrf"] + ms["trtri"] + ms["lauum"]) * 1e-3
     achieved = flops_factor_inverse / t_dense / 1e12
-    # the GEMM kernel alone, one launch (8192^3), timed with CUDA events inside the library
-    rng = np.random.default_rng(0)
-    A = np.asfortranarray(rng.standard_normal((4096, 4096)))
-    _, gemm_ms = _ffi.dbg_dgemm(ctx, "T", "N", 1.0, A, A, 0.0, np.zeros((4096, 4096), order="F"), reps=6)
     gemm_tf = 2 * 4096 ** 3 / gemm_ms / 1e9
 
     # secondary metrics of BASELINE.json: Cholesky TFLOP/s, predict points/s
     extra = {"cholesky_tflops": N ** 3 / 3 / ms["potrf"] / 1e9, "inverse_tflops": 2 * N ** 3 / 3 / (ms["trtri"] + ms["lauum"]) / 1e9,
              "stage_ms_per_step": {k: round(v, 3) for k, v in ms.items() if v > 0 and not k.startswith("pred")}}
-    if not args.no_predict:
-        M = 16384
-        xp = np.asfortranarray(np.random.default_rng(4004).random((D, M)))
-        mh.update_cache(hp0)
-        mh.predict(xp, want_var=True)
-        t0 = time.perf_counter()
-        mu, var, _ = mh.predict(xp, want_var=True)
-        dt = time.perf_counter() - t0
-        tp = mh.timings()
-        extra["predict_points_per_s"] = M / dt
-        extra["predict_var_tflops"] = M * float(N) ** 2 / dt / 1e12
-        extra["predict_stage_ms"] = {k: round(v, 3) for k, v in tp.items() if k.startswith("pred")}
-        # the two streaming kernels (K* . wt and row norms of V) read 8*M*N bytes each
-        hbm = 6478.9
-        try:
-            hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-        except Exception:
-            pass
-        # streams of the prediction: the K* tile is written once (8*M*N bytes) and V = K* U^-1 is read once for the row
-        # norms; mu = K* wt is reduced inside the K* build (no separate stream since round 1c)
-        extra["predict_stream_gbs"] = {"kstar_build_write": 8.0 * M * N / tp["pred_kstar"] / 1e6, "rownorm_v": 8.0 * M * N / tp["pred_rownorm"] / 1e6,
-                                       "mean": "fused into the K* build", "hbm_peak_gbs": hbm}
-        mh.predict(xp, want_var=False)
-        t0 = time.perf_counter()
-        mh.predict(xp, want_var=False)
-        extra["predict_mean_only_points_per_s"] = M / (time.perf_counter() - t0)
-        extra["predict_config"] = f"mean+diag variance, M={M} general test points, host in/out, N={N}"
+    extra.update(pred_extra)
+    extra.update(sharded)
 
     hp_peak = None
     try:
@@ -330,8 +612,7 @@ def run_gpu(args, rank, world, local_rank):
 
     base = None
     if world == 1 and not args.no_cpu:
-        base, _, _ = cpu_baseline(hp0, budget_s=25.0)
-        base = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        base = cpu_baseline(budget_s=30.0)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -359,6 +640,9 @@ def main():
     ap.add_argument("--n", type=int, default=N_FULL, help="training-set size (default: the metric's N=32768)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-predict", action="store_true", help="skip the secondary predict metric")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded extras (config 4 / config 5 / 3-ext / training)")
+    ap.add_argument("--config5-n", type=int, default=None, help="override N of the config-5 extra (default 65536 for 1-2 GPUs, 131072 for 4-8)")
+    ap.add_argument("--config5-base", action="store_true", help="1 GPU only: also run config 5 at N = 131072 in place on one GPU (strong-scaling base, ~2.5 min)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -70,6 +70,7 @@ struct GemmParams {
   long long sA, sB, sC;   // strided batch (blockIdx.z)
   const int* col_gtile;   // GEMM_MAP_*: global 128-tile column per local 128-tile column (device memory)
   int row_gtile0, k_gtile0;
+  const double* E; long long lde;   // EPI instantiation: C = alpha * (op(A) op(B)) .* E + beta * C  (E laid out like C)
 };
 
 // smem layout of one operand tile with ROWS rows (m or n extent) and 16 k
@@ -123,8 +124,11 @@ template <bool KC> __device__ __forceinline__ int gemm_col_of(int wn, int j, int
   return KC ? (32 * wn + 8 * j + q) : (32 * wn + 16 * (j >> 1) + 2 * q + (j & 1));
 }
 
-template <bool A_KC, bool B_KC, int MI, int WN>
+// EPI: Hadamard epilogue C = alpha * acc .* E + beta * C (T,N form only) -- the split-predict mean
+// mu += A_k .* (B_k (Diagonal(wt) C_k)) of /root/reference/src/split_predict.jl:14-16 in one pass, no BCw round trip.
+template <bool A_KC, bool B_KC, int MI, int WN, bool EPI = false>
 __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN_CTAS) dgemm128_kernel(const GemmParams p) {
+  static_assert(!EPI || (A_KC && B_KC), "the Hadamard epilogue exists for the T,N form only");
   extern __shared__ __align__(16) double gemm_smem[];
   using Cfg = GemmCfg<MI, WN>;
   constexpr int BN = Cfg::BN;
@@ -276,6 +280,16 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     double old[MI][2];
+    double ep[EPI ? MI : 1][2];
+    if constexpr (EPI) {
+      const double* Ep = p.E + bz * p.sC + m0 + n0 * p.lde;
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const double* Ecol = Ep + (long long)gemm_col_of<B_KC>(wn, j, 2 * t + v) * p.lde;
+#pragma unroll
+        for (int i = 0; i < (EPI ? MI : 1); ++i) ep[i][v] = Ecol[gemm_row_of<true, MI>(wm, i, g)];
+      }
+    }
     if (beta != 0.0) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
@@ -314,7 +328,8 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
         for (int i = 0; i < MI; ++i) {
           const int row = gemm_row_of<true, MI>(wm, i, g);
           if (diag_tile && row > col + coff) continue;
-          Ccol[row] = alpha * acc[i][j][v] + beta * old[i][v];
+          if constexpr (EPI) Ccol[row] = alpha * acc[i][j][v] * ep[i][v] + beta * old[i][v];
+          else Ccol[row] = alpha * acc[i][j][v] + beta * old[i][v];
         }
       } else {
 #pragma unroll
@@ -334,7 +349,7 @@ __global__ void __launch_bounds__(GemmCfg<MI, WN>::THREADS, GemmCfg<MI, WN>::MIN
   }
 }
 
-template <bool A_KC, bool B_KC, int MI, int WN> constexpr size_t gemm_smem_bytes() {
+template <bool A_KC, bool B_KC, int MI, int WN, bool EPI = false> constexpr size_t gemm_smem_bytes() {
   return (size_t)GemmCfg<MI, WN>::STAGES *
          (GemmTile<A_KC, GEMM_BM>::ELEMS + GemmTile<B_KC, GemmCfg<MI, WN>::BN>::ELEMS) * sizeof(double);
 }
@@ -354,6 +369,9 @@ inline cudaError_t gemm_setup_attributes() {
   cudaError_t e = gemm_set_attr_cfg<8, 4>();
   if (e == cudaSuccess) e = gemm_set_attr_cfg<8, 2>();
   if (e == cudaSuccess) e = gemm_set_attr_cfg<4, 4>();
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(dgemm128_kernel<true, true, 8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)gemm_smem_bytes<true, true, 8, 2>());
   return e;
 }
 
@@ -370,28 +388,32 @@ inline cudaError_t gemm_launch_form(cudaStream_t st, const GemmParams& p, int ba
   return gemm_launch_cfg<false, false, MI, WN>(st, p, batch);
 }
 
-// Tile configuration: 0 = automatic, 1 = 128x128 / 8 warps, 2 = 128x64 / 4 warps x 2 CTAs, 3 = 128x128 / 16 warps
-// (option "gemm_cfg": tuning and tests).
-inline int& gemm_forced_cfg() { static int v = 0; return v; }
-
+// Tile configuration `cfg`: 0 = automatic, 1 = 128x128 / 8 warps, 2 = 128x64 / 4 warps x 2 CTAs, 3 = 128x128 / 16 warps
+// (per-context option "gemm_cfg": tuning and tests; passed in by the caller, there is no process-global state).
 // transA/transB: 'N' or 'T' (BLAS meaning, column major).  Supported: TN, NN, NT.
 inline cudaError_t launch_dgemm128(cudaStream_t st, char transA, char transB, int M, int N, int K, double alpha,
                                    const double* A, long long lda, const double* B, long long ldb, double beta,
                                    double* C, long long ldc, int flags, int batch = 1, long long sA = 0,
                                    long long sB = 0, long long sC = 0, const int* col_gtile = nullptr,
-                                   int row_gtile0 = 0, int k_gtile0 = 0) {
+                                   int row_gtile0 = 0, int k_gtile0 = 0, int cfg = 0, const double* E = nullptr,
+                                   long long lde = 0) {
   if (M <= 0 || N <= 0 || batch <= 0) return cudaSuccess;
   if ((M % GEMM_BM) || (N % GEMM_BN) || (K % GEMM_BK) || K <= 0 || batch > 65535) return cudaErrorInvalidValue;
   if ((flags & GEMM_K_FROM_N) && K < N) return cudaErrorInvalidValue;
   if ((flags & (GEMM_MAP_UPPER | GEMM_MAP_KUPTO | GEMM_MAP_BROWS)) && !col_gtile) return cudaErrorInvalidValue;
-  GemmParams p{M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, flags, sA, sB, sC, col_gtile, row_gtile0, k_gtile0};
+  GemmParams p{M, N, K, alpha, beta, A, lda, B, ldb, C, ldc, flags, sA, sB, sC, col_gtile, row_gtile0, k_gtile0, E, lde};
   const bool aT = (transA == 'T' || transA == 't'), bT = (transB == 'T' || transB == 't');
   if (aT && bT) return cudaErrorNotSupported;
+  if (E) {   // Hadamard epilogue: T,N form, 128x64 tile
+    if (!aT || bT || flags) return cudaErrorNotSupported;
+    dim3 grid(M / GEMM_BM, N / GemmCfg<8, 2>::BN, batch), block(GemmCfg<8, 2>::THREADS);
+    dgemm128_kernel<true, true, 8, 2, true><<<grid, block, gemm_smem_bytes<true, true, 8, 2>(), st>>>(p);
+    return cudaGetLastError();
+  }
   // C written over the A operand: a CTA must own every k column it reads -> full-width 128x128 tile.
   const bool alias_a = (flags & GEMM_C_ALIASES_A) || (const double*)C == A;
   // default: 128x64 tiles, two co-resident CTAs per SM (measured on B200 at 4096^3: TN 33.8 / NN 34.3 / NT 31.4
   // TFLOP/s vs 31.5 / 30.8 / 29.8 for the single-CTA 128x128 tile; cuBLAS DGEMM 35.4)
-  int cfg = gemm_forced_cfg();
   if (cfg < 1 || cfg > 3) cfg = 2;
   if (alias_a && cfg == 2) cfg = 1;
   if (cfg == 1) return gemm_launch_form<8, 4>(st, p, batch, aT, bT);

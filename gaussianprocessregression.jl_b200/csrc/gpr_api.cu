@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -25,6 +27,14 @@ using namespace gpr;
 namespace {
 
 thread_local std::string g_create_error;
+
+// Live-handle registry.  A host with finalizers (the Julia glue, julia/GPRsm100a.jl) may release a context before the
+// models created on it, or a handle twice at exit: a *_destroy call on a handle that is not (or no longer) registered
+// is a no-op, and destroying a context first releases the models it still owns.
+std::mutex g_live_mu;
+std::set<const void*> g_live;
+bool live_take(const void* h) { std::lock_guard<std::mutex> l(g_live_mu); return g_live.erase(h) > 0; }
+void live_add(const void* h) { std::lock_guard<std::mutex> l(g_live_mu); g_live.insert(h); }
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
@@ -45,6 +55,8 @@ struct gpr_ctx {
   int inplace_lauum = 0;   // option "inplace_lauum": force the recursive in-place W W^T (saves one N x N buffer)
   int leaf_lookahead = 1;  // option "leaf_lookahead": factor the next diagonal leaf on the side queue (csrc/blocked.hpp)
   int alpha_from_inverse = 1;   // option "alpha_from_inverse": alpha = K^-1 y by a symmetric product on the gradient path
+  int gemm_cfg = 0;             // option "gemm_cfg": forced tile configuration of dgemm128 (0 = automatic), per context
+  std::vector<gpr_model*> models;   // live models of this context (released by gpr_ctx_destroy if the caller has not)
   long long launches = 0;
   long long* d_info = nullptr;
   cudaError_t pending = cudaSuccess;   // first launch error seen by the backend
@@ -82,9 +94,16 @@ struct CudaBE {
     for (int64_t z0 = 0; z0 < batch; z0 += 32768) {
       const int64_t nb = std::min<int64_t>(32768, batch - z0);
       note(launch_dgemm128(ctx->stream, tA, tB, (int)M, (int)N, (int)K, alpha, A + z0 * sA, lda, B + z0 * sB, ldb, beta,
-                           C + z0 * sC, ldc, flags, (int)nb, sA, sB, sC));
+                           C + z0 * sC, ldc, flags, (int)nb, sA, sB, sC, nullptr, 0, 0, ctx->gemm_cfg));
       ctx->launches++;
     }
+  }
+  // C = (A^T B) .* E + beta C, T,N form with the Hadamard epilogue (split-predict mean)
+  void gemm_hadamard(int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb,
+                     const double* E, int64_t lde, double beta, double* C, int64_t ldc) {
+    note(launch_dgemm128(ctx->stream, 'T', 'N', (int)M, (int)N, (int)K, 1.0, A, lda, B, ldb, beta, C, ldc, 0, 1, 0, 0, 0, nullptr, 0, 0,
+                         0, E, lde));
+    ctx->launches++;
   }
   void activate() { note(cudaSetDevice(ctx->device)); }
   void fork() { note(cudaEventRecord(ctx->ev_fork, ctx->main_stream)); note(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0)); }
@@ -94,7 +113,7 @@ struct CudaBE {
   void gemm_map(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, const TileMap& map) {
     note(launch_dgemm128(ctx->stream, tA, tB, (int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, 0, 0, 0,
-                         map.col_gtile, map.row_gtile0, map.k_gtile0));
+                         map.col_gtile, map.row_gtile0, map.k_gtile0, ctx->gemm_cfg));
     ctx->launches++;
   }
   void potrf_leaf(double* A, int64_t lda, double* dinv, int64_t goff) {
@@ -214,6 +233,7 @@ struct gpr_model {
   int64_t info_host = 0;
   // predict workspaces (lazy)
   DevBuf w_kxp, w_xp, w_part, w_mean, w_var;
+  DevBuf w_sA, w_sBt, w_sC, w_sCu, w_sx, w_smu;   // split predict (GPRSplitPredictCache)
   Timer tm;
 };
 
@@ -231,6 +251,7 @@ void timer_free(Timer& t) {
 void timer_reset(Timer& t) { for (int i = 0; i < GPR_T_COUNT; ++i) { t.used[i] = false; t.acc_ms[i] = 0.0; } }
 void timer_reset_predict(Timer& t) {
   for (int i = GPR_T_PRED_KSTAR; i <= GPR_T_PRED_ROWNORM; ++i) { t.used[i] = false; t.acc_ms[i] = 0.0; }
+  for (int i = GPR_T_SPLIT_BUILD; i <= GPR_T_SPLIT_D2H; ++i) { t.used[i] = false; t.acc_ms[i] = 0.0; }
 }
 // accumulate a previously recorded slot (needs the events to have completed)
 void timer_collect(Timer& t, int slot) {
@@ -478,14 +499,16 @@ int gpr_ctx_create(int device, gpr_ctx** out) {
   e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  live_add(ctx);
   if (e != cudaSuccess) { gpr_ctx_destroy(ctx); return fail_cuda(nullptr, e, "side queue", __LINE__); }
   *out = ctx;
   return GPR_OK;
 }
 
 int gpr_ctx_destroy(gpr_ctx* ctx) {
-  if (!ctx) return GPR_OK;
+  if (!ctx || !live_take(ctx)) return GPR_OK;
   cudaSetDevice(ctx->device);
+  while (!ctx->models.empty()) gpr_model_destroy(ctx->models.back());   // models the caller has not released yet
   if (ctx->main_stream) ctx->stream = ctx->main_stream;
   cudaStreamSynchronize(ctx->stream);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
@@ -509,7 +532,7 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
   if (!strcmp(name, "inplace_lauum")) { ctx->inplace_lauum = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "leaf_lookahead")) { ctx->leaf_lookahead = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "alpha_from_inverse")) { ctx->alpha_from_inverse = value ? 1 : 0; return GPR_OK; }
-  if (!strcmp(name, "gemm_cfg")) { gemm_forced_cfg() = (int)value; return GPR_OK; }   // 0 auto, 1..3: see dgemm_sm100.cuh
+  if (!strcmp(name, "gemm_cfg")) { ctx->gemm_cfg = (int)value; return GPR_OK; }   // 0 auto, 1..3: see dgemm_sm100.cuh
   return fail(ctx, GPR_ERR_ARG, std::string("unknown option ") + name);
 }
 
@@ -556,6 +579,8 @@ int gpr_model_create(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, int6
   const int64_t T = (N + GR_TILE - 1) / GR_TILE;
   m->gr_blocks = (int)std::min<int64_t>(T * (T + 1) / 2, (int64_t)ctx->sm_count * 4);
   A(&m->d_gpart, (size_t)m->gr_blocks * (m->P + 1));
+  live_add(m);
+  ctx->models.push_back(m);
   if (e != cudaSuccess) { gpr_model_destroy(m); return fail_cuda(ctx, e, "cudaMalloc(model)", __LINE__); }
   e = cudaMemcpyAsync(m->d_x, x, sizeof(double) * D * N, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_y, y, sizeof(double) * N * ny, cudaMemcpyHostToDevice, ctx->stream);
@@ -566,7 +591,11 @@ int gpr_model_create(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, int6
 }
 
 int gpr_model_destroy(gpr_model* m) {
-  if (!m) return GPR_OK;
+  if (!m || !live_take(m)) return GPR_OK;    // unknown / already released (e.g. by gpr_ctx_destroy): nothing to do
+  {
+    auto& v = m->ctx->models;
+    v.erase(std::remove(v.begin(), v.end(), m), v.end());
+  }
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   cudaFree(m->d_x); cudaFree(m->d_y); cudaFree(m->d_hp); cudaFree(m->d_U);
@@ -574,6 +603,7 @@ int gpr_model_destroy(gpr_model* m) {
   cudaFree(m->d_W);
   cudaFree(m->d_dinv); cudaFree(m->d_wt); cudaFree(m->d_scal); cudaFree(m->d_G); cudaFree(m->d_gpart);
   cudaFree(m->w_kxp.p); cudaFree(m->w_xp.p); cudaFree(m->w_part.p); cudaFree(m->w_mean.p); cudaFree(m->w_var.p);
+  cudaFree(m->w_sA.p); cudaFree(m->w_sBt.p); cudaFree(m->w_sC.p); cudaFree(m->w_sCu.p); cudaFree(m->w_sx.p); cudaFree(m->w_smu.p);
   timer_free(m->tm);
   delete m;
   return GPR_OK;
@@ -968,7 +998,7 @@ struct SplitBufs {
 // transposed tile assembly reads coalesced.  d_hp: device global hp.  x: D x N device.
 int split_build(gpr_ctx* ctx, const KSpec& spec, int D, const double* d_hp, const double* d_xe, int64_t ne,
                 const double* d_xq, int64_t nq, const double* d_x, int64_t N, int64_t Np, double eps, SplitBufs& sb,
-                bool want_C, const double* c_row_scale, bool want_Ct) {
+                bool want_B, bool want_C, const double* c_row_scale, bool want_Cu, bool want_Bt) {
   (void)eps;
   const int64_t nep = sb.nep, nqp = sb.nqp;
   int k = 0;
@@ -983,19 +1013,23 @@ int split_build(gpr_ctx* ctx, const KSpec& spec, int D, const double* d_hp, cons
     a.x1 = d_xe; a.x2 = d_xq; a.sigma_one = 1; a.row_scale = nullptr;
     int rc = launch_kbuild(ctx, DM_SPLIT_A, a); if (rc) return rc;
     // B[:, :, k] = exp(-|l (xe - xs)|^2), sigma := 1                    (split_kernel.jl:156)
-    a.out = sb.B + (int64_t)k * nep * Np; a.ldo = nep; a.R = ne; a.C = N; a.Rp = nep; a.Cp = Np;
-    a.x1 = d_xe; a.x2 = d_x; a.sigma_one = 1;
-    rc = launch_kbuild(ctx, DM_EUCLID, a); if (rc) return rc;
+    if (want_B) {
+      a.out = sb.B + (int64_t)k * nep * Np; a.ldo = nep; a.R = ne; a.C = N; a.Rp = nep; a.Cp = Np;
+      a.x1 = d_xe; a.x2 = d_x; a.sigma_one = 1;
+      rc = launch_kbuild(ctx, DM_EUCLID, a); if (rc) return rc;
+    }
     // C[:, :, k] = sigma^2 exp(+2 sum l^2 xs xq)                         (split_kernel.jl:157)
     if (want_C) {
       a.out = sb.C + (int64_t)k * Np * nqp; a.ldo = Np; a.R = N; a.C = nq; a.Rp = Np; a.Cp = nqp;
       a.x1 = d_x; a.x2 = d_xq; a.sigma_one = 0; a.row_scale = c_row_scale;
       rc = launch_kbuild(ctx, DM_SPLIT_C, a); if (rc) return rc;
     }
-    if (want_Ct) {
+    if (want_Cu) {
       a.out = sb.Cu + (int64_t)k * Np * nqp; a.ldo = Np; a.R = N; a.C = nq; a.Rp = Np; a.Cp = nqp;
       a.x1 = d_x; a.x2 = d_xq; a.sigma_one = 0; a.row_scale = nullptr;
       rc = launch_kbuild(ctx, DM_SPLIT_C, a); if (rc) return rc;
+    }
+    if (want_Bt) {
       a.out = sb.Bt + (int64_t)k * Np * nep; a.ldo = Np; a.R = N; a.C = ne; a.Rp = Np; a.Cp = nep;
       a.x1 = d_x; a.x2 = d_xe; a.sigma_one = 1; a.row_scale = nullptr;
       rc = launch_kbuild(ctx, DM_EUCLID, a); if (rc) return rc;   // B is symmetric in its two point sets: Bt[s, e] = B[e, s]
@@ -1033,7 +1067,7 @@ int gpr_split_kernel(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, cons
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_hp, hp, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream);
   rc = GPR_OK;
   if (e == cudaSuccess) {
-    rc = split_build(ctx, spec, D, d_hp, sb.d_xe, ne, sb.d_xq, nq, d_x, N, N, 0.0, sb, true, nullptr, false);
+    rc = split_build(ctx, spec, D, d_hp, sb.d_xe, ne, sb.d_xq, nq, d_x, N, N, 0.0, sb, true, true, nullptr, false, false);
     if (!rc) e = cudaMemcpyAsync(A, sb.A, sizeof(double) * ne * nq * nk, cudaMemcpyDeviceToHost, ctx->stream);
     if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(B, sb.B, sizeof(double) * ne * N * nk, cudaMemcpyDeviceToHost, ctx->stream);
     if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(C, sb.C, sizeof(double) * N * nq * nk, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1058,49 +1092,58 @@ int gpr_split_predict(gpr_model* m, const double* xe, int64_t ne, const double* 
   timer_reset_predict(m->tm);
   const int D = m->D, nk = m->nk;
   const int64_t N = m->N, Np = m->Np;
+  const bool want_var = var != nullptr && e_hi >= e_lo;
+  // Workspaces live in the model handle (the reference's GPRSplitPredictCache, src/caches/split_kernel.jl:1-30, is
+  // allocated once per cache as well): no cudaMalloc / cudaFree on the path after the first call of a given shape.
   SplitBufs sb; sb.nep = round_up(ne, 128); sb.nqp = round_up(nq, 128);
   const int64_t nep = sb.nep, nqp = sb.nqp;
-  double *d_bcw = nullptr, *d_mu = nullptr, *d_var = nullptr;
-  int rc = GPR_OK;
-  cudaError_t e = cudaMalloc(&sb.A, sizeof(double) * nep * nqp * nk);
-  if (e == cudaSuccess) e = cudaMalloc(&sb.B, sizeof(double) * nep * Np * nk);
-  if (e == cudaSuccess) e = cudaMalloc(&sb.C, sizeof(double) * Np * nqp * nk);
-  if (e == cudaSuccess && var) e = cudaMalloc(&sb.Cu, sizeof(double) * nqp * Np * nk);
-  if (e == cudaSuccess && var) e = cudaMalloc(&sb.Bt, sizeof(double) * nep * Np * nk);
-  if (e == cudaSuccess) e = cudaMalloc(&sb.d_xe, sizeof(double) * D * ne);
-  if (e == cudaSuccess) e = cudaMalloc(&sb.d_xq, sizeof(double) * D * nq);
-  if (e == cudaSuccess) e = cudaMalloc(&d_bcw, sizeof(double) * nep * nqp);
-  if (e == cudaSuccess) e = cudaMalloc(&d_mu, sizeof(double) * nep * nqp);
-  if (e == cudaSuccess && var) e = cudaMalloc(&d_var, sizeof(double) * nqp * std::max<int64_t>(1, ctx->predict_tile / nqp));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(sb.d_xe, xe, sizeof(double) * D * ne, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(sb.d_xq, xq, sizeof(double) * D * nq, cudaMemcpyHostToDevice, ctx->stream);
-  auto cleanup = [&]() { cudaStreamSynchronize(ctx->stream); sb.release(); cudaFree(d_bcw); cudaFree(d_mu); cudaFree(d_var); };
-  if (e != cudaSuccess) { cleanup(); return fail_cuda(ctx, e, "split predict alloc", __LINE__); }
-
-  // C is built pre-multiplied by wt:  Cw = Diagonal(wt) * C[:, :, k]   (split_predict.jl:13)
-  rc = split_build(ctx, m->spec, D, m->d_hp, sb.d_xe, ne, sb.d_xq, nq, m->d_x, N, Np, 0.0, sb, true, m->d_wt, var != nullptr);
-  if (rc) { cleanup(); return rc; }
+  int rc = ensure(ctx, m->w_sA, (size_t)nep * nqp * nk);
+  if (!rc) rc = ensure(ctx, m->w_sBt, (size_t)Np * nep * nk);
+  if (!rc) rc = ensure(ctx, m->w_sC, (size_t)Np * nqp * nk);
+  if (!rc && want_var) rc = ensure(ctx, m->w_sCu, (size_t)Np * nqp * nk);
+  if (!rc) rc = ensure(ctx, m->w_sx, (size_t)D * (ne + nq));
+  if (!rc) rc = ensure(ctx, m->w_smu, (size_t)nep * nqp);
+  if (rc) return rc;
+  sb.A = m->w_sA.p; sb.Bt = m->w_sBt.p; sb.C = m->w_sC.p; sb.Cu = want_var ? m->w_sCu.p : nullptr;
+  sb.d_xe = m->w_sx.p; sb.d_xq = m->w_sx.p + (size_t)D * ne;
+  double* d_mu = m->w_smu.p;
+  CK(cudaMemcpyAsync(sb.d_xe, xe, sizeof(double) * D * ne, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(sb.d_xq, xq, sizeof(double) * D * nq, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    // A, Bt = B^T (training index fastest), Cw = Diagonal(wt) * C[:, :, k] (split_predict.jl:13), and Cu for the variance
+    Scope s(m->tm, GPR_T_SPLIT_BUILD, ctx->stream);
+    rc = split_build(ctx, m->spec, D, m->d_hp, sb.d_xe, ne, sb.d_xq, nq, m->d_x, N, Np, 0.0, sb, false, true, m->d_wt, want_var, true);
+    if (rc) return rc;
+  }
   CudaBE be{ctx};
-  for (int k = 0; k < nk; ++k) {
-    // BCw = B[:, :, k] * Cw ; BCw .*= A[:, :, k] ; mu .+= BCw   (split_predict.jl:14-16)
-    be.gemm('N', 'N', nep, nqp, Np, 1.0, sb.B + (int64_t)k * nep * Np, nep, sb.C + (int64_t)k * Np * nqp, Np, 0.0, d_bcw, nep, 0);
-    hadamard_acc_kernel<<<(unsigned)std::min<int64_t>((nep * nqp + 255) / 256, 65535), 256, 0, ctx->stream>>>(
-        d_mu, nep, sb.A + (int64_t)k * nep * nqp, nep, d_bcw, nep, nep, nqp, k == 0);
-    ctx->launches++;
+  {
+    // mu = sum_k A_k .* (B_k Cw_k)  (split_predict.jl:14-16): per component ONE T,N product Bt_k^T Cw_k whose epilogue
+    // multiplies by A_k and accumulates into mu -- no BCw buffer, no separate Hadamard pass
+    Scope s(m->tm, GPR_T_SPLIT_GEMM, ctx->stream);
+    for (int k = 0; k < nk; ++k)
+      be.gemm_hadamard(nep, nqp, Np, sb.Bt + (int64_t)k * Np * nep, Np, sb.C + (int64_t)k * Np * nqp, Np,
+                       sb.A + (int64_t)k * nep * nqp, nep, k == 0 ? 0.0 : 1.0, d_mu, nep);
   }
   rc = check_pending(ctx, "split mean");
-  if (!rc) {
-    e = cudaMemcpy2DAsync(mean, sizeof(double) * ne, d_mu, sizeof(double) * nep, sizeof(double) * ne, nq, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) rc = fail_cuda(ctx, e, "split mean download", __LINE__);
+  if (rc) return rc;
+  {
+    Scope s(m->tm, GPR_T_SPLIT_D2H, ctx->stream);
+    CK(cudaMemcpy2DAsync(mean, sizeof(double) * ne, d_mu, sizeof(double) * nep, sizeof(double) * ne, nq, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  if (!rc && var) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (var) {
     const double prior = prior_diag(m);
     for (int64_t i = 0; i < ne * nq; ++i) var[i] = prior;   // fill!(Sigma.diag, sum sigma^2)  (src/predict.jl:55-58)
+  }
+  if (want_var) {
+    const double prior = prior_diag(m);
     const int64_t EB = std::max<int64_t>(1, ctx->predict_tile / nqp);
     rc = ensure(ctx, m->w_kxp, (size_t)EB * nqp * Np);
+    if (!rc) rc = ensure(ctx, m->w_var, (size_t)EB * nqp);
+    if (rc) return rc;
+    double* d_var = m->w_var.p;
     Blocked<CudaBE> blk(be, m->d_dinv);
-    for (int64_t e0 = e_lo - 1; !rc && e0 < e_hi; e0 += EB) {
+    for (int64_t e0 = e_lo - 1; e0 < e_hi; e0 += EB) {
       const int64_t ec = std::min<int64_t>(EB, e_hi - e0);
       const int64_t rows = ec * nqp;
       {
@@ -1119,17 +1162,14 @@ int gpr_split_predict(gpr_model* m, const double* xe, int64_t ne, const double* 
         colsumsq_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(m->w_kxp.p, Np, Np, rows, prior, d_var);
         ctx->launches++;
       }
-      if (rc) break;
       rc = check_pending(ctx, "split variance");
-      if (rc) break;
+      if (rc) return rc;
       // var[(e-1)*nq + q]  (q fastest within e: split_predict.jl:48)
-      e = cudaMemcpy2DAsync(var + e0 * nq, sizeof(double) * nq, d_var, sizeof(double) * nqp, sizeof(double) * nq, ec, cudaMemcpyDeviceToHost, ctx->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-      if (e != cudaSuccess) rc = fail_cuda(ctx, e, "split variance download", __LINE__);
+      CK(cudaMemcpy2DAsync(var + e0 * nq, sizeof(double) * nq, d_var, sizeof(double) * nqp, sizeof(double) * nq, ec, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
     }
   }
-  cleanup();
-  return rc;
+  return GPR_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -1271,7 +1311,8 @@ int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, d
     for (int r = 0; r < reps && e == cudaSuccess; ++r) {
       e = cudaMemcpyAsync(dC, dC0, sizeof(double) * ldc * N, cudaMemcpyDeviceToDevice, ctx->stream);
       cudaEventRecord(e0, ctx->stream);
-      if (e == cudaSuccess) e = launch_dgemm128(ctx->stream, transA, transB, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, flags);
+      if (e == cudaSuccess) e = launch_dgemm128(ctx->stream, transA, transB, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, flags, 1, 0, 0, 0,
+                                                        nullptr, 0, 0, ctx->gemm_cfg);
       ctx->launches++;
       cudaEventRecord(e1, ctx->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

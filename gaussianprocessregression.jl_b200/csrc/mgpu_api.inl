@@ -174,6 +174,7 @@ struct gpr_mgpu {
   //   trtri  mode 0: 3760   mode 1: 3779   mode 2: 3688     lauum  mode 0: 3735   mode 1: 3552   mode 2: 3140
   // (at 2 GPUs the three modes are within 0.5 % of each other), hence the defaults.
   int prefetch_trtri = 2, prefetch_lauum = 2;
+  struct gpr_mgpu_model* model = nullptr;   // the one live model of this context (released with it if still alive)
 };
 
 namespace {
@@ -610,6 +611,7 @@ int gpr_mgpu_create(int nranks, const int* devices, int64_t nb, gpr_mgpu** out) 
   if (nranks < 1 || nranks > MGPU_MAX_RANKS) return mfail(nullptr, GPR_ERR_ARG, "number of ranks must be in 1..16");
   if (nb < 128 || nb % 128) return mfail(nullptr, GPR_ERR_ARG, "panel width nb must be a positive multiple of 128");
   mg = new gpr_mgpu();
+  live_add(mg);
   mg->G = nranks; mg->nb = nb;
   mg->rk.resize(nranks);
   for (int r = 0; r < nranks; ++r) {
@@ -663,6 +665,7 @@ int gpr_dist_create(int device, int rank, int world, const void* id128, int64_t 
   NcclApi* api = nccl_api(err);
   if (!api) return mfail(nullptr, GPR_ERR_UNSUPPORTED, err);
   gpr_mgpu* mg = new gpr_mgpu();
+  live_add(mg);
   mg->G = world; mg->nb = nb; mg->transport = 2; mg->nccl = api;
   mg->prefetch_trtri = mg->prefetch_lauum = 0;
   mg->rk.resize(1);
@@ -688,7 +691,8 @@ int gpr_dist_create(int device, int rank, int world, const void* id128, int64_t 
 }
 
 int gpr_mgpu_destroy(gpr_mgpu* mg) {
-  if (!mg) return GPR_OK;
+  if (!mg || !live_take(mg)) return GPR_OK;
+  if (mg->model) { gpr_mgpu_model* mm = mg->model; mg->model = nullptr; if (live_take(mm)) delete mm; }
   mdense_free(mg);
   if (mg->comm && mg->nccl) { cudaSetDevice(mg->rk[0].ctx->device); mg->nccl->CommDestroy((ncclComm_t)mg->comm); mg->comm = nullptr; }
   for (auto& R : mg->rk) {
@@ -764,12 +768,15 @@ int gpr_mgpu_model_create(gpr_mgpu* mg, const int* comp_types, int ncomp, int D,
       return mfail(mg, e == cudaErrorMemoryAllocation ? GPR_ERR_MEMORY : GPR_ERR_CUDA, std::string("model allocation / upload: ") + cudaGetErrorString(e));
     }
   }
+  live_add(m);
+  mg->model = m;
   *out = m;
   return GPR_OK;
 }
 
 int gpr_mgpu_model_destroy(gpr_mgpu_model* m) {
-  if (!m) return GPR_OK;
+  if (!m || !live_take(m)) return GPR_OK;    // already released together with its gpr_mgpu
+  m->mg->model = nullptr;
   mdense_free(m->mg);
   delete m;
   return GPR_OK;

@@ -22,7 +22,7 @@ GPR_ERR_NOT_POSDEF = 1
 KERN_SE, KERN_NOISE, KERN_MATERN52 = 1, 2, 3
 FETCH_U, FETCH_ALPHA, FETCH_KINV, FETCH_WT = 0, 1, 2, 3
 T_NAMES = ["kbuild", "potrf", "potrs", "trtri", "lauum", "grad", "total", "pred_kstar", "pred_mean", "pred_trsm",
-           "pred_rownorm", "eval"]
+           "pred_rownorm", "eval", "split_build", "split_gemm", "split_d2h"]
 T_COUNT = 16
 
 _dp = C.POINTER(C.c_double)

@@ -77,6 +77,9 @@ extern "C" {
 #define GPR_T_PRED_TRSM 9
 #define GPR_T_PRED_ROWNORM 10
 #define GPR_T_EVAL 11        /* one whole gpr_nlml_grad call: hp upload .. F, G on the host side of the stream */
+#define GPR_T_SPLIT_BUILD 12 /* gpr_split_predict: A, B^T, Diagonal(wt) C (and C for the variance) builds */
+#define GPR_T_SPLIT_GEMM 13  /* gpr_split_predict: sum_k A_k .* (B_k Cw_k), fused epilogue */
+#define GPR_T_SPLIT_D2H 14   /* gpr_split_predict: mean tile to the caller's host buffer */
 #define GPR_T_COUNT 16
 
 typedef struct gpr_ctx gpr_ctx;

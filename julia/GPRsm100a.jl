@@ -1,7 +1,9 @@
 # GPRsm100a.jl -- Julia glue binding libgpr_sm100a.so (include/gpr_sm100a.h) into
-# srinix007/GaussianProcessRegression.jl.  SOURCE ONLY: no `julia` binary exists in the build image, so this
-# file has never been executed; the executed binding of the same C ABI is the ctypes layer
-# gaussianprocessregression.jl_b200/gpr_sm100a/_ffi.py, which mirrors it call for call.
+# srinix007/GaussianProcessRegression.jl.  EXPERIMENTAL, SOURCE ONLY: no `julia` binary exists in the build image, so
+# this file has never been executed (it is desk-checked against the reference's type definitions, see the notes at
+# each definition); the executed bindings of the same C ABI are the ctypes layer
+# gaussianprocessregression.jl_b200/gpr_sm100a/_ffi.py, which mirrors it call for call, and the plain-C caller
+# tests/cabi/test_cabi.c.
 #
 # Seam (SURVEY.md 8b): the reference's callers (train, update_sample!, cv_step!, predict*) only ever touch the
 # non-allocating, cache-based API.  New cache types hold an opaque model handle; the methods below overload
@@ -17,9 +19,10 @@ module GPRsm100a
 
 using GaussianProcessRegression
 using LinearAlgebra
+using Random
 import GaussianProcessRegression: update_cache!, loss, grad!, loss_grad!, log_loss_grad!, loss_cache, grad_cache,
     loss_grad_cache, predict_cache, predict_mean!, predict!, AbstractGPRModel, AbstractLossCache, AbstractGradCache,
-    AbstractPredictCache, MarginalLikelihood, SquaredExp, WhiteNoise, ComposedKernel, GPRModel, Cmap, get_sample, islog
+    AbstractPredictCache, AbstractKernel, MarginalLikelihood, SquaredExp, WhiteNoise, ComposedKernel, GPRModel, Cmap, get_sample
 
 const LIB = get(ENV, "GPR_SM100A_LIB", "libgpr_sm100a")
 const GPR_KERN_SE, GPR_KERN_NOISE = Cint(1), Cint(2)
@@ -47,13 +50,22 @@ end
 comp_types(::SquaredExp) = Cint[GPR_KERN_SE]
 comp_types(K::ComposedKernel) = Cint[k isa WhiteNoise ? GPR_KERN_NOISE : GPR_KERN_SE for k in K.kernels]
 
-"Wrapper that routes a GPRModel to the sm_100a caches (everything else is forwarded)."
-struct SM100{M<:GPRModel} <: AbstractGPRModel{Any,Float64,Vector{Float64},Matrix{Float64}}
+"""
+Wrapper that routes a GPRModel to the sm_100a caches (every field access is forwarded to the wrapped model).
+
+The supertype carries the wrapped model's own parameters: `AbstractGPRModel{K<:AbstractKernel,T,P<:AbstractArray{T},
+X<:AbstractArray{T}}` (src/models.jl:3-4) -- so the reference's trait dispatch works unaided on the wrapper:
+`islog(::MarginalLikelihood, ::AbstractGPRModel{<:SquaredExp})` and `islog(::MarginalLikelihood,
+md::AbstractGPRModel{<:ComposedKernel})` (src/cost.jl:4-8; the latter reads `md.covar.kernels`, forwarded below),
+`train(md::AbstractModel, ...)` (src/train.jl:9-12), `predict(md::AbstractGPRModel, xp)` (src/predict.jl:6-25).
+"""
+struct SM100{K<:AbstractKernel,T,P<:AbstractArray{T},X<:AbstractArray{T,2},M<:GPRModel{K,T,P,X}} <: AbstractGPRModel{K,T,P,X}
     md::M
 end
+SM100(md::GPRModel{K,T,P,X}) where {K,T,P,X} = SM100{K,T,P,X,typeof(md)}(md)
 Base.getproperty(s::SM100, f::Symbol) = f === :md ? getfield(s, :md) : getproperty(getfield(s, :md), f)
-GaussianProcessRegression.get_sample(s::SM100) = get_sample(s.md)
-GaussianProcessRegression.islog(c::MarginalLikelihood, s::SM100) = islog(c, s.md)
+Base.propertynames(s::SM100) = (:md, propertynames(getfield(s, :md))...)
+GaussianProcessRegression.get_sample(s::SM100) = get_sample(s.md)      # src/models.jl:39-45 is typed on GPRModel
 
 mutable struct Handle
     c::Ctx
@@ -62,13 +74,15 @@ end
 function Handle(md)
     c = ctx()
     t = comp_types(md.covar)
-    y = md.y isa Vector ? reshape(md.y, :, 1) : md.y
+    y = md.y isa AbstractVector ? reshape(md.y, :, 1) : md.y
     r = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:gpr_model_create, LIB), Cint,
         (Ptr{Cvoid}, Ptr{Cint}, Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Ref{Ptr{Cvoid}}),
         c.h, t, length(t), size(md.x, 1), size(md.x, 2), md.x, y, size(y, 2), md.train_axis, r)
     check(c, rc)
     h = Handle(c, r[])
+    # The Handle keeps its Ctx reachable, but at process exit finalizers run in no particular order: the library
+    # tolerates that (gpr_ctx_destroy releases the models it still owns; gpr_model_destroy on such a handle is a no-op).
     finalizer(x -> ccall((:gpr_model_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), h)
 end
 
@@ -137,6 +151,12 @@ end
 function predict!(μₚ, Σₚ::AbstractMatrix, md::SM100, xp::AbstractMatrix, pc::SM100PredictCache)
     rc = ccall((:gpr_predict, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
         pc.h.h, xp, size(xp, 2), xp === md.x, μₚ, C_NULL, Σₚ)
+    check(pc.h.c, rc)
+end
+function predict_mean!(μₚ, md::SM100, xeq::Cmap, pc::SM100SplitPredictCache)       # src/split_predict.jl:5-19
+    rc = ccall((:gpr_split_predict, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
+        pc.h.h, xeq.xe, size(xeq.xe, 2), xeq.xq, size(xeq.xq, 2), 1, 0, μₚ, C_NULL)
     check(pc.h.c, rc)
 end
 function predict!(μₚ, Σₚ::Diagonal, md::SM100, xeq::Cmap, pc::SM100SplitPredictCache)

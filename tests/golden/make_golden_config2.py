@@ -1,5 +1,6 @@
 """Oracle NLML + gradient for BASELINE.json config 2 (ARD SE + noise, N=8192, D=8, three hyper-parameter sets;
-SURVEY.md 8d).  Inputs are regenerated from the seed, only F and G are stored (config2_n8192.npz).
+SURVEY.md 8d) plus the "cond-limited" set D (plain SquaredExp(), jitter only, hyper-parameters of set A without the
+noise term).  Inputs are regenerated from the seed, only F and G are stored (config2_n8192.npz).
 Takes a few minutes of CPU:  python tests/golden/make_golden_config2.py"""
 import os
 import sys
@@ -31,4 +32,22 @@ if __name__ == "__main__":
         F, G = o.loss_grad(hp, md)
         out["F_" + name], out["G_" + name], out["hp_" + name] = F, G, hp
         print(name, F, np.linalg.norm(G), flush=True)
+    # set D: jitter-only SquaredExp(); cond(K) from lambda_max (power iteration) / lambda_min (inverse iteration)
+    hpD = sets["A"][:-1]
+    md = o.GPRModel(o.SE, hpD, x, y)
+    tc = o.MllGradCache(md)
+    F, G = o.loss_grad(hpD, md, tc)
+    v = np.ones(N) / np.sqrt(N)
+    K = o.kernel(o.SE, hpD, x)
+    for _ in range(50):
+        v = K @ v
+        lmax = np.linalg.norm(v)
+        v /= lmax
+    w = np.random.default_rng(0).standard_normal(N)
+    for _ in range(50):
+        w = tc.Kinv @ w
+        linv = np.linalg.norm(w)
+        w /= linv
+    out["F_D"], out["G_D"], out["hp_D"], out["cond_D"] = F, G, hpD, lmax * linv
+    print("D", F, np.linalg.norm(G), "cond", lmax * linv, flush=True)
     np.savez(os.path.join(HERE, "config2_n8192.npz"), **out)

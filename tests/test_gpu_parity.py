@@ -6,7 +6,8 @@ Tolerances (BASELINE.json north_star / SURVEY.md 8d): K entries rel 1e-10; NLML 
 rel 1e-8 (component error relative to max(|g_i|, 1e-8 |g|)); predictive mean rel 1e-8 (relative to
 max(|mu|, 1e-8 |y|_inf)); variance abs 1e-8 * sum sigma^2.  For jitter-only models (no WhiteNoise) the
 attainable agreement of two correct FP64 Choleskys is ~cond(K)*eps, so the tolerance is
-max(stated, 50*cond*eps) and the condition number is asserted to be the reason.
+max(stated, 10*cond*eps) (round 1 used 50x; the observed errors are 0.02-0.8 cond*eps, and
+tests/test_extended_precision.py referees both sides against a longdouble ground truth).
 """
 import glob
 import os
@@ -43,7 +44,7 @@ def case_cov(name):
 
 
 def ctol(stated, cond):
-    return max(stated, 50.0 * cond * EPS)
+    return max(stated, 10.0 * cond * EPS)
 
 
 def grad_err(G, Gref):
@@ -351,6 +352,101 @@ def test_config2_n8192_three_hp_sets(gpr):
         assert abs(F - Fo) <= TOL_F * abs(Fo), (name, F, Fo)
         assert grad_err(G, Go) <= TOL_G, (name, grad_err(G, Go))
     tc.close()
+
+
+def _load_module(name, fname):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(HERE, "golden", fname))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_config2_set_D_cond_limited(gpr):
+    """SURVEY 8d config 2, set D: plain SquaredExp() (jitter only) with the hyper-parameters of set A at N = 8192.
+    cond(K) ~ 1e11-1e12: the oracle value is reproduced to the cond * eps band, which is asserted as the reason."""
+    mg2 = _load_module("mg2", "make_golden_config2.py")
+    x, y, sets = mg2.inputs()
+    g = np.load(os.path.join(HERE, "golden", "config2_n8192.npz"))
+    if "F_D" not in g.files:
+        pytest.skip("config2_n8192.npz predates set D")
+    hp = sets["A"][:-1]
+    md = gpr.GPRModel(gpr.SquaredExp(), hp, x, y)
+    tc = gpr.MllGradCache(md)
+    G = np.empty(len(hp))
+    F = gpr.loss_grad_(gpr.MarginalLikelihood(), True, G, hp, md, tc)
+    tc.close()
+    cond = float(g["cond_D"])
+    relF, relG = abs(F - float(g["F_D"])) / abs(float(g["F_D"])), grad_err(G, g["G_D"])
+    print(f"\nconfig 2 set D: cond_est {cond:.2e}, cond*eps {cond * EPS:.1e}, relF {relF:.1e}, relG {relG:.1e}")
+    assert cond * EPS > TOL_F          # the condition number IS the reason the stated 1e-8 does not apply
+    assert relF <= ctol(TOL_F, cond) and relG <= ctol(TOL_G, cond)
+
+
+def test_config3_n32768_benchmarked_path_vs_oracle(gpr):
+    """BASELINE.json config 3 (3-ref) + config 4 at FULL size: the exact model bench.py times (N = 32768, D = 8, P = 19,
+    seed 3003) through gpr_nlml_grad / gpr_fetch / gpr_predict / gpr_split_predict against oracle values committed in
+    tests/golden/config3_n32768.npz (make_golden_config3.py; reference path src/cost.jl:96-127, src/predict.jl:29-95,
+    src/split_predict.jl:10-53).  This is the out-of-place trtri_t + lauum_oop_t + alpha-from-inverse path."""
+    path = os.path.join(HERE, "golden", "config3_n32768.npz")
+    if not os.path.exists(path):
+        pytest.skip("config3_n32768.npz not generated")
+    mg3 = _load_module("mg3", "make_golden_config3.py")
+    g = np.load(path)
+    x, y, hp = mg3.inputs()
+    xp, xe, xq, samp = mg3.test_inputs()
+    cov = gpr.SquaredExp() + gpr.SquaredExp() + gpr.WhiteNoise()
+    md = gpr.GPRModel(cov, hp, x, y)
+    ll = gpr.MarginalLikelihood()
+    tc = gpr.MllGradCache(md)
+    G = np.empty(len(hp))
+    F = gpr.loss_grad_(ll, True, G, hp, md, tc)
+    Gl = np.empty(len(hp))
+    Fl = gpr.log_loss_grad_(ll, True, Gl, np.log(hp), md, tc)
+    alpha = tc.alpha
+    tc.close()
+    relF, relG, relGl = abs(F - float(g["F"])) / abs(float(g["F"])), grad_err(G, g["G"]), grad_err(Gl, g["G_log"])
+    rela = np.abs(alpha - g["alpha"]).max() / np.abs(g["alpha"]).max()
+    print(f"\nconfig 3 (N=32768): cond_est {float(g['cond_est']):.2e}; relF {relF:.2e}, relG {relG:.2e}, relG_log {relGl:.2e}, alpha {rela:.2e}")
+    assert relF <= TOL_F and abs(Fl - float(g["F"])) <= TOL_F * abs(float(g["F"]))
+    assert relG <= TOL_G and relGl <= TOL_G
+    assert rela <= TOL_F
+    prior = float(hp[0] ** 2 + hp[9] ** 2 + hp[18] ** 2)
+    mu, Sd = gpr.predict(md, xp, diagonal_var=True)
+    e_mu, e_var = mean_err(mu, g["pred_mean"], y), np.abs(Sd.diag - g["pred_var"]).max() / prior
+    print(f"predict (4096 points): mean {e_mu:.2e}, var {e_var:.2e}")
+    assert e_mu <= TOL_MU and e_var <= TOL_VAR
+    nq = xq.shape[1]
+    smu, sS = gpr.predict(md, gpr.Cmap(np.add, xe, xq), diagonal_var=True)      # default var_range = 1:3
+    e_rows = mean_err(smu[:3, :], g["split_mean_rows"], y)
+    e_samp = mean_err(smu.reshape(-1, order="F")[samp], g["split_mean_sampled"], y)
+    e_svar = np.abs(sS.diag[:3 * nq] - g["split_var_rows"]).max() / prior
+    print(f"split predict (16.8 M points): mean rows {e_rows:.2e}, sampled {e_samp:.2e}, var rows 1:3 {e_svar:.2e}")
+    assert e_rows <= TOL_MU and e_samp <= TOL_MU and e_svar <= TOL_VAR
+    assert np.all(sS.diag[3 * nq:3 * nq + 64] == prior)                          # rows beyond var_range keep the prior
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+def test_config5_n16384_distributed_vs_oracle(gpr, G):
+    """SURVEY 8d config 5 parity: the block-cyclic distributed path (MultiGPUGradCache) at N = 16384, D = 16,
+    SquaredExp()+WhiteNoise(), G = 1, 2, 4, 8 ranks (cycled over the visible GPUs) against the committed oracle value
+    (tests/golden/config5_n16384.npz, make_golden_config5.py; reference path src/cost.jl:96-127)."""
+    path = os.path.join(HERE, "golden", "config5_n16384.npz")
+    if not os.path.exists(path):
+        pytest.skip("config5_n16384.npz not generated")
+    mg5 = _load_module("mg5", "make_golden_config5.py")
+    g = np.load(path)
+    x, y, hp = mg5.inputs()
+    md = gpr.GPRModel(gpr.SquaredExp() + gpr.WhiteNoise(), hp, x, y)
+    tc = gpr.MultiGPUGradCache(md, devices=_devices(G), nb=1024)
+    Gd = np.empty(len(hp))
+    F = gpr.loss_grad_(gpr.MarginalLikelihood(), True, Gd, hp, md, tc)
+    alpha = tc.alpha
+    tc.close()
+    relF, relG = abs(F - float(g["F"])) / abs(float(g["F"])), grad_err(Gd, g["G"])
+    rela = np.abs(alpha - g["alpha"]).max() / np.abs(g["alpha"]).max()
+    print(f"\nconfig 5 parity (N=16384, G={G}): relF {relF:.2e}, relG {relG:.2e}, alpha {rela:.2e}")
+    assert relF <= TOL_F and relG <= TOL_G and rela <= TOL_F
 
 
 def test_invariants_n16384(gpr):
