@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fastexp.cuh"
+
 namespace gpr {
 
 constexpr int KSPEC_MAXC = 8;
@@ -295,6 +297,8 @@ __global__ void __launch_bounds__(GR_THREADS) grad_reduce_kernel(const GradArgs 
   double* x2 = x1 + (size_t)D * GR_TILE;                   // D * 64
   double* al1 = x2 + (size_t)D * GR_TILE;                  // 64
   double* al2 = al1 + GR_TILE;                             // 64
+  double* etab = al2 + GR_TILE;                            // 32: 2^(j/32) (fastexp.cuh)
+  if (tid < 32) etab[tid] = kg_exp2_tab[tid];
   for (int s = 0; s <= P; ++s) acc[s * GR_THREADS + tid] = 0.0;
 
   const long long T = (a.N + GR_TILE - 1) / GR_TILE;
@@ -374,13 +378,13 @@ __global__ void __launch_bounds__(GR_THREADS) grad_reduce_kernel(const GradArgs 
           const long long r = r0 + tx + 16 * i, c = c0 + ty + 16 * j;
           double kc, kl;
           if (type == KT_SE) {
-            kc = sig2 * exp(-dist[i][j]);
+            kc = sig2 * exp_tab32(-dist[i][j], etab);
             if (r == c) kc += a.eps;        // dK/dsigma and dK/dl both use the jittered K (deriv_covar.jl:23,26)
             kl = kc;
           } else {
             const double rr = sqrt(dist[i][j]);
             const double s5r = 2.23606797749978969640917366873128 * rr;
-            const double e = exp(-s5r);
+            const double e = exp_tab32(-s5r, etab);
             kc = sig2 * (1.0 + s5r + (5.0 / 3.0) * dist[i][j]) * e;
             if (r == c) kc += a.eps;
             kl = (5.0 / 6.0) * sig2 * (1.0 + s5r) * e;

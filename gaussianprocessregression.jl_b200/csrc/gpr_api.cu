@@ -20,6 +20,8 @@
 #include "dist_blocked.hpp"
 #include "cov_kernels.cuh"
 #include "dgemm_sm100.cuh"
+#include "kbuild_tma.cuh"
+#include "dgemm_tma.cuh"
 #include "leaf_kernels.cuh"
 
 using namespace gpr;
@@ -56,6 +58,8 @@ struct gpr_ctx {
   int leaf_lookahead = 1;  // option "leaf_lookahead": factor the next diagonal leaf on the side queue (csrc/blocked.hpp)
   int alpha_from_inverse = 1;   // option "alpha_from_inverse": alpha = K^-1 y by a symmetric product on the gradient path
   int gemm_cfg = 0;             // option "gemm_cfg": forced tile configuration of dgemm128 (0 = automatic), per context
+  int gemm_tma = 1;             // option "gemm_tma": T,N products through the TMA-fed kernel (csrc/dgemm_tma.cuh)
+  int kbuild_gram = 1;          // option "kbuild_gram": TMA-fed Gram-form covariance build (csrc/kbuild_tma.cuh); 0 = direct-difference kernel
   std::vector<gpr_model*> models;   // live models of this context (released by gpr_ctx_destroy if the caller has not)
   long long launches = 0;
   long long* d_info = nullptr;
@@ -64,6 +68,7 @@ struct gpr_ctx {
   // launches currently go to and equals main_stream outside those drivers
   cudaStream_t main_stream = nullptr, side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};   // split predict: chunk-ready events for the overlapped download
 };
 
 namespace {
@@ -93,6 +98,13 @@ struct CudaBE {
     // grid.z is limited to 65535: split very large batches
     for (int64_t z0 = 0; z0 < batch; z0 += 32768) {
       const int64_t nb = std::min<int64_t>(32768, batch - z0);
+      if (ctx->gemm_tma && gemm_tma_supported(tA, tB, (int)M, (int)N, (int)K, A, B, C, flags, (int)nb, sA, sB)) {
+        // TMA-fed operand ring (csrc/dgemm_tma.cuh), T,N form
+        note(launch_dgemm128_tma(ctx->stream, (int)M, (int)N, (int)K, alpha, A + z0 * sA, lda, B + z0 * sB, ldb, beta, C + z0 * sC, ldc,
+                                 flags, (int)nb, sA, sB, sC));
+        ctx->launches++;
+        continue;
+      }
       note(launch_dgemm128(ctx->stream, tA, tB, (int)M, (int)N, (int)K, alpha, A + z0 * sA, lda, B + z0 * sB, ldb, beta,
                            C + z0 * sC, ldc, flags, (int)nb, sA, sB, sC, nullptr, 0, 0, ctx->gemm_cfg));
       ctx->launches++;
@@ -101,8 +113,11 @@ struct CudaBE {
   // C = (A^T B) .* E + beta C, T,N form with the Hadamard epilogue (split-predict mean)
   void gemm_hadamard(int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb,
                      const double* E, int64_t lde, double beta, double* C, int64_t ldc) {
-    note(launch_dgemm128(ctx->stream, 'T', 'N', (int)M, (int)N, (int)K, 1.0, A, lda, B, ldb, beta, C, ldc, 0, 1, 0, 0, 0, nullptr, 0, 0,
-                         0, E, lde));
+    if (ctx->gemm_tma && gemm_tma_supported('T', 'N', (int)M, (int)N, (int)K, A, B, C, 0, 1, 0, 0))
+      note(launch_dgemm128_tma(ctx->stream, (int)M, (int)N, (int)K, 1.0, A, lda, B, ldb, beta, C, ldc, 0, 1, 0, 0, 0, nullptr, 0, 0, E, lde));
+    else
+      note(launch_dgemm128(ctx->stream, 'T', 'N', (int)M, (int)N, (int)K, 1.0, A, lda, B, ldb, beta, C, ldc, 0, 1, 0, 0, 0, nullptr, 0, 0,
+                           0, E, lde));
     ctx->launches++;
   }
   void activate() { note(cudaSetDevice(ctx->device)); }
@@ -112,8 +127,12 @@ struct CudaBE {
   // tile-mapped GEMM of the block-cyclic multi-GPU drivers (csrc/dist_blocked.hpp)
   void gemm_map(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, const TileMap& map) {
-    note(launch_dgemm128(ctx->stream, tA, tB, (int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, 0, 0, 0,
-                         map.col_gtile, map.row_gtile0, map.k_gtile0, ctx->gemm_cfg));
+    if (ctx->gemm_tma && gemm_tma_supported(tA, tB, (int)M, (int)N, (int)K, A, B, C, flags, 1, 0, 0))
+      note(launch_dgemm128_tma(ctx->stream, (int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, 0, 0, 0, map.col_gtile,
+                               map.row_gtile0, map.k_gtile0));
+    else
+      note(launch_dgemm128(ctx->stream, tA, tB, (int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, 0, 0, 0,
+                           map.col_gtile, map.row_gtile0, map.k_gtile0, ctx->gemm_cfg));
     ctx->launches++;
   }
   void potrf_leaf(double* A, int64_t lda, double* dinv, int64_t goff) {
@@ -153,11 +172,15 @@ struct CudaBE {
 
 int setup_kernel_attributes(gpr_ctx* ctx) {
   CK(gemm_setup_attributes());
+  CK(gemm_tma_set_attr());
   CK(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM_BYTES));
   CK(cudaFuncSetAttribute(leaf_mv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_MV_SMEM_BYTES));
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_SPLIT_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_SPLIT_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(kbuild_gram_kernel<DM_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(kbuild_gram_kernel<DM_SPLIT_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(kbuild_gram_kernel<DM_SPLIT_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(grad_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(grad_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return GPR_OK;
@@ -182,10 +205,19 @@ int make_spec(gpr_ctx* ctx, const int* types, int ncomp, int D, KSpec* spec, int
   return GPR_OK;
 }
 
-// covariance build launcher
-int launch_kbuild(gpr_ctx* ctx, int mode, const KBuildArgs& a) {
+// covariance build launcher.  centre: D doubles on the device (Euclidean Gram form), skip_lower: single-GPU training build.
+int launch_kbuild(gpr_ctx* ctx, int mode, const KBuildArgs& a, const double* centre = nullptr, int skip_lower = 0) {
   int nk = 0;
   for (int c = 0; c < a.spec.ncomp; ++c) if (a.spec.type[c] != KT_NOISE) nk++;
+  if (ctx->kbuild_gram && kgram_supported(a, nk)) {
+    // TMA-fed Gram form on the DMMA pipe (csrc/kbuild_tma.cuh)
+    KGramArgs ka{a, centre, skip_lower};
+    cudaError_t e = mode == DM_EUCLID ? kgram_launch<DM_EUCLID>(ctx->stream, ka, nk)
+                  : mode == DM_SPLIT_A ? kgram_launch<DM_SPLIT_A>(ctx->stream, ka, nk) : kgram_launch<DM_SPLIT_C>(ctx->stream, ka, nk);
+    ctx->launches++;
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "kbuild_gram launch", __LINE__);
+    return GPR_OK;
+  }
   size_t smem = (size_t)2 * nk * a.D * KB_TILE * sizeof(double);
   if (a.mean_w || a.mean_w_rows) smem = std::max(smem, (size_t)16 * (KB_TILE + 1) * sizeof(double));
   if (smem > 200 * 1024) return fail(ctx, GPR_ERR_UNSUPPORTED, "covariance build: (#components x D) too large for shared memory");
@@ -197,6 +229,13 @@ int launch_kbuild(gpr_ctx* ctx, int mode, const KBuildArgs& a) {
   ctx->launches++;
   CK(cudaGetLastError());
   return GPR_OK;
+}
+
+// rows of the output one CTA of the covariance build covers (the fused-mean partials are per CTA row tile)
+int kbuild_rows_per_cta(gpr_ctx* ctx, const KBuildArgs& a) {
+  int nk = 0;
+  for (int c = 0; c < a.spec.ncomp; ++c) if (a.spec.type[c] != KT_NOISE) nk++;
+  return (ctx->kbuild_gram && kgram_supported(a, nk)) ? KG_BM : KB_TILE;
 }
 
 struct DevBuf {
@@ -301,7 +340,7 @@ int factor_and_solve(gpr_model* m, const double* hp, double eps, int64_t* info, 
     // (kchol_base keeps K there, test/test_loss.jl:46), so it is filled in lazily by gpr_fetch(U)
     a.zero_lower = 1;
     m->lower_is_k = false;
-    int rc = launch_kbuild(ctx, DM_EUCLID, a);
+    int rc = launch_kbuild(ctx, DM_EUCLID, a, m->d_x, 1);
     if (rc) return rc;
   }
   CudaBE be{ctx};
@@ -431,7 +470,7 @@ int compute_grad(gpr_model* m, int log_scale, double* G_host) {
     a.Kinv = m->d_Kinv; a.ld = m->Np; a.alpha = m->d_wt + (int64_t)(m->train_axis - 1) * m->Np;
     a.x = m->d_x; a.D = m->D; a.N = m->N; a.hp = m->d_hp; a.spec = m->spec; a.P = m->P; a.eps = m->eps_host;
     a.partial = m->d_gpart;
-    const size_t smem = ((size_t)(m->P + 1) * GR_THREADS + 2 * (size_t)m->D * GR_TILE + 2 * GR_TILE) * sizeof(double);
+    const size_t smem = ((size_t)(m->P + 1) * GR_THREADS + 2 * (size_t)m->D * GR_TILE + 2 * GR_TILE + 32) * sizeof(double);
     grad_reduce_kernel<false><<<m->gr_blocks, GR_THREADS, smem, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -514,6 +553,7 @@ int gpr_ctx_destroy(gpr_ctx* ctx) {
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  for (auto& ev : ctx->ev_chunk) if (ev) cudaEventDestroy(ev);
   cudaFree(ctx->d_info);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -532,6 +572,8 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
   if (!strcmp(name, "inplace_lauum")) { ctx->inplace_lauum = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "leaf_lookahead")) { ctx->leaf_lookahead = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "alpha_from_inverse")) { ctx->alpha_from_inverse = value ? 1 : 0; return GPR_OK; }
+  if (!strcmp(name, "gemm_tma")) { ctx->gemm_tma = value ? 1 : 0; return GPR_OK; }
+  if (!strcmp(name, "kbuild_gram")) { ctx->kbuild_gram = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "gemm_cfg")) { ctx->gemm_cfg = (int)value; return GPR_OK; }   // 0 auto, 1..3: see dgemm_sm100.cuh
   return fail(ctx, GPR_ERR_ARG, std::string("unknown option ") + name);
 }
@@ -654,7 +696,7 @@ int gpr_kernel(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, const doub
     a.out = d_out; a.ldo = N; a.R = N; a.C = M; a.Rp = N; a.Cp = M;
     a.x1 = d_x; a.x2 = same_x ? d_x : d_xp; a.D = D; a.hp = d_hp; a.spec = spec;
     a.eps = eps; a.same = same_x; a.add_noise = add_noise; a.pad_identity = 0; a.sigma_one = 0; a.row_scale = nullptr; a.diag_shift = 0;
-    rc = launch_kbuild(ctx, DM_EUCLID, a);
+    rc = launch_kbuild(ctx, DM_EUCLID, a, d_x);
     if (!rc) e = cudaMemcpyAsync(out, d_out, sizeof(double) * N * M, cudaMemcpyDeviceToHost, ctx->stream);
     if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   }
@@ -850,14 +892,15 @@ int predict_tile(gpr_model* m, const double* d_xp, int64_t mt, int64_t m0, int s
     // vector y: mu = K* wt is reduced inside the build (per-CTA partial sums over 64 training points), so the tile is
     // not re-read; without a variance request it is not even stored
     const bool fuse_mean = (m->ny == 1);
-    const int64_t nrow_tiles = (Np + KB_TILE - 1) / KB_TILE;
+    const int64_t rt = kbuild_rows_per_cta(ctx, a);
+    const int64_t nrow_tiles = (Np + rt - 1) / rt;
     if (fuse_mean) {
       rc = ensure(ctx, m->w_part, (size_t)nrow_tiles * mtp);
       if (rc) return rc;
       a.mean_w_rows = m->d_wt; a.mean_partial = m->w_part.p;
       if (!d_var) a.out = nullptr;
     }
-    rc = launch_kbuild(ctx, DM_EUCLID, a);
+    rc = launch_kbuild(ctx, DM_EUCLID, a, m->d_x);
     if (rc) return rc;
     if (fuse_mean) {
       rowreduce_finalize_kernel<<<(unsigned)((mt + 255) / 256), 256, 0, ctx->stream>>>(m->w_part.p, (int)nrow_tiles, mtp, mt, 0.0, 1.0, d_mean);
@@ -939,7 +982,7 @@ int gpr_predict(gpr_model* m, const double* xp, int64_t M, int same_x, double* m
       a.out = d_sigma; a.ldo = Mp; a.R = M; a.C = M; a.Rp = Mp; a.Cp = Mp;
       a.x1 = m->w_xp.p; a.x2 = m->w_xp.p; a.D = D; a.hp = m->d_hp; a.spec = m->spec;
       a.eps = m->eps_host; a.same = 1; a.add_noise = 1; a.pad_identity = 0; a.sigma_one = 0; a.row_scale = nullptr; a.diag_shift = 0;
-      rc = launch_kbuild(ctx, DM_EUCLID, a);   // kernel!(Sigma, covar, params, xp)  (src/predict.jl:45)
+      rc = launch_kbuild(ctx, DM_EUCLID, a, m->w_xp.p);   // kernel!(Sigma, covar, params, xp)  (src/predict.jl:45)
     }
     if (!rc) {
       CudaBE be{ctx};
@@ -1016,7 +1059,7 @@ int split_build(gpr_ctx* ctx, const KSpec& spec, int D, const double* d_hp, cons
     if (want_B) {
       a.out = sb.B + (int64_t)k * nep * Np; a.ldo = nep; a.R = ne; a.C = N; a.Rp = nep; a.Cp = Np;
       a.x1 = d_xe; a.x2 = d_x; a.sigma_one = 1;
-      rc = launch_kbuild(ctx, DM_EUCLID, a); if (rc) return rc;
+      rc = launch_kbuild(ctx, DM_EUCLID, a, d_x); if (rc) return rc;
     }
     // C[:, :, k] = sigma^2 exp(+2 sum l^2 xs xq)                         (split_kernel.jl:157)
     if (want_C) {
@@ -1032,7 +1075,7 @@ int split_build(gpr_ctx* ctx, const KSpec& spec, int D, const double* d_hp, cons
     if (want_Bt) {
       a.out = sb.Bt + (int64_t)k * Np * nep; a.ldo = Np; a.R = N; a.C = ne; a.Rp = Np; a.Cp = nep;
       a.x1 = d_x; a.x2 = d_xe; a.sigma_one = 1; a.row_scale = nullptr;
-      rc = launch_kbuild(ctx, DM_EUCLID, a); if (rc) return rc;   // B is symmetric in its two point sets: Bt[s, e] = B[e, s]
+      rc = launch_kbuild(ctx, DM_EUCLID, a, d_x); if (rc) return rc;   // B is symmetric in its two point sets: Bt[s, e] = B[e, s]
     }
     ++k;
   }
@@ -1116,20 +1159,37 @@ int gpr_split_predict(gpr_model* m, const double* xe, int64_t ne, const double* 
     if (rc) return rc;
   }
   CudaBE be{ctx};
+  // mu = sum_k A_k .* (B_k Cw_k)  (split_predict.jl:14-16): per component ONE T,N product Bt_k^T Cw_k whose epilogue
+  // multiplies by A_k and accumulates into mu -- no BCw buffer, no separate Hadamard pass.  The columns are processed in
+  // up to 4 chunks: the device -> host copy of a finished chunk (pageable destination: ~4 GB/s, it would otherwise add
+  // 35 ms to a 64 ms product at ne = nq = 4096) runs on the side queue while the next chunk is being computed.
+  const int nch = (nqp >= 1024 && (nqp / 128) % 4 == 0) ? 4 : 1;
+  const int64_t cw = nqp / nch;
+  if (!ctx->ev_chunk[0])
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
   {
-    // mu = sum_k A_k .* (B_k Cw_k)  (split_predict.jl:14-16): per component ONE T,N product Bt_k^T Cw_k whose epilogue
-    // multiplies by A_k and accumulates into mu -- no BCw buffer, no separate Hadamard pass
     Scope s(m->tm, GPR_T_SPLIT_GEMM, ctx->stream);
-    for (int k = 0; k < nk; ++k)
-      be.gemm_hadamard(nep, nqp, Np, sb.Bt + (int64_t)k * Np * nep, Np, sb.C + (int64_t)k * Np * nqp, Np,
-                       sb.A + (int64_t)k * nep * nqp, nep, k == 0 ? 0.0 : 1.0, d_mu, nep);
+    for (int ch = 0; ch < nch; ++ch) {
+      const int64_t q0 = ch * cw;
+      for (int k = 0; k < nk; ++k)
+        be.gemm_hadamard(nep, cw, Np, sb.Bt + (int64_t)k * Np * nep, Np, sb.C + (int64_t)k * Np * nqp + q0 * Np, Np,
+                         sb.A + (int64_t)k * nep * nqp + q0 * nep, nep, k == 0 ? 0.0 : 1.0, d_mu + q0 * nep, nep);
+      CK(cudaEventRecord(ctx->ev_chunk[ch], ctx->stream));
+    }
   }
   rc = check_pending(ctx, "split mean");
   if (rc) return rc;
   {
-    Scope s(m->tm, GPR_T_SPLIT_D2H, ctx->stream);
-    CK(cudaMemcpy2DAsync(mean, sizeof(double) * ne, d_mu, sizeof(double) * nep, sizeof(double) * ne, nq, cudaMemcpyDeviceToHost, ctx->stream));
+    Scope s(m->tm, GPR_T_SPLIT_D2H, ctx->side_stream);
+    for (int ch = 0; ch < nch; ++ch) {
+      const int64_t q0 = ch * cw, qn = std::min<int64_t>(cw, nq - q0);
+      if (qn <= 0) break;
+      CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_chunk[ch], 0));
+      CK(cudaMemcpy2DAsync(mean + q0 * ne, sizeof(double) * ne, d_mu + q0 * nep, sizeof(double) * nep, sizeof(double) * ne, qn,
+                           cudaMemcpyDeviceToHost, ctx->side_stream));
+    }
   }
+  CK(cudaStreamSynchronize(ctx->side_stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (var) {
     const double prior = prior_diag(m);
@@ -1260,7 +1320,7 @@ int gpr_sample_mvn(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, const 
     a.out = d_S; a.ldo = Np; a.R = N; a.C = N; a.Rp = Np; a.Cp = Np;
     a.x1 = d_x; a.x2 = d_x; a.D = D; a.hp = d_hp; a.spec = spec;
     a.eps = 1e-8; a.same = 1; a.add_noise = 1; a.pad_identity = 1; a.zero_lower = 1; a.all_shift = shift;   // kernel(cov, theta, x): src/distributions.jl:43
-    rc = launch_kbuild(ctx, DM_EUCLID, a);
+    rc = launch_kbuild(ctx, DM_EUCLID, a, d_x);
     if (!rc) {
       CudaBE be{ctx};
       Blocked<CudaBE> blk(be, d_dinv);
@@ -1311,8 +1371,13 @@ int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, d
     for (int r = 0; r < reps && e == cudaSuccess; ++r) {
       e = cudaMemcpyAsync(dC, dC0, sizeof(double) * ldc * N, cudaMemcpyDeviceToDevice, ctx->stream);
       cudaEventRecord(e0, ctx->stream);
-      if (e == cudaSuccess) e = launch_dgemm128(ctx->stream, transA, transB, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, flags, 1, 0, 0, 0,
-                                                        nullptr, 0, 0, ctx->gemm_cfg);
+      if (e == cudaSuccess) {
+        if (ctx->gemm_tma && gemm_tma_supported(transA, transB, M, N, K, dA, dB, dC, flags, 1, 0, 0))
+          e = launch_dgemm128_tma(ctx->stream, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, flags, 1, 0, 0, 0);
+        else
+          e = launch_dgemm128(ctx->stream, transA, transB, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, flags, 1, 0, 0, 0,
+                              nullptr, 0, 0, ctx->gemm_cfg);
+      }
       ctx->launches++;
       cudaEventRecord(e1, ctx->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

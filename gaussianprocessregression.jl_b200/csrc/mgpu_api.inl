@@ -712,6 +712,10 @@ int gpr_mgpu_destroy(gpr_mgpu* mg) {
 int gpr_mgpu_set_option(gpr_mgpu* mg, const char* name, int64_t value) {
   if (!mg || !name) return GPR_ERR_ARG;
   if (value < 0 || value > 2) return mfail(mg, GPR_ERR_ARG, "option value must be 0, 1 or 2");
+  if (!strcmp(name, "gemm_tma") || !strcmp(name, "kbuild_gram")) {   // forwarded to every rank's context
+    for (auto& R : mg->rk) if (R.ctx) gpr_ctx_set_option(R.ctx, name, value);
+    return GPR_OK;
+  }
   if (!strcmp(name, "transport")) {
     if (mg->transport == 2 || value == 2) return mfail(mg, GPR_ERR_ARG, "transport 2 (NCCL, one process per rank) is chosen by gpr_dist_create only");
     if (mg->rk[0].L) return mfail(mg, GPR_ERR_STATE, "set the transport before creating a model");
@@ -828,7 +832,7 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
       a.x1 = R.x; a.x2 = R.x + (cvalid > 0 ? J * nb * m->D : 0); a.D = m->D; a.hp = R.hp; a.spec = m->spec;
       a.eps = eps; a.same = 1; a.add_noise = 1; a.pad_identity = 1; a.sigma_one = 0; a.row_scale = nullptr;
       a.diag_shift = J * nb; a.zero_lower = 1;
-      int rc = launch_kbuild(ctx, DM_EUCLID, a);
+      int rc = launch_kbuild(ctx, DM_EUCLID, a, R.x);
       if (rc) return mfail(mg, rc, ctx->err);
     }
     if (r == lay.y_owner()) {
@@ -927,7 +931,7 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
       GradArgs a{};
       a.Kinv = R.L; a.ld = ld; a.alpha = R.alpha; a.x = R.x; a.D = m->D; a.N = N; a.hp = R.hp; a.spec = m->spec; a.P = P;
       a.eps = eps; a.partial = R.gpart; a.G = Gn; a.rank = r; a.nbt = (int)(nb / GR_TILE); a.lcol_tiles = lay.nloc(r) * (nb / GR_TILE);
-      const size_t smem = ((size_t)(P + 1) * GR_THREADS + 2 * (size_t)m->D * GR_TILE + 2 * GR_TILE) * sizeof(double);
+      const size_t smem = ((size_t)(P + 1) * GR_THREADS + 2 * (size_t)m->D * GR_TILE + 2 * GR_TILE + 32) * sizeof(double);
       grad_reduce_kernel<true><<<R.gr_blocks, GR_THREADS, smem, ctx->stream>>>(a);
       ctx->launches++;
       MCK(cudaGetLastError());

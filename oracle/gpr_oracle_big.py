@@ -332,7 +332,8 @@ def reference_shaped_eval(cov, log_hp, x, y, eps=1e-8, ws=None):
                     np.multiply(row, -2.0 * h[li], out=row)
                     np.multiply(Kc[:, j], row, out=dK[:, j])
             np.dot(dK, alpha, out=tt)                                          # mul!(tt, dK, alpha)   dgemv
-            G[off[c] + li] = -0.5 * (float(np.dot(tt, alpha)) - float(np.vdot(Ki, dK)))
+            # dot(K^-1, dK): ddot over the N^2 entries (both Fortran ordered: the flat views alias the buffers)
+            G[off[c] + li] = -0.5 * (float(np.dot(tt, alpha)) - float(np.dot(Ki.reshape(-1, order="F"), dK.reshape(-1, order="F"))))
     st["gradient"] = time.perf_counter() - t0
     G *= hp                                                                    # cost.jl:65
     F = 0.5 * (float(np.dot(y, alpha)) + 2.0 * float(np.sum(np.log(np.diag(U)))) + N * math.log(2.0 * math.pi))

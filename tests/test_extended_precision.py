@@ -86,7 +86,7 @@ def test_gpu_against_extended_precision(gpr, name):
         ctx.set_option("alpha_from_inverse", route)
         mh = _ffi.ModelHandle(ctx, types, x.shape[0], np.asfortranarray(x), y)
         F, G = mh.nlml_grad(hp)
-        alpha, Kinv = mh.fetch("alpha"), mh.fetch("Kinv")
+        alpha, Kinv = mh.fetch(_ffi.FETCH_ALPHA), mh.fetch(_ffi.FETCH_KINV)
         mu, var, _ = mh.predict(np.asfortranarray(xt), want_var=True)
         e = errors(F, G, alpha, Kinv, mu.reshape(-1), var, t, y, prior)
         res[route] = (e, F, G, alpha)

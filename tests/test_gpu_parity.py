@@ -187,6 +187,36 @@ def test_covariance_reference_suite(gpr, n, dim):
     assert gpr.grad(cov, 4, hp7, x2).lam == pytest.approx(2 * hs[1][0])
 
 
+@pytest.mark.parametrize("dim,shift,scale", [(2, 0.0, 40.0), (8, 1000.0, 1.0), (4, 0.0, 6.0), (16, -50.0, 2.0)])
+def test_gram_form_and_table_exp_accuracy(gpr, ctx, dim, shift, scale):
+    """The TMA-fed Gram-form build (csrc/kbuild_tma.cuh: d = |a|^2 + |b|^2 - 2 a.b on the DMMA pipe, centred; table-driven
+    exp, csrc/fastexp.cuh) against the oracle's direct difference + libm exp (src/covariance.jl:72-95) where they are most
+    exposed: distances up to the underflow threshold of exp (K entries down to 1e-300), inputs far from the origin
+    (cancellation in the Gram form), and against the direct-difference kernel of the library itself (option
+    kbuild_gram = 0).  Tolerance: the stated 1e-10 relative on every K entry that is not subnormal."""
+    rng = np.random.default_rng(dim)
+    n, m = 300, 200
+    x, xp = shift + scale * rng.random((dim, n)), shift + scale * rng.random((dim, m))
+    SE, WN = gpr.SquaredExp(), gpr.WhiteNoise()
+    hp = np.concatenate([[1.3], 0.5 + rng.random(dim), [0.7], 0.2 + rng.random(dim), [0.1]])
+    cov, cov_o = SE + SE + WN, (o.SE, o.SE, o.NOISE)
+    Kref, Kcref = o.kernel(cov_o, hp, x), o.kernel(cov_o, hp, x, xp)
+    for flag in (1, 0):
+        ctx.set_option("kbuild_gram", flag)
+        try:
+            Ks, Kc = gpr.kernel(cov, hp, x), gpr.kernel(cov, hp, x, xp)
+        finally:
+            ctx.set_option("kbuild_gram", 1)
+        for got, ref in ((Ks, Kref), (Kc, Kcref)):
+            big = ref > 1e-300
+            err = np.abs(got[big] / ref[big] - 1).max()
+            print(f"\nD={dim} shift={shift} scale={scale} gram={flag}: max rel err {err:.2e} over {big.sum()} entries, min K {ref[big].min():.1e}")
+            assert err < TOL_K
+            assert np.all(np.abs(got[~big]) <= 1e-299)
+        assert np.array_equal(Ks, Ks.T)                      # symmetric to the last bit
+        assert np.all(np.diag(Ks) == np.diag(Kref))           # d_ii = 0 exactly -> sigma^2 (+ eps, + noise) exactly
+
+
 @pytest.mark.parametrize("n,dim,ny", [(10, 2, 1), (20, 5, 1), (100, 2, 1), (100, 5, 5), (300, 3, 10)])
 def test_loss_reference_suite(gpr, n, dim, ny):
     """test/test_loss.jl:21-97"""
@@ -329,6 +359,59 @@ def test_train_matches_oracle_trajectory(gpr):
     np.testing.assert_allclose(hp_gpu, np.exp(res_o.x), rtol=1e-6)
     assert res.fun == pytest.approx(res_o.fun, rel=1e-9)
     assert 0.05 < hp_gpu[2] < 0.2          # recovers the noise level 0.1
+
+
+def test_tma_fed_gemm_matches_ldgsts_gemm(gpr):
+    """csrc/dgemm_tma.cuh (operand ring filled by cp.async.bulk.tensor + mbarriers, swizzled fragment loads) against
+    numpy and against the LDGSTS kernel: plain, accumulate (beta), upper-only and the triangular K-from-N product, and a
+    whole factor + inverse with the option on (every T,N product of potrf / trtri_t / lauum_oop_t, incl. batched levels)."""
+    from gpr_sm100a import _ffi
+    rng = np.random.default_rng(12)
+    ctx = gpr.Context(0)
+    try:
+        for (M, N, K, flags, beta) in ((128, 64 * 2, 16, 0, 0.0), (256, 384, 48, 0, 0.0), (512, 256, 1040, 0, 0.5), (384, 384, 384, 1, 1.0),
+                                       (512, 512, 512, 3, 0.0), (1024, 1152, 2048, 0, -1.0)):
+            A = np.asfortranarray(rng.standard_normal((K, M)))
+            B = np.asfortranarray(rng.standard_normal((K, N)))
+            C0 = np.asfortranarray(rng.standard_normal((M, N)))
+            outs = []
+            for tma in (0, 1):
+                ctx.set_option("gemm_tma", tma)
+                C, _ = _ffi.dbg_dgemm(ctx, "T", "N", 0.75, A, B, beta, C0, flags=flags)
+                outs.append(C)
+            ref = 0.75 * (A.T @ B) + beta * C0
+            if flags & 2:      # K-from-N: tile column block J contracts over k >= 128 J only
+                ref = beta * C0.copy()
+                for J in range(N // 128):
+                    ref[:, 128 * J:128 * (J + 1)] += 0.75 * (A[128 * J:, :].T @ B[128 * J:, 128 * J:128 * (J + 1)])
+            mask = np.ones((M, N), dtype=bool)
+            if flags & 1:
+                mask = np.triu(mask)
+            assert np.array_equal(outs[0][mask], outs[1][mask]), (M, N, K, flags)          # same arithmetic order -> same bits
+            assert np.abs(outs[1] - ref)[mask].max() <= 1e-12 * max(1.0, np.abs(ref).max()) * K ** 0.5
+            if flags & 1:
+                assert np.array_equal(outs[1][~mask], C0[~mask])                            # below the diagonal untouched
+        n = 1536
+        X = rng.standard_normal((n, n))
+        Kmat = X @ X.T / n + np.eye(n)
+        res = []
+        for tma in (0, 1):
+            ctx.set_option("gemm_tma", tma)
+            res.append(_ffi.dbg_factor(ctx, Kmat.copy(order="F"), mode=3)[0])
+        assert np.array_equal(np.triu(res[0]), np.triu(res[1]))
+        assert np.abs(np.triu(res[1]) - np.triu(np.linalg.inv(Kmat))).max() <= 1e-11 * np.abs(np.linalg.inv(Kmat)).max()
+        # tile-mapped forms (block-cyclic multi-GPU drivers) and the Hadamard epilogue (split-predict mean): TMA on vs off
+        mats = []
+        for tma in (0, 1):
+            mc = _ffi.MultiContext([0, 0, 0], nb=256)
+            mc.set_option("gemm_tma", tma)
+            A, Y, _ = mc.dbg_factor(np.triu(Kmat), rng.standard_normal((n, 2)) * 0 + 1.0, 2)
+            mc.close()
+            mats.append((A, Y))
+        assert np.array_equal(mats[0][0], mats[1][0]) and np.array_equal(mats[0][1], mats[1][1])
+    finally:
+        ctx.set_option("gemm_tma", 1)
+        ctx.close()
 
 
 # ------------------------------------------------------------------ (4) larger sizes: oracle where it is cheap, else invariants
