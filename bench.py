@@ -525,9 +525,11 @@ def run_gpu(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dist = None
+    cpu_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")     # host-side barrier: an NCCL barrier would spin on the waiting ranks' SMs
 
     def barrier():
         if dist is not None:
@@ -617,9 +619,11 @@ def run_gpu(args, rank, world, local_rank):
             # peer-memory reads / copy-engine transfers over NVLink, next-step panels prefetched on a side queue) -- the
             # transport a single-process Julia host would use; rank 0 runs it, the other ranks wait
             single = None
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)              # every rank has released its GPU memory and is idle
             if rank == 0:
                 single = config5_single_process(_ffi, world, n_override=args.config5_n)
-            dist.barrier()
+            dist.barrier(group=cpu_group)              # the waiting ranks block on the host, their GPUs stay free
             sharded["config5_single_process"] = single
         if args.config5_base and world == 1:
             sharded["config5_base_1gpu_n131072"] = config5_distributed(torch, dist, _ffi, rank, world, local_rank, n_override=131072)

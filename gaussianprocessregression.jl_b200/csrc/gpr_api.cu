@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -22,6 +23,7 @@
 #include "dgemm_sm100.cuh"
 #include "kbuild_tma.cuh"
 #include "dgemm_tma.cuh"
+#include "ozaki_i8.cuh"
 #include "leaf_kernels.cuh"
 
 using namespace gpr;
@@ -58,6 +60,14 @@ struct gpr_ctx {
   int leaf_lookahead = 1;  // option "leaf_lookahead": factor the next diagonal leaf on the side queue (csrc/blocked.hpp)
   int alpha_from_inverse = 1;   // option "alpha_from_inverse": alpha = K^-1 y by a symmetric product on the gradient path
   int gemm_cfg = 0;             // option "gemm_cfg": forced tile configuration of dgemm128 (0 = automatic), per context
+  int ozaki = 0;                // option "ozaki": number of 7-bit digits S (0 = off, 6 / 7 / 8) of the INT8-tensor-core FP64 product
+                                // (csrc/ozaki_i8.cuh) used for large T,N products; "ozaki_min": smallest M, N, K routed there
+  int64_t ozaki_min = 1024;
+  int64_t ozaki_panel = 4096;   // option "ozaki_panel": k-panel of the W^T W product (own digit scales per panel)
+  int oz_mask = 11, oz_cur = 8;   // option "ozaki_phases": bit 0 potrf, 1 trtri, 2 lauum (W^T W), 3 everything else (prediction solves).
+                                  // Default without W^T W: its operand columns span many orders of magnitude and one power-of-two scale per
+                                  // column costs the gradient three digits (1e-7 vs the oracle against 6e-11), profiles/README.md
+  void* oz_ws = nullptr; size_t oz_ws_bytes = 0;
   int gemm_tma = 1;             // option "gemm_tma": T,N products through the TMA-fed kernel (csrc/dgemm_tma.cuh)
   int kbuild_gram = 1;          // option "kbuild_gram": TMA-fed Gram-form covariance build (csrc/kbuild_tma.cuh); 0 = direct-difference kernel
   std::vector<gpr_model*> models;   // live models of this context (released by gpr_ctx_destroy if the caller has not)
@@ -92,10 +102,54 @@ int fail_cuda(gpr_ctx* ctx, cudaError_t e, const char* what, int line) {
 struct CudaBE {
   gpr_ctx* ctx;
   void note(cudaError_t e) { if (e != cudaSuccess && ctx->pending == cudaSuccess) ctx->pending = e; }
+  bool ozaki_eligible(char tA, char tB, int64_t M, int64_t N, int64_t K, const double* A, const double* B, const double* C, int flags,
+                      int64_t batch) const {
+    if (!ctx->ozaki || ctx->stream != ctx->main_stream || !(ctx->oz_mask & ctx->oz_cur)) return false;
+    if (tA != 'T' || tB != 'N') return false;
+    if (flags & ~(BLK_UPPER_ONLY | BLK_K_FROM_N | BLK_SKIP_TILE00)) return false;
+    if ((const double*)C == A || (const double*)C == B) return false;
+    if (batch < 1 || batch > 16) return false;
+    const int64_t mn = ctx->ozaki_min;
+    return M >= mn && N >= mn && K >= mn && K <= 32768 && (M % 128) == 0 && (N % 128) == 0 && (K % 128) == 0;
+  }
   void gemm(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
             const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int64_t batch = 1,
             int64_t sA = 0, int64_t sB = 0, int64_t sC = 0) {
     // grid.z is limited to 65535: split very large batches
+    if (ozaki_eligible(tA, tB, M, N, K, A, B, C, flags, batch)) {
+      // large T,N product: INT8 tensor cores (csrc/ozaki_i8.cuh), one launch per batch member
+      const size_t need = oz_workspace_bytes((int)std::max(M, N), (int)N, (int)K, ctx->ozaki);
+      if (need > ctx->oz_ws_bytes) {
+        cudaStreamSynchronize(ctx->main_stream);
+        cudaFree(ctx->oz_ws); ctx->oz_ws = nullptr; ctx->oz_ws_bytes = 0;
+        if (cudaMalloc(&ctx->oz_ws, need) == cudaSuccess) ctx->oz_ws_bytes = need; else cudaGetLastError();
+      }
+      if (ctx->oz_ws_bytes >= need && batch == 1 && flags == (BLK_UPPER_ONLY | BLK_K_FROM_N) && A == B && lda == ldb && M == N && N == K &&
+          K > ctx->ozaki_panel) {
+        // W^T W of the inverse (lauum_oop_t): the columns of the triangular factor span many orders of magnitude (O(1/sigma_n)
+        // next to the diagonal, tiny far from it), and the digit planes of a column share ONE power-of-two scale.  Summing the
+        // product over k-panels, each with its own column scales, keeps the error relative to the panel-local magnitudes
+        // (measured on the benchmark model: gradient error vs the oracle 1.1e-7 with one scale per column -> see profiles/).
+        // The last panel touches every column and initialises C (beta), the earlier ones accumulate into their leading block.
+        const int64_t P = ctx->ozaki_panel;
+        for (int64_t p1 = K; p1 > 0; p1 -= P) {
+          const int64_t p0 = std::max<int64_t>(0, p1 - P);
+          const int64_t cols = std::min<int64_t>(N, p1);
+          note(launch_ozaki_dgemm(ctx->stream, (int)cols, (int)cols, (int)(p1 - p0), ctx->ozaki, alpha, A + p0, lda, B + p0, ldb,
+                                  p1 == K ? beta : 1.0, C, ldc, flags, ctx->oz_ws, (int)p0));
+          ctx->launches += 2;
+        }
+        return;
+      }
+      if (ctx->oz_ws_bytes >= need) {
+        for (int64_t z = 0; z < batch; ++z) {
+          note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, ctx->ozaki, alpha, A + z * sA, lda, B + z * sB, ldb, beta, C + z * sC, ldc,
+                                  flags, ctx->oz_ws));
+          ctx->launches += 3;
+        }
+        return;
+      }
+    }
     for (int64_t z0 = 0; z0 < batch; z0 += 32768) {
       const int64_t nb = std::min<int64_t>(32768, batch - z0);
       if (ctx->gemm_tma && gemm_tma_supported(tA, tB, (int)M, (int)N, (int)K, A, B, C, flags, (int)nb, sA, sB)) {
@@ -173,6 +227,7 @@ struct CudaBE {
 int setup_kernel_attributes(gpr_ctx* ctx) {
   CK(gemm_setup_attributes());
   CK(gemm_tma_set_attr());
+  CK(oz_set_attr());
   CK(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM_BYTES));
   CK(cudaFuncSetAttribute(leaf_mv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_MV_SMEM_BYTES));
   CK(cudaFuncSetAttribute(kbuild_kernel<DM_EUCLID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -348,7 +403,9 @@ int factor_and_solve(gpr_model* m, const double* hp, double eps, int64_t* info, 
   blk.leaf_lookahead = ctx->leaf_lookahead != 0;
   {
     Scope s(m->tm, GPR_T_POTRF, ctx->stream);
+    ctx->oz_cur = 1;
     blk.potrf(m->d_U, Np, Np, 0);
+    ctx->oz_cur = 8;
   }
   {
     Scope s(m->tm, GPR_T_POTRS, ctx->stream);
@@ -406,11 +463,14 @@ int form_inverse(gpr_model* m) {
   if (m->d_W) {
     {
       Scope s(m->tm, GPR_T_TRTRI, ctx->stream);
+      ctx->oz_cur = 2;
       blk.trtri_t(m->d_U, Np, m->d_W, Np, Np, 0);      // lower(W) = U^-T, all products in the T,N form
     }
     {
       Scope s(m->tm, GPR_T_LAUUM, ctx->stream);
+      ctx->oz_cur = 4;
       blk.lauum_oop_t(m->d_W, Np, Np, m->d_Kinv, Np);  // K^-1 = (U^-T)^T U^-T
+      ctx->oz_cur = 8;
     }
   } else {
     {
@@ -535,6 +595,12 @@ int gpr_ctx_create(int device, gpr_ctx** out) {
   int rc = setup_kernel_attributes(ctx);
   if (rc) { g_create_error = ctx->err; cudaFree(ctx->d_info); cudaStreamDestroy(ctx->stream); delete ctx; return rc; }
   ctx->main_stream = ctx->stream;
+  if (const char* ev = getenv("GPR_OZAKI")) {   // run an unmodified caller (the parity suite) with the INT8-tensor-core product
+    const int v = atoi(ev);
+    if (v == 0 || v == 6 || v == 7 || v == 8) ctx->ozaki = v;
+  }
+  if (const char* ev = getenv("GPR_OZAKI_MIN")) ctx->ozaki_min = std::max<int64_t>(128, atoll(ev));
+  if (const char* ev = getenv("GPR_OZAKI_PHASES")) ctx->oz_mask = atoi(ev) & 15;
   e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
@@ -554,6 +620,7 @@ int gpr_ctx_destroy(gpr_ctx* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (auto& ev : ctx->ev_chunk) if (ev) cudaEventDestroy(ev);
+  cudaFree(ctx->oz_ws);
   cudaFree(ctx->d_info);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -573,6 +640,13 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
   if (!strcmp(name, "leaf_lookahead")) { ctx->leaf_lookahead = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "alpha_from_inverse")) { ctx->alpha_from_inverse = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "gemm_tma")) { ctx->gemm_tma = value ? 1 : 0; return GPR_OK; }
+  if (!strcmp(name, "ozaki")) {
+    if (value != 0 && value != 6 && value != 7 && value != 8) return fail(ctx, GPR_ERR_ARG, "ozaki: number of digits must be 0 (off), 6, 7 or 8");
+    ctx->ozaki = (int)value; return GPR_OK;
+  }
+  if (!strcmp(name, "ozaki_panel")) { ctx->ozaki_panel = std::max<int64_t>(128, (value / 128) * 128); return GPR_OK; }
+  if (!strcmp(name, "ozaki_phases")) { ctx->oz_mask = (int)value & 15; return GPR_OK; }
+  if (!strcmp(name, "ozaki_min")) { ctx->ozaki_min = std::max<int64_t>(128, value); return GPR_OK; }
   if (!strcmp(name, "kbuild_gram")) { ctx->kbuild_gram = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "gemm_cfg")) { ctx->gemm_cfg = (int)value; return GPR_OK; }   // 0 auto, 1..3: see dgemm_sm100.cuh
   return fail(ctx, GPR_ERR_ARG, std::string("unknown option ") + name);
@@ -1391,6 +1465,47 @@ int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, d
   if (ms) *ms = total / (float)(reps > 1 ? reps - 1 : 1);
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dC0);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "gpr_dbg_dgemm", __LINE__);
+  return GPR_OK;
+}
+
+int gpr_dbg_ozaki_dgemm(gpr_ctx* ctx, int M, int N, int K, int S, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                        double beta, double* C, int64_t ldc, int flags, int reps, double* ms) {
+  if (!ctx) return GPR_ERR_ARG;
+  if (!A || !B || !C) return fail(ctx, GPR_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  double *dA = nullptr, *dB = nullptr, *dC = nullptr, *dC0 = nullptr;
+  void* ws = nullptr;
+  cudaError_t e = cudaMalloc(&dA, sizeof(double) * lda * M);
+  if (e == cudaSuccess) e = cudaMalloc(&dB, sizeof(double) * ldb * N);
+  if (e == cudaSuccess) e = cudaMalloc(&dC, sizeof(double) * ldc * N);
+  if (e == cudaSuccess) e = cudaMalloc(&dC0, sizeof(double) * ldc * N);
+  if (e == cudaSuccess) e = cudaMalloc(&ws, oz_workspace_bytes(M, N, K, S));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dA, A, sizeof(double) * lda * M, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dB, B, sizeof(double) * ldb * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dC0, C, sizeof(double) * ldc * N, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  float total = 0.f;
+  if (e == cudaSuccess) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (reps < 1) reps = 1;
+    for (int r = 0; r < reps && e == cudaSuccess; ++r) {
+      e = cudaMemcpyAsync(dC, dC0, sizeof(double) * ldc * N, cudaMemcpyDeviceToDevice, ctx->stream);
+      cudaEventRecord(e0, ctx->stream);
+      if (e == cudaSuccess) e = launch_ozaki_dgemm(ctx->stream, M, N, K, S, alpha, dA, lda, dB, ldb, beta, dC, ldc, flags, ws);
+      ctx->launches += 3;
+      cudaEventRecord(e1, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      float t = 0.f; cudaEventElapsedTime(&t, e0, e1);
+      if (r > 0 || reps == 1) total += t;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(C, dC, sizeof(double) * ldc * N, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (ms) *ms = total / (float)(reps > 1 ? reps - 1 : 1);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dC0); cudaFree(ws);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "gpr_dbg_ozaki_dgemm", __LINE__);
   return GPR_OK;
 }
 

@@ -1,0 +1,341 @@
+// FP64 GEMM through the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators): an Ozaki-type splitting.
+//
+//   C (M x N) = alpha * op(A)^T-form product + beta * C,   op(A)[m, k] = A[k + m lda], op(B)[k, n] = B[k + n ldb]   (T,N form)
+//
+// sm_100a has no FP64 kind of tcgen05.mma; its FP64 tensor path is the warp-level DMMA (35.9 TFLOP/s measured with the
+// TMA-fed kernel of dgemm_tma.cuh = the roof of that pipe).  The INT8 path of the 5th-generation tensor cores is
+// ~120x wider, so an FP64 product can be bought with several exact integer products:
+//
+//   1. every row of op(A) (a vector over k) is scaled by a power of two 2^-ea so that |a| < 1/2 and cut into S signed
+//      7-bit digits:  a 2^-ea = sum_{s=1..S} A_s 2^(-7 s),  A_s in [-64, 64]  (round-to-nearest digits, exact);
+//      likewise every column of op(B).  (oz_slice_kernel)
+//   2. the integer products A_s B_t^T are EXACT in int32 for K <= 2^17 (|sum| <= K 2^12), and all pairs of one
+//      diagonal d = s + t share the weight 2^(-7 d), so a diagonal accumulates in ONE int32 TMEM accumulator over all
+//      its pairs and the whole contraction (K <= 32768: |sum| <= 8 K 2^12 = 2^30);
+//   3. pairs with s + t > S + 1 are dropped (their weight is below 2^(-7 (S + 2)), i.e. 2^-70 for S = 8 relative to the
+//      row / column maxima): S (S + 1) / 2 = 36 integer products for S = 8;
+//   4. the epilogue converts the S diagonals to FP64, weights and sums them (smallest first), rescales by
+//      2^(ea_m + eb_n) and applies alpha / beta.
+// Error: every retained term is exact, so the result differs from the exact product by the dropped digits only:
+// <= ~2^-56 max_k|a_mk| max_k|b_kn| K for S = 8 -- a NORM-wise FP64 product (measured against DGEMM in
+// tests/test_gpu_parity.py::test_ozaki_*).  It is not component-wise accurate for rows with a huge dynamic range.
+//
+// Kernel (oz_gemm_kernel): one CTA per 128 x 64 tile of C, 6 warps:
+//   warp 0  TMA producer: per k-tile of 64 (bytes) ONE cp.async.bulk.tensor.3d per operand brings all S digit planes
+//           (A: S x 128 x 64 B, B: S x 64 x 64 B, SWIZZLE_64B) into one of two 96 KB stages;
+//   warp 1  one thread issues tcgen05.mma.cta_group::1.kind::i8 (M 128, N 64, K 32) for the 36 (s, t) pairs x 2 k-steps
+//           of the stage into accumulator (s + t - 2) of the 8 x 64-column TMEM accumulators (all 512 columns), then
+//           tcgen05.commit releases the stage; after the last k-tile a commit signals the epilogue;
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 16 columns) per diagonal, int32 -> FP64, weighted sum, scaling, C update.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dgemm_tma.cuh"
+#include "kbuild_tma.cuh"
+
+namespace gpr {
+
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64;        // tile of C; k-tile in int8 elements (= bytes)
+constexpr int OZ_SMAX = 8;
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_STAGES = 2;
+
+__host__ __device__ inline size_t oz_stage_bytes(int S) { return (size_t)S * (OZ_BM + OZ_BN) * OZ_BK; }
+__host__ __device__ inline size_t oz_smem_bytes(int S) { return OZ_STAGES * oz_stage_bytes(S) + 1024 + 128; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// digit planes: X is K x R column major (column r = the vector over k of row / column r of the product operand).
+// planes[s][r][k] (int8, k contiguous, row pitch Kp), scale[r] = 2^e_r (so that x = scale * sum_s planes_s 2^(-7 s)).
+// One warp per column r.
+// ---------------------------------------------------------------------------------------------------------------
+// kfrom != 0: column r only holds data for k >= 128 * (r / 128) (lower-triangular operand of a K-from-N product, whose
+// upper part may be uninitialised): everything above is treated as zero.
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ X, long long ldx, int K, int R, int S, int8_t* __restrict__ planes,
+                                                       long long Kp, long long Rp, double* __restrict__ scale, int kfrom, int k_off) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= Rp) return;
+  if (r >= R) {   // padding rows: zero digits
+    for (int s = 0; s < S; ++s)
+      for (long long k = lane * 16; k < Kp; k += 32 * 16) *reinterpret_cast<int4*>(planes + ((long long)s * Rp + r) * Kp + k) = make_int4(0, 0, 0, 0);
+    if (lane == 0) scale[r] = 1.0;
+    return;
+  }
+  const double* col = X + (long long)r * ldx;
+  const int kbeg = kfrom ? max(0, 128 * (r / 128) - k_off) : 0;   // k_off: global row of this operand's first k (k-panel of a larger product)
+  double amax = 0.0;
+  for (int k = kbeg + lane; k < K; k += 32) amax = fmax(amax, fabs(col[k]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  int e = 0;
+  if (amax > 0.0) { (void)frexp(amax, &e); e += 1; }          // amax = m 2^(e-1), m in [0.5, 1)  ->  |x| 2^-e < 1/2
+  const double down = ldexp(1.0, -e);
+  if (lane == 0) scale[r] = ldexp(1.0, e);
+  // 16 consecutive k per lane and step: one 16-byte store per plane
+  for (long long k0 = lane * 16; k0 < Kp; k0 += 32 * 16) {
+    double rem[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) rem[i] = (k0 + i < K && k0 + i >= kbeg) ? col[k0 + i] * down : 0.0;
+    for (int s = 0; s < S; ++s) {
+      unsigned w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const double sc = rem[i] * 128.0;                     // exact
+        const double q = rint(sc);                            // |q| <= 64
+        rem[i] = sc - q;                                      // exact, |rem| <= 1/2
+        w[i >> 2] |= ((unsigned)(int)q & 0xffu) << (8 * (i & 3));
+      }
+      *reinterpret_cast<uint4*>(planes + ((long long)s * Rp + r) * Kp + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tcgen05 primitives
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier wait that gives up (trap -> launch failure) instead of hanging the device if a barrier is never completed
+__device__ __forceinline__ void oz_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] B[smem]^T, int8 x int8 -> int32, M = 128, N = 64, K = 32
+__device__ __forceinline__ void tc_mma_i8(unsigned tmem_d, uint64_t desc_a, uint64_t desc_b, unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// K-major operand tile with 64-byte rows, SWIZZLE_64B: 8-row groups are 512 bytes apart
+__device__ __forceinline__ uint64_t oz_smem_desc(const void* p) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  uint64_t d = 0;
+  d |= (uint64_t)((a & 0x3FFFFu) >> 4);          // start address, bits [0, 14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset: 1 (16 B) for swizzled K-major layouts (CUTLASS make_umma_desc)
+  d |= (uint64_t)(512u >> 4) << 32;              // stride byte offset: 8 rows x 64 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;                        // layout type: SWIZZLE_64B
+  return d;
+}
+// instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128
+constexpr unsigned OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(OZ_BN >> 3) << 17) | ((unsigned)(OZ_BM >> 4) << 24);
+
+struct OzParams {
+  int M, N, K, S;
+  double alpha, beta;
+  double* C; long long ldc;
+  const double* scaleA; const double* scaleB;    // 2^ea (M), 2^eb (N)
+  int flags;                                     // GEMM_UPPER_ONLY, GEMM_K_FROM_N (same meaning as dgemm_sm100.cuh)
+  int k_off;                                     // K-from-N: global index of the first contraction row (k-panels of one product)
+};
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+  extern __shared__ unsigned char oz_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
+  const size_t stage_bytes = oz_stage_bytes(S);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * stage_bytes);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* tfull = empty + OZ_STAGES;
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(tfull + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const int blk_n = (tile_n * OZ_BN) >> 7;
+  if ((p.flags & 1) && tile_m > blk_n) return;                       // GEMM_UPPER_ONLY: whole CTA leaves before any allocation
+  if ((p.flags & 64) && tile_m == 0 && blk_n == 0) return;           // GEMM_SKIP_TILE00
+  const int kt0 = (p.flags & 2) ? max(0, blk_n * 128 - p.k_off) / OZ_BK : 0;   // GEMM_K_FROM_N
+  const int KT = p.K / OZ_BK - kt0;
+  const int m0 = tile_m * OZ_BM, n0 = tile_n * OZ_BN;
+
+  if (tid == 0) {
+    for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {   // TMEM: all 512 columns (8 diagonals x 64)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"((unsigned)__cvta_generic_to_shared(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt & 1;
+        if (kt >= OZ_STAGES) oz_wait(&empty[s], (unsigned)(((kt >> 1) - 1) & 1));
+        unsigned char* st = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full[s], (unsigned)stage_bytes);
+        tma_load_3d(st, &mapA, &full[s], (kt0 + kt) * OZ_BK, m0, 0);                               // S x 128 x 64 B
+        tma_load_3d(st + (size_t)S * OZ_BM * OZ_BK, &mapB, &full[s], (kt0 + kt) * OZ_BK, n0, 0);   // S x  64 x 64 B
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // One thread issues every MMA of the CTA, so its instruction stream is the critical path: S is a template parameter,
+    // the pair loops are fully unrolled and a descriptor is the stage's base descriptor plus a compile-time constant.
+    if (lane == 0) {
+      uint64_t baseA[OZ_STAGES], baseB[OZ_STAGES];
+#pragma unroll
+      for (int s = 0; s < OZ_STAGES; ++s) {
+        baseA[s] = oz_smem_desc(smem + (size_t)s * stage_bytes);
+        baseB[s] = oz_smem_desc(smem + (size_t)s * stage_bytes + (size_t)S * OZ_BM * OZ_BK);
+      }
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt & 1;
+        oz_wait(&full[s], (unsigned)((kt >> 1) & 1));
+        tc_fence_after();
+        const uint64_t dA = s ? baseA[1] : baseA[0], dB = s ? baseB[1] : baseB[0];
+        const unsigned acc_first = (kt > 0) ? 1u : 0u;
+#pragma unroll
+        for (int t = 1; t <= S; ++t) {
+#pragma unroll
+          for (int sa = 1; sa + t <= S + 1; ++sa) {
+#pragma unroll
+            for (int kk = 0; kk < OZ_BK / 32; ++kk) {   // 32-byte k-steps inside the 64-byte swizzle atom: +2 in the 16-byte address field
+              const uint64_t da = dA + (uint64_t)(((sa - 1) * OZ_BM * OZ_BK + 32 * kk) >> 4);
+              const uint64_t db = dB + (uint64_t)(((t - 1) * OZ_BN * OZ_BK + 32 * kk) >> 4);
+              tc_mma_i8(tmem_base + (unsigned)((sa + t - 2) * OZ_BN), da, db, OZ_IDESC, (kk > 0 || t > 1) ? 1u : acc_first);
+            }
+          }
+        }
+        tc_commit(&empty[s]);              // the stage may be refilled once these MMAs have read it
+      }
+      tc_commit(tfull);                    // all accumulators complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lanes 32 (warp % 4) .. +31 = rows of the tile =====
+    oz_wait(tfull, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const unsigned lane_addr = tmem_base + ((unsigned)(32 * q) << 16);
+    const bool diag_tile = (p.flags & 1) && (tile_m == blk_n);
+    const int coff = n0 & 127;
+    const double sa = p.scaleA[m0 + row] * p.alpha;
+    double* Crow = p.C + (long long)(m0 + row) + (long long)n0 * p.ldc;
+    for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+      double acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+      for (int d = S + 1; d >= 2; --d) {   // smallest weights first
+        unsigned v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(lane_addr + (unsigned)((d - 2) * OZ_BN + c0)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        const double w = __hiloint2double((1023 - 7 * d) << 20, 0);   // 2^(-7 d)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fma((double)(int)v[j], w, acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = c0 + j;
+        if (diag_tile && row > col + coff) continue;
+        double* cp = Crow + (long long)col * p.ldc;
+        const double r = acc[j] * sa * p.scaleB[n0 + col];
+        *cp = (p.beta != 0.0) ? fma(p.beta, *cp, r) : r;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- host side ----
+// int8 digit planes as a 3-D tensor {k (bytes), rows, plane}: box = {64, box_rows, S}, SWIZZLE_64B
+inline bool oz_make_map(CUtensorMap* map, const int8_t* base, uint64_t Kp, uint64_t Rp, int S, uint32_t box_rows) {
+  PFN_encodeTiled fn = tma_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {Kp, Rp, (cuuint64_t)S};
+  cuuint64_t strides[2] = {Kp, Kp * Rp};
+  cuuint32_t box[3] = {OZ_BK, box_rows, (cuuint32_t)S};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int S> inline cudaError_t oz_set_attr_s() {
+  return cudaFuncSetAttribute(oz_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(S));
+}
+inline cudaError_t oz_set_attr() {
+  cudaError_t e = oz_set_attr_s<8>();
+  if (e == cudaSuccess) e = oz_set_attr_s<7>();
+  if (e == cudaSuccess) e = oz_set_attr_s<6>();
+  if (e == cudaSuccess) e = oz_set_attr_s<2>();
+  return e;
+}
+
+// workspace (bytes) for the digit planes and scales of one product
+inline size_t oz_workspace_bytes(int M, int N, int K, int S) {
+  const size_t Kp = ((size_t)K + 127) / 128 * 128;
+  return (size_t)S * Kp * ((size_t)M + (size_t)N) + sizeof(double) * ((size_t)M + (size_t)N) + 512;
+}
+
+// C = alpha A^T B + beta C through the int8 tensor cores.  M % 128 == 0, N % 128 == 0, K % 128 == 0, K <= 32768.
+// flags: GEMM_UPPER_ONLY (1), GEMM_K_FROM_N (2), GEMM_SKIP_TILE00 (64).  When A and B are the same matrix (the symmetric
+// updates of potrf and the W^T W product of the inverse) its digit planes are formed once and shared.
+inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int S, double alpha, const double* A, long long lda, const double* B,
+                                      long long ldb, double beta, double* C, long long ldc, int flags, void* workspace, int k_off = 0) {
+  if ((S != 8 && S != 7 && S != 6 && S != 2) || (M % OZ_BM) || (N % 128) || (K % 128) || K > 32768) return cudaErrorInvalidValue;
+  const size_t Kp = (size_t)K;
+  const bool shared = (A == B && lda == ldb);
+  const int kfrom = (flags & 2) ? 1 : 0;
+  const int Ra = shared ? (M > N ? M : N) : M;
+  int8_t* pa = reinterpret_cast<int8_t*>(workspace);
+  int8_t* pb = shared ? pa : pa + (size_t)S * Kp * Ra;
+  const int Rb = shared ? Ra : N;
+  double* sa = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(pa + (size_t)S * Kp * ((size_t)Ra + (shared ? 0 : (size_t)N))) + 255) & ~(uintptr_t)255);
+  double* sb = shared ? sa : sa + Ra;
+  // K-from-N: only op(B)'s columns are triangular (column block J holds data for k >= 128 J).  With shared planes (W^T W, upper
+  // only) the rows I <= J of op(A)^T are the same columns, read for k >= 128 J >= 128 I only, so the same masking is exact.
+  oz_slice_kernel<<<(Ra + 7) / 8, 256, 0, st>>>(A, lda, K, Ra, S, pa, (long long)Kp, Ra, sa, shared ? kfrom : 0, k_off);
+  if (!shared) oz_slice_kernel<<<(N + 7) / 8, 256, 0, st>>>(B, ldb, K, N, S, pb, (long long)Kp, N, sb, kfrom, k_off);
+  CUtensorMap mA, mB;
+  if (!oz_make_map(&mA, pa, Kp, (uint64_t)Ra, S, OZ_BM) || !oz_make_map(&mB, pb, Kp, (uint64_t)Rb, S, OZ_BN)) return cudaErrorInvalidValue;
+  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags, k_off};
+  dim3 grid(M / OZ_BM, N / OZ_BN);
+  if (S == 8) oz_gemm_kernel<8><<<grid, OZ_THREADS, oz_smem_bytes(8), st>>>(p, mA, mB);
+  else if (S == 7) oz_gemm_kernel<7><<<grid, OZ_THREADS, oz_smem_bytes(7), st>>>(p, mA, mB);
+  else if (S == 6) oz_gemm_kernel<6><<<grid, OZ_THREADS, oz_smem_bytes(6), st>>>(p, mA, mB);
+  else oz_gemm_kernel<2><<<grid, OZ_THREADS, oz_smem_bytes(2), st>>>(p, mA, mB);
+  return cudaGetLastError();
+}
+
+}  // namespace gpr

@@ -37,6 +37,8 @@ _SIGS = {
     "gpr_ctx_destroy": (C.c_int, [_vp]),
     "gpr_last_error": (C.c_char_p, [_vp]),
     "gpr_ctx_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
+    "gpr_dbg_ozaki_dgemm": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _i64, _dp, _i64, C.c_double, _dp, _i64,
+                                      C.c_int, C.c_int, _dp]),
     "gpr_ctx_launch_count": (_i64, [_vp]),
     "gpr_dim_hp": (C.c_int, [_ip, C.c_int, C.c_int]),
     "gpr_model_create": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _i64, _dp, _dp, C.c_int, C.c_int, C.POINTER(_vp)]),
@@ -368,6 +370,18 @@ def dbg_dgemm(ctx, transA, transB, alpha, A, B, beta, Cm, flags=0, reps=1):
     ms = C.c_double(0.0)
     ctx.check(lib().gpr_dbg_dgemm(ctx.handle, transA.encode(), transB.encode(), M, N, K, float(alpha), dptr(A), A.shape[0],
                                   dptr(B), B.shape[0], float(beta), dptr(Cm), Cm.shape[0], int(flags), int(reps), C.byref(ms)))
+    return Cm, ms.value
+
+
+def dbg_ozaki_dgemm(ctx, alpha, A, B, beta, Cm, S=8, flags=0, reps=1):
+    """C = alpha A^T B + beta C through the INT8 tensor cores (csrc/ozaki_i8.cuh).  A: (K, M), B: (K, N), Fortran ordered."""
+    A, B = f64(A), f64(B)
+    Cm = np.array(Cm, dtype=np.float64, order="F")
+    K, M = A.shape
+    N = B.shape[1]
+    ms = C.c_double(0.0)
+    ctx.check(lib().gpr_dbg_ozaki_dgemm(ctx.handle, M, N, K, int(S), float(alpha), dptr(A), A.shape[0], dptr(B), B.shape[0], float(beta),
+                                        dptr(Cm), Cm.shape[0], int(flags), int(reps), C.byref(ms)))
     return Cm, ms.value
 
 

@@ -172,6 +172,12 @@ int gpr_sample_mvn(gpr_ctx* ctx, const int* comp_types, int ncomp, int D, const 
 int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, double alpha, const double* A,
                   int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, int reps,
                   double* ms);
+/* diagnostics / prototype: C = alpha A^T B + beta C (T,N form: A is K x M, B is K x N, both k-contiguous) through the INT8
+ * tensor cores (tcgen05.mma kind::i8 with TMEM accumulators): Ozaki-type splitting of every row of A^T and column of B
+ * into S signed 7-bit digits, S (S + 1) / 2 exact integer products, FP64 recombination (csrc/ozaki_i8.cuh).
+ * M % 128 == 0, N % 128 == 0, K % 128 == 0, K <= 32768, 2 <= S <= 8.  flags: 1 = upper only, 2 = K-from-N. */
+int gpr_dbg_ozaki_dgemm(gpr_ctx* ctx, int M, int N, int K, int S, double alpha, const double* A, int64_t lda, const double* B,
+                        int64_t ldb, double beta, double* C, int64_t ldc, int flags, int reps, double* ms);
 /* factor (and optionally invert) a host SPD matrix in place through the blocked path; A is N x N.
  * mode 0: potrf (upper = U), 1: potrf + trtri (upper = U^-1), 2: potrf + trtri + in-place lauum (upper = A^-1),
  * 3: potrf + trtri + out-of-place W W^T (upper = A^-1; the path gpr_update_cache takes when memory allows). */
