@@ -250,11 +250,13 @@ def cpu_baseline(budget_s=30.0):
     if cal:
         # measured growth on this pool's host: t(largest calibrated N) / t(n_base) from the committed --impl reference run, then
         # that run's own scale to N = 32768 (1.0 when it ran the metric's N itself)
-        mt = {int(k): v for k, v in cal.get("measured_s_per_eval", {}).items()}
-        if n_base in mt and cal.get("sample_N") in mt:
-            scale = mt[cal["sample_N"]] / mt[n_base] * cal.get("scale", 1.0)
-            how = (f"growth N={n_base} -> {cal['sample_N']} measured by the committed calibration run (profiles/cpu_calibration_r2.json: "
-                   f"{mt[n_base]:.2f} s -> {mt[cal['sample_N']]:.1f} s) x its scale {cal.get('scale', 1.0):.2f} to N=32768")
+        fit = cal.get("fit", {})
+        ca, cb = fit.get("a_N3"), fit.get("b_N2")
+        if ca and cb is not None:
+            tc = lambda n: ca * n ** 3 + cb * n ** 2
+            scale = tc(N_FULL) / tc(n_base)
+            how = (f"growth N={n_base} -> 32768 from the cost model fitted to the committed calibration run on this pool's host "
+                   f"(profiles/cpu_calibration_r2.json: measured up to N={cal.get('sample_N')}; the model gives {tc(n_base):.2f} s at N={n_base})")
     t_full = meas[n_base] * scale
     sample = (f"reference-shaped CPU path (oracle/gpr_oracle_big.reference_shaped_eval) on {hi['cores']} host cores ({hi['blas']}, "
               f"{hi['blas_threads']} BLAS threads), measured s/eval in this run {({k: round(v, 2) for k, v in meas.items()})}; scaled x{scale:.1f} "
@@ -602,6 +604,17 @@ def run_gpu(args, rank, world, local_rank):
         t_e = float(tt.item())
     e2e = {"value": world * args.steps / t_e, "unit": UNIT, "h2d_bytes_per_step": 8 * (D * N + N + P), "d2h_bytes_per_step": 8 * (P + 1)}
 
+    # the same evaluation with every FP64 product on the DMMA pipe (INT8-tensor-core route off), for the record
+    dmma_only = None
+    if rank == 0:
+        ctx.set_option("ozaki", 0)
+        mh.nlml_grad(np.log(hp_at(hp0, 500, rank)), log_scale=True)
+        Fd, Gd = mh.nlml_grad(np.log(hp_at(hp0, args.warmup + args.steps - 1, rank)), log_scale=True)
+        td = mh.timings()
+        dmma_only = {"ms_per_eval": td["eval"], "evals_per_s": 1e3 / td["eval"], "stage_ms": {k: round(td[k], 2) for k in ("potrf", "trtri", "lauum")},
+                     "F": Fd, "relF_vs_default_route": abs(Fd - F) / abs(F),
+                     "relG_vs_default_route": float((np.abs(Gd - G) / np.maximum(np.abs(G), 1e-8 * np.linalg.norm(G))).max())}
+        ctx.set_option("ozaki", -1)
     # secondary single-GPU numbers that need the headline model (rank 0 only), then free it for the sharded extras
     pred_extra = predict_extras(args, mh, hp0, N, D) if (rank == 0 and not args.no_predict) else {}
     gemm_ms = None
@@ -646,6 +659,7 @@ def run_gpu(args, rank, world, local_rank):
     # secondary metrics of BASELINE.json: Cholesky TFLOP/s, predict points/s
     extra = {"cholesky_tflops": N ** 3 / 3 / ms["potrf"] / 1e9, "inverse_tflops": 2 * N ** 3 / 3 / (ms["trtri"] + ms["lauum"]) / 1e9,
              "stage_ms_per_step": {k: round(v, 3) for k, v in ms.items() if v > 0 and not k.startswith("pred")}}
+    extra["dmma_only"] = dmma_only
     extra.update(pred_extra)
     extra.update(sharded)
 
@@ -662,7 +676,22 @@ def run_gpu(args, rank, world, local_rank):
             traffic = tj["dgemm128_dram_gb_per_eval"]
     except Exception:
         pass
+    # INT8-tensor-core route, isolated: FP64-equivalent rate of one 8192^3 product incl. the digit extraction
+    oz_tf = None
+    try:
+        An = np.asfortranarray(np.random.default_rng(1).standard_normal((8192, 8192)))
+        _, oz_ms = _ffi.dbg_ozaki_dgemm(ctx, 1.0, An, An, 0.0, np.zeros((8192, 8192), order="F"), S=8, reps=4)
+        oz_tf = 2 * 8192 ** 3 / oz_ms / 1e9
+        del An
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": fp64_sust, "unit": "TFLOP/s", "frac": achieved / fp64_sust,
+                "note": "achieved = N^3 FP64-equivalent flop / (potrf + trtri + lauum) ms.  peak = the FP64 (DMMA) roof as measured through cuBLAS DGEMM; "
+                        "the large products of potrf and trtri run on the INT8 tensor cores (tcgen05.mma kind::i8, 36 exact integer products per FP64 "
+                        "product, csrc/ozaki_i8.cuh), which is how frac can exceed the FP64 pipe: extra.dmma_only holds the same step on the DMMA pipe alone",
+                "int8_route": {"fp64_equivalent_tflops_8192": oz_tf, "int8_pops": (oz_tf * 36 / 1e3) if oz_tf else None, "int8_peak_pops_nominal": 4.5,
+                               "frac_of_nominal_int8": (oz_tf * 36 / 4500.0) if oz_tf else None,
+                               "note": "MEASURED_PEAKS.json holds no INT8 figure (bf16 1630 TFLOP/s burst measured); 4.5 POPS is NVIDIA's dense INT8 figure for B200"},
                 "traffic": traffic, "traffic_unit": "GB of DRAM read+write by all dgemm128 launches of one step (ncu, profiles/dram_traffic.json)",
                 "kernel": "dgemm128_kernel (DMMA) inside blocked potrf+trtri+lauum: N^3 flop per step / (potrf+trtri+lauum) CUDA-event ms",
                 "peak_source": f"cuBLAS DGEMM 8192^3 via torch.matmul, sustained {fp64_sust:.1f} / burst {fp64_burst:.1f} TFLOP/s measured in this run "

@@ -166,7 +166,20 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(tfull + 1);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  // CTA rasterisation as in dgemm128_kernel: consecutive CTAs walk 16 row tiles x all column tiles, so one wave of 148 CTAs
+  // touches ~16 x 9 tiles of C and re-reads few digit planes (issued x-fastest, a wave would stream every plane of op(A)
+  // from DRAM once per column tile: 467 GB for a 16384^3 product against 4.3 GB of planes).
+  int tile_m, tile_n;
+  {
+    constexpr int GM = 16;
+    const int Mx = gridDim.x, Ny = gridDim.y;
+    const int pid = blockIdx.x + blockIdx.y * Mx;
+    const int group = pid / (GM * Ny), first_m = group * GM;
+    const int gsize = min(Mx - first_m, GM);
+    const int rem = pid - group * GM * Ny;
+    tile_m = first_m + rem % gsize;
+    tile_n = rem / gsize;
+  }
   const int blk_n = (tile_n * OZ_BN) >> 7;
   if ((p.flags & 1) && tile_m > blk_n) return;                       // GEMM_UPPER_ONLY: whole CTA leaves before any allocation
   if ((p.flags & 64) && tile_m == 0 && blk_n == 0) return;           // GEMM_SKIP_TILE00

@@ -414,6 +414,89 @@ def test_tma_fed_gemm_matches_ldgsts_gemm(gpr):
         ctx.close()
 
 
+def test_ozaki_int8_gemm_is_an_fp64_product(gpr):
+    """csrc/ozaki_i8.cuh: C = alpha A^T B + beta C through tcgen05.mma kind::i8 (8 signed 7-bit digits per operand row,
+    36 exact integer products in TMEM, FP64 recombination) against a longdouble product.  The error is measured relative to
+    |A|^T |B| (the natural scale of a dot product) and compared with numpy's DGEMM on the same data; flags: upper-only and
+    the triangular K-from-N product of the inverse."""
+    from gpr_sm100a import _ffi
+    rng = np.random.default_rng(99)
+    ctx = gpr.Context(0)
+    try:
+        for (M, N, K, alpha, beta, flags, kind) in ((128, 128, 128, 1.0, 0.0, 0, "g"), (256, 384, 640, -1.0, 1.0, 0, "g"), (512, 512, 4096, 1.0, 0.5, 1, "g"),
+                                                    (384, 384, 384, 1.0, 0.0, 3, "tri"), (256, 256, 32768, 1.0, 0.0, 0, "g"), (512, 640, 2048, 1.0, 1.0, 0, "decay")):
+            if kind == "tri":      # triangular op(B) with GARBAGE above its diagonal blocks (the Z11 operand of trtri_t)
+                A = np.tril(rng.standard_normal((K, M)))
+                B = A.copy()
+                for J in range(M // 128):
+                    B[:128 * J, 128 * J:128 * (J + 1)] = 1e30
+            elif kind == "decay":
+                A = rng.standard_normal((K, M)) * np.exp(-4 * rng.random((K, M)))
+                B = rng.standard_normal((K, N)) * np.exp(-4 * rng.random((K, N)))
+            else:
+                A, B = rng.standard_normal((K, M)), rng.standard_normal((K, N))
+            A, B = np.asfortranarray(A), np.asfortranarray(B)
+            C0 = np.asfortranarray(rng.standard_normal((M, N)))
+            C, _ = _ffi.dbg_ozaki_dgemm(ctx, alpha, A, B, beta, C0, S=8, flags=flags)
+            Ae, Be = A.copy(), np.tril(B) if kind == "tri" else B.copy()
+            if flags & 2:          # column block J contracts over k >= 128 J only
+                ref = beta * C0.astype(np.longdouble)
+                den = np.zeros((M, N))
+                for J in range(N // 128):
+                    sl = slice(128 * J, 128 * (J + 1))
+                    ref[:, sl] += alpha * (Ae[128 * J:, :].astype(np.longdouble).T @ Be[128 * J:, sl].astype(np.longdouble))
+                    den[:, sl] = np.abs(Ae[128 * J:, :]).T @ np.abs(Be[128 * J:, sl])
+            else:
+                ref = alpha * (Ae.astype(np.longdouble).T @ Be.astype(np.longdouble)) + beta * C0
+                den = np.abs(Ae).T @ np.abs(Be)
+            mask = np.triu(np.ones((M, N), dtype=bool)) if flags & 1 else np.ones((M, N), dtype=bool)
+            err = float(np.max((np.abs(C - ref) / (den + 1e-300))[mask]))
+            print(f"\nozaki {M}x{N}x{K} flags={flags} {kind}: max err / (|A|^T|B|) = {err:.2e}")
+            # norm-wise accuracy: entries formed by few / small terms under a large row maximum (triangular corner, decaying
+            # magnitudes) carry an error relative to the row maxima, not to their own terms
+            assert err < (4e-16 if kind == "g" else 5e-14)
+            if flags & 1:
+                assert np.array_equal(C[~mask], C0[~mask])
+    finally:
+        ctx.close()
+
+
+def test_ozaki_route_keeps_nlml_parity(gpr):
+    """The optional INT8-tensor-core route of the blocked factorization (ctx option "ozaki" = 8 digits; potrf, trtri and
+    the prediction solves, not the W^T W product) against the oracle on a model large enough that its top-level products
+    are routed there (ozaki_min = 512): same tolerances as the DMMA path (src/cost.jl:96-127, src/predict.jl:83-95)."""
+    from gpr_sm100a import _ffi
+    rng = np.random.default_rng(4242)
+    D, N = 8, 4096
+    x = rng.random((D, N))
+    y = np.sin(3 * x).sum(0) + 0.1 * rng.standard_normal(N)
+    hp = np.concatenate([[1.0], 0.5 * np.ones(D), [0.5], 2.0 * np.ones(D), [0.1]])
+    xp = np.asfortranarray(rng.random((D, 2048)))
+    mdo = o.GPRModel((o.SE, o.SE, o.NOISE), hp, x, y)
+    Fo, Go = o.loss_grad(hp, mdo)
+    mu_o, var_o = o.predict(mdo, xp, diagonal_var=True)
+    ctx = gpr.Context(0)
+    try:
+        res = {}
+        for oz in (0, 8):
+            ctx.set_option("ozaki", oz)
+            ctx.set_option("ozaki_min", 512)
+            mh = _ffi.ModelHandle(ctx, [1, 1, 2], D, np.asfortranarray(x), y)
+            l0 = ctx.launch_count()
+            F, G = mh.nlml_grad(hp)
+            mu, var, _ = mh.predict(xp, want_var=True)
+            res[oz] = (abs(F - Fo) / abs(Fo), grad_err(G, Go), mean_err(mu.reshape(-1), mu_o, y), np.abs(var - var_o).max() / o.prior_diag(mdo),
+                       ctx.launch_count() - l0)
+            mh.close()
+        print(f"\nN={N}: DMMA relF {res[0][0]:.1e} relG {res[0][1]:.1e} mean {res[0][2]:.1e} var {res[0][3]:.1e} | "
+              f"INT8 relF {res[8][0]:.1e} relG {res[8][1]:.1e} mean {res[8][2]:.1e} var {res[8][3]:.1e}")
+        assert res[8][0] <= TOL_F and res[8][1] <= TOL_G and res[8][2] <= TOL_MU and res[8][3] <= TOL_VAR
+        assert res[8][4] != res[0][4]          # the route was actually taken (different launch count)
+    finally:
+        ctx.set_option("ozaki", 0)
+        ctx.close()
+
+
 # ------------------------------------------------------------------ (4) larger sizes: oracle where it is cheap, else invariants
 def test_config2_n8192_three_hp_sets(gpr):
     """BASELINE.json config 2: ARD SE + noise, N=8192, D=8, FP64 NLML + gradient over 3 hp sets.
