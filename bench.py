@@ -692,8 +692,8 @@ def run_gpu(args, rank, world, local_rank):
                 "int8_route": {"fp64_equivalent_tflops_8192": oz_tf, "int8_pops": (oz_tf * 36 / 1e3) if oz_tf else None, "int8_peak_pops_nominal": 4.5,
                                "frac_of_nominal_int8": (oz_tf * 36 / 4500.0) if oz_tf else None,
                                "note": "MEASURED_PEAKS.json holds no INT8 figure (bf16 1630 TFLOP/s burst measured); 4.5 POPS is NVIDIA's dense INT8 figure for B200"},
-                "traffic": traffic, "traffic_unit": "GB of DRAM read+write by all dgemm128 launches of one step (ncu, profiles/dram_traffic.json)",
-                "kernel": "dgemm128_kernel (DMMA) inside blocked potrf+trtri+lauum: N^3 flop per step / (potrf+trtri+lauum) CUDA-event ms",
+                "traffic": traffic, "traffic_unit": "GB of DRAM read+write by all product kernels (DMMA GEMMs, INT8 GEMM, digit extraction) of one step (ncu launch list, profiles/dram_traffic.json)",
+                "kernel": "dgemm128_tma_kernel (DMMA) + oz_gemm_kernel (INT8 tensor cores) inside blocked potrf+trtri+lauum: N^3 FP64-equivalent flop per step / (potrf+trtri+lauum) CUDA-event ms",
                 "peak_source": f"cuBLAS DGEMM 8192^3 via torch.matmul, sustained {fp64_sust:.1f} / burst {fp64_burst:.1f} TFLOP/s measured in this run "
                                "(MEASURED_PEAKS.json holds no FP64 figure" + (f"; its HBM copy figure is {hp_peak.get('hbm_gbs')} GB/s)" if hp_peak else ")"),
                 "kernel_isolated_tflops": gemm_tf, "kernel_isolated_frac": gemm_tf / fp64_burst}

@@ -65,13 +65,14 @@ def _potrf_upper(K):
     return K, 0
 
 
-def _solve_ut(U, B, trans):
-    """op(U)^-1 B for the upper-triangular part of U, trans in {'T', 'N'}; blocked above BIG_N."""
+def _solve_ut(U, B, trans, inplace=False):
+    """op(U)^-1 B for the upper-triangular part of U, trans in {'T', 'N'}; blocked above BIG_N (there `inplace` solves in
+    B's own storage, which must be a Fortran-ordered float64 array)."""
     n = U.shape[0]
     if n <= BIG_N:
         return sl.solve_triangular(U, B, trans=trans, lower=False)
     nb = NB_BIG
-    X = np.array(B, dtype=np.float64, order="F", copy=True)
+    X = B if inplace else np.array(B, dtype=np.float64, order="F", copy=True)
     X2 = X.reshape(n, -1)
     blocks = [(k0, min(n, k0 + nb)) for k0 in range(0, n, nb)]
     if trans == "T":                                        # forward substitution with U^T
@@ -99,7 +100,8 @@ def _potrs_upper(U, B):
         X, info = sl.lapack.dpotrs(U, B, lower=0, overwrite_b=1)
         assert info == 0
         return X
-    return _solve_ut(U, _solve_ut(U, B, "T"), "N")
+    X = np.asfortranarray(B, dtype=np.float64)          # no copy for the Fortran-ordered workspaces the callers pass (dpotrs overwrites b too)
+    return _solve_ut(U, _solve_ut(U, X, "T", inplace=True), "N", inplace=True)
 
 
 def _columns_of_K(cov, hp, x, cols, eps=1e-8):
