@@ -66,6 +66,7 @@ struct gpr_ctx {
                                 // DMMA otherwise; "ozaki_min": smallest M, N, K routed there
   int oz_active = 0;            // digits in force for the model being worked on (set by the entry points)
   int64_t ozaki_min = 1024;
+  int ozaki_windows = 0;        // option "ozaki_windows": two-diagonal-window 128 x 128 kernel for the INT8 products (csrc/ozaki_i8.cuh)
   int64_t ozaki_panel = 4096;   // option "ozaki_panel": k-panel of the W^T W product (own digit scales per panel)
   int oz_mask = 11, oz_cur = 8;   // option "ozaki_phases": bit 0 potrf, 1 trtri, 2 lauum (W^T W), 3 everything else (prediction solves).
                                   // Default without W^T W: its operand columns span many orders of magnitude and one power-of-two scale per
@@ -147,7 +148,7 @@ struct CudaBE {
       if (ctx->oz_ws_bytes >= need) {
         for (int64_t z = 0; z < batch; ++z) {
           note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, ctx->oz_active, alpha, A + z * sA, lda, B + z * sB, ldb, beta, C + z * sC, ldc,
-                                  flags, ctx->oz_ws));
+                                  flags | (ctx->ozaki_windows ? 512 : 0), ctx->oz_ws));
           ctx->launches += 3;
         }
         return;
@@ -184,6 +185,23 @@ struct CudaBE {
   // tile-mapped GEMM of the block-cyclic multi-GPU drivers (csrc/dist_blocked.hpp)
   void gemm_map(char tA, char tB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int flags, const TileMap& map) {
+    if (flags == BLK_MAP_UPPER && ctx->oz_active > 0 && ctx->stream == ctx->main_stream && (ctx->oz_mask & ctx->oz_cur) && tA == 'T' &&
+        tB == 'N' && (const double*)C != A && (const double*)C != B && M >= ctx->ozaki_min && N >= ctx->ozaki_min && K >= ctx->ozaki_min &&
+        K <= 32768 && !(M % 128) && !(N % 128) && !(K % 128)) {
+      // rank-nb trailing update of the block-cyclic potrf on the INT8 tensor cores (csrc/ozaki_i8.cuh)
+      const size_t need = oz_workspace_bytes((int)M, (int)N, (int)K, ctx->oz_active);
+      if (need > ctx->oz_ws_bytes) {
+        cudaStreamSynchronize(ctx->main_stream);
+        cudaFree(ctx->oz_ws); ctx->oz_ws = nullptr; ctx->oz_ws_bytes = 0;
+        if (cudaMalloc(&ctx->oz_ws, need) == cudaSuccess) ctx->oz_ws_bytes = need; else cudaGetLastError();
+      }
+      if (ctx->oz_ws_bytes >= need) {
+        note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, ctx->oz_active, alpha, A, lda, B, ldb, beta, C, ldc, flags, ctx->oz_ws, 0,
+                                map.col_gtile, map.row_gtile0));
+        ctx->launches += 3;
+        return;
+      }
+    }
     if (ctx->gemm_tma && gemm_tma_supported(tA, tB, (int)M, (int)N, (int)K, A, B, C, flags, 1, 0, 0))
       note(launch_dgemm128_tma(ctx->stream, (int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc, flags, 1, 0, 0, 0, map.col_gtile,
                                map.row_gtile0, map.k_gtile0));
@@ -675,6 +693,7 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
       return fail(ctx, GPR_ERR_ARG, "ozaki: number of digits must be -1 (automatic), 0 (off), 6, 7 or 8");
     ctx->ozaki = (int)value; ctx->oz_active = value > 0 ? (int)value : 0; return GPR_OK;
   }
+  if (!strcmp(name, "ozaki_windows")) { ctx->ozaki_windows = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "ozaki_panel")) { ctx->ozaki_panel = std::max<int64_t>(128, (value / 128) * 128); return GPR_OK; }
   if (!strcmp(name, "ozaki_phases")) { ctx->oz_mask = (int)value & 15; return GPR_OK; }
   if (!strcmp(name, "ozaki_min")) { ctx->ozaki_min = std::max<int64_t>(128, value); return GPR_OK; }

@@ -711,6 +711,11 @@ int gpr_mgpu_destroy(gpr_mgpu* mg) {
 
 int gpr_mgpu_set_option(gpr_mgpu* mg, const char* name, int64_t value) {
   if (!mg || !name) return GPR_ERR_ARG;
+  if (!strcmp(name, "ozaki") || !strcmp(name, "ozaki_min") || !strcmp(name, "ozaki_phases")) {   // INT8 route of the trailing updates
+    for (auto& R : mg->rk)
+      if (R.ctx && gpr_ctx_set_option(R.ctx, name, value) != GPR_OK) return mfail(mg, GPR_ERR_ARG, R.ctx->err);
+    return GPR_OK;
+  }
   if (value < 0 || value > 2) return mfail(mg, GPR_ERR_ARG, "option value must be 0, 1 or 2");
   if (!strcmp(name, "gemm_tma") || !strcmp(name, "kbuild_gram")) {   // forwarded to every rank's context
     for (auto& R : mg->rk) if (R.ctx) gpr_ctx_set_option(R.ctx, name, value);
@@ -852,9 +857,26 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
   db.prefetch_trtri = mg->prefetch_trtri != 0;
   db.prefetch_lauum = mg->prefetch_lauum != 0;
 
+  // INT8-tensor-core route of the rank-nb trailing updates of potrf (same automatic rule as the single-GPU path)
+  {
+    double sig2 = 0.0, noise2 = 0.0;
+    bool have_noise = false;
+    for (int c = 0; c < m->ncomp; ++c) {
+      const double v = hp[m->spec.hp_off[c]];
+      if (m->spec.type[c] == KT_NOISE) { if (!have_noise) { noise2 = v * v; have_noise = true; } }
+      else sig2 += v * v;
+    }
+    const double floor_ = noise2 + m->nk * eps;
+    const int auto_digits = (floor_ > 0.0 && ((double)N * sig2 + floor_) / floor_ <= 1e8) ? 8 : 0;
+    for (auto& R : mg->rk) R.ctx->oz_active = R.ctx->ozaki >= 0 ? R.ctx->ozaki : auto_digits;
+  }
+  auto set_phase = [&](int ph) { for (auto& R : mg->rk) R.ctx->oz_cur = ph; };
+
   // ---- potrf (+ forward substitution of y), log det
   tick();
+  set_phase(1);
   db.potrf();
+  set_phase(8);
   for (auto& R : mg->rk) {
     const int r = R.rank;
     MCK(cudaSetDevice(R.ctx->device));

@@ -152,6 +152,7 @@ struct OzParams {
   const double* scaleA; const double* scaleB;    // 2^ea (M), 2^eb (N)
   int flags;                                     // GEMM_UPPER_ONLY, GEMM_K_FROM_N (same meaning as dgemm_sm100.cuh)
   int k_off;                                     // K-from-N: global index of the first contraction row (k-panels of one product)
+  const int* col_gtile; int row_gtile0;          // GEMM_MAP_UPPER (flag 8): global 128-tile column of each local 128-tile column (csrc/dist_blocked.hpp)
 };
 
 template <int S>
@@ -183,6 +184,11 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
   const int blk_n = (tile_n * OZ_BN) >> 7;
   if ((p.flags & 1) && tile_m > blk_n) return;                       // GEMM_UPPER_ONLY: whole CTA leaves before any allocation
   if ((p.flags & 64) && tile_m == 0 && blk_n == 0) return;           // GEMM_SKIP_TILE00
+  int gt = 0;
+  if (p.flags & 8) {                                                  // GEMM_MAP_UPPER: tile-mapped trailing update of the block-cyclic potrf
+    gt = p.col_gtile[blk_n];
+    if (p.row_gtile0 + tile_m > gt) return;
+  }
   const int kt0 = (p.flags & 2) ? max(0, blk_n * 128 - p.k_off) / OZ_BK : 0;   // GEMM_K_FROM_N
   const int KT = p.K / OZ_BK - kt0;
   const int m0 = tile_m * OZ_BM, n0 = tile_n * OZ_BN;
@@ -208,6 +214,7 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
         const int s = kt & 1;
         if (kt >= OZ_STAGES) oz_wait(&empty[s], (unsigned)(((kt >> 1) - 1) & 1));
         unsigned char* st = smem + (size_t)s * stage_bytes;
+        if ((p.flags & 256) && kt >= OZ_STAGES) { mbar_arrive(&full[s]); continue; }   // timing probe: no reload (results are garbage)
         mbar_expect_tx(&full[s], (unsigned)stage_bytes);
         tma_load_3d(st, &mapA, &full[s], (kt0 + kt) * OZ_BK, m0, 0);                               // S x 128 x 64 B
         tma_load_3d(st + (size_t)S * OZ_BM * OZ_BK, &mapB, &full[s], (kt0 + kt) * OZ_BK, n0, 0);   // S x  64 x 64 B
@@ -217,7 +224,18 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
     // ===== MMA issuer =====
     // One thread issues every MMA of the CTA, so its instruction stream is the critical path: S is a template parameter,
     // the pair loops are fully unrolled and a descriptor is the stage's base descriptor plus a compile-time constant.
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow and one elected lane issues: inside a divergent `if (lane == 0)` the
+    // compiler wraps every uniform-datapath instruction (UTCIMMA, its descriptor arithmetic) into an ELECT / BRA.U.ANY loop,
+    // ~8 SASS instructions per MMA, and the issue stream -- not the tensor pipe -- sets the pace (58 cycles per MMA measured).
+    {
+      unsigned elected = 0;
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "elect.sync _|p, 0xffffffff;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(elected));
       uint64_t baseA[OZ_STAGES], baseB[OZ_STAGES];
 #pragma unroll
       for (int s = 0; s < OZ_STAGES; ++s) {
@@ -230,21 +248,24 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
         tc_fence_after();
         const uint64_t dA = s ? baseA[1] : baseA[0], dB = s ? baseB[1] : baseB[0];
         const unsigned acc_first = (kt > 0) ? 1u : 0u;
+        if (elected) {
 #pragma unroll
-        for (int t = 1; t <= S; ++t) {
+          for (int t = 1; t <= S; ++t) {
 #pragma unroll
-          for (int sa = 1; sa + t <= S + 1; ++sa) {
+            for (int sa = 1; sa + t <= S + 1; ++sa) {
 #pragma unroll
-            for (int kk = 0; kk < OZ_BK / 32; ++kk) {   // 32-byte k-steps inside the 64-byte swizzle atom: +2 in the 16-byte address field
-              const uint64_t da = dA + (uint64_t)(((sa - 1) * OZ_BM * OZ_BK + 32 * kk) >> 4);
-              const uint64_t db = dB + (uint64_t)(((t - 1) * OZ_BN * OZ_BK + 32 * kk) >> 4);
-              tc_mma_i8(tmem_base + (unsigned)((sa + t - 2) * OZ_BN), da, db, OZ_IDESC, (kk > 0 || t > 1) ? 1u : acc_first);
+              for (int kk = 0; kk < OZ_BK / 32; ++kk) {   // 32-byte k-steps inside the 64-byte swizzle atom: +2 in the 16-byte address field
+                const uint64_t da = dA + (uint64_t)(((sa - 1) * OZ_BM * OZ_BK + 32 * kk) >> 4);
+                const uint64_t db = dB + (uint64_t)(((t - 1) * OZ_BN * OZ_BK + 32 * kk) >> 4);
+                tc_mma_i8(tmem_base + (unsigned)((sa + t - 2) * OZ_BN), da, db, OZ_IDESC, (kk > 0 || t > 1) ? 1u : acc_first);
+              }
             }
           }
+          tc_commit(&empty[s]);              // the stage may be refilled once these MMAs have read it
         }
-        tc_commit(&empty[s]);              // the stage may be refilled once these MMAs have read it
+        __syncwarp();
       }
-      tc_commit(tfull);                    // all accumulators complete
+      if (elected) tc_commit(tfull);       // all accumulators complete
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lanes 32 (warp % 4) .. +31 = rows of the tile =====
@@ -253,7 +274,7 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
     const int q = warp & 3;
     const int row = 32 * q + lane;
     const unsigned lane_addr = tmem_base + ((unsigned)(32 * q) << 16);
-    const bool diag_tile = (p.flags & 1) && (tile_m == blk_n);
+    const bool diag_tile = ((p.flags & 1) && (tile_m == blk_n)) || ((p.flags & 8) && (p.row_gtile0 + tile_m == gt));
     const int coff = n0 & 127;
     const double sa = p.scaleA[m0 + row] * p.alpha;
     double* Crow = p.C + (long long)(m0 + row) + (long long)n0 * p.ldc;
@@ -291,6 +312,184 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second-generation kernel: a WINDOW of diagonals per launch, 128 x 128 tile.
+// One UTCIMMA of shape M128 N64 K32 occupies the tensor pipe for ~58 cycles however cleanly it is issued (measured with and
+// without operand reloads, tools/ozaki_probe.py) -- 0.58 of the INT8 rate the pipe reaches with wide N -- and the eight diagonal
+// accumulators of one pass cannot be wider than 64 TMEM columns each.  Splitting the 36 pairs into two launches by diagonal,
+//   low order  d = 6 .. 9  (26 pairs, all 8 digit planes, k-tile 32 bytes / SWIZZLE_32B),  C  = alpha * (...) + beta * C
+//   high order d = 2 .. 5  (10 pairs, digit planes 1-4,   k-tile 64 bytes / SWIZZLE_64B),  C += alpha * (...)
+// needs four accumulators per launch, i.e. N = 128 per MMA: half as many tensor-pipe instructions for the same work.
+// The digit planes are streamed twice (once per window).  MEASURED (profiles/ozaki_probe_r2p.log): an N = 128 instruction takes
+// twice as long as an N = 64 one -- 73.5 against 69.1 TFLOP/s FP64-equivalent at 8192^3, nothing inside the factorization --
+// so the tensor pipe itself (~2.65 INT8 POPS in this access pattern), not the instruction shape, is the limit.  Kept as the
+// optional variant (launch flag 512, option "ozaki_windows").
+// ---------------------------------------------------------------------------------------------------------------
+template <int S, int BN, int BK, int DLO, int DHI> struct OzWin {
+  static constexpr int NACC = DHI - DLO + 1;
+  static constexpr int PL = (DHI - 1 < S) ? DHI - 1 : S;                  // digit planes needed
+  static constexpr size_t STAGE = (size_t)PL * (OZ_BM + BN) * BK;
+  static constexpr int NST = (int)((200 * 1024) / STAGE) > 4 ? 4 : (int)((200 * 1024) / STAGE);
+  static constexpr size_t SMEM = NST * STAGE + 1024 + 256;
+  static constexpr unsigned IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(OZ_BM >> 4) << 24);
+  static_assert(NACC * BN <= 512, "accumulators exceed TMEM");
+  static_assert(NST >= 2, "need two stages");
+};
+
+template <int BK> __device__ __forceinline__ uint64_t oz_smem_desc_k(const void* p) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  uint64_t d = 0;
+  d |= (uint64_t)((a & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8u * BK) >> 4) << 32;          // 8-row groups are 8 * BK bytes apart
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(BK == 64 ? 4 : 6) << 61;         // SWIZZLE_64B / SWIZZLE_32B
+  return d;
+}
+
+template <int S, int BN, int BK, int DLO, int DHI>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+  using W = OzWin<S, BN, BK, DLO, DHI>;
+  constexpr int NST = W::NST, PL = W::PL;
+  extern __shared__ unsigned char oz_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * W::STAGE);
+  uint64_t* empty = full + NST;
+  uint64_t* tfull = empty + NST;
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(tfull + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int tile_m, tile_n;
+  {
+    constexpr int GM = 8;      // 8 row tiles x all column tiles per pass (tiles are 128 x 128 here)
+    const int Mx = gridDim.x, Ny = gridDim.y;
+    const int pid = blockIdx.x + blockIdx.y * Mx;
+    const int group = pid / (GM * Ny), first_m = group * GM;
+    const int gsize = min(Mx - first_m, GM);
+    const int rem = pid - group * GM * Ny;
+    tile_m = first_m + rem % gsize;
+    tile_n = rem / gsize;
+  }
+  const int blk_n = (tile_n * BN) >> 7;
+  if ((p.flags & 1) && tile_m > blk_n) return;
+  if ((p.flags & 64) && tile_m == 0 && blk_n == 0) return;
+  int gt = 0;
+  if (p.flags & 8) {
+    gt = p.col_gtile[blk_n];
+    if (p.row_gtile0 + tile_m > gt) return;
+  }
+  const int kt0 = (p.flags & 2) ? max(0, blk_n * 128 - p.k_off) / BK : 0;
+  const int KT = p.K / BK - kt0;
+  const int m0 = tile_m * OZ_BM, n0 = tile_n * BN;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"((unsigned)__cvta_generic_to_shared(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % NST;
+        if (kt >= NST) oz_wait(&empty[s], (unsigned)((kt / NST - 1) & 1));
+        unsigned char* st = smem + (size_t)s * W::STAGE;
+        mbar_expect_tx(&full[s], (unsigned)W::STAGE);
+        tma_load_3d(st, &mapA, &full[s], (kt0 + kt) * BK, m0, 0);                               // PL x 128 x BK
+        tma_load_3d(st + (size_t)PL * OZ_BM * BK, &mapB, &full[s], (kt0 + kt) * BK, n0, 0);     // PL x BN  x BK
+      }
+    }
+  } else if (warp == 1) {
+    unsigned elected = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(elected));
+    const uint64_t baseA0 = oz_smem_desc_k<BK>(smem), baseB0 = oz_smem_desc_k<BK>(smem + (size_t)PL * OZ_BM * BK);
+    for (int kt = 0; kt < KT; ++kt) {
+      const int s = kt % NST;
+      oz_wait(&full[s], (unsigned)((kt / NST) & 1));
+      tc_fence_after();
+      const uint64_t dA = baseA0 + (uint64_t)((s * W::STAGE) >> 4), dB = baseB0 + (uint64_t)((s * W::STAGE) >> 4);
+      const unsigned acc_first = (kt > 0) ? 1u : 0u;
+      if (elected) {
+#pragma unroll
+        for (int t = 1; t <= PL; ++t) {
+#pragma unroll
+          for (int sa = 1; sa <= PL; ++sa) {
+            if (sa + t < DLO || sa + t > DHI) continue;
+            // first pair of diagonal d = sa + t in this loop order: t = max(1, d - PL)
+            const bool first_pair = (t == ((sa + t - PL) > 1 ? (sa + t - PL) : 1));
+#pragma unroll
+            for (int kk = 0; kk < BK / 32; ++kk) {
+              const uint64_t da = dA + (uint64_t)(((sa - 1) * OZ_BM * BK + 32 * kk) >> 4);
+              const uint64_t db = dB + (uint64_t)(((t - 1) * BN * BK + 32 * kk) >> 4);
+              tc_mma_i8(tmem_base + (unsigned)((sa + t - DLO) * BN), da, db, W::IDESC, (kk > 0 || !first_pair) ? 1u : acc_first);
+            }
+          }
+        }
+        tc_commit(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (elected) tc_commit(tfull);
+  } else {
+    oz_wait(tfull, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const unsigned lane_addr = tmem_base + ((unsigned)(32 * q) << 16);
+    const bool diag_tile = ((p.flags & 1) && (tile_m == blk_n)) || ((p.flags & 8) && (p.row_gtile0 + tile_m == gt));
+    const int coff = n0 & 127;
+    const double sa = p.scaleA[m0 + row] * p.alpha;
+    double* Crow = p.C + (long long)(m0 + row) + (long long)n0 * p.ldc;
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      double acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll
+      for (int d = DHI; d >= DLO; --d) {
+        unsigned v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(lane_addr + (unsigned)((d - DLO) * BN + c0)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        const double w = __hiloint2double((1023 - 7 * d) << 20, 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fma((double)(int)v[j], w, acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = c0 + j;
+        if (diag_tile && row > col + coff) continue;
+        double* cp = Crow + (long long)col * p.ldc;
+        const double r = acc[j] * sa * p.scaleB[n0 + col];
+        *cp = (p.beta != 0.0) ? fma(p.beta, *cp, r) : r;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+  }
+}
+
 // ---- host side ----
 // int8 digit planes as a 3-D tensor {k (bytes), rows, plane}: box = {64, box_rows, S}, SWIZZLE_64B
 inline bool oz_make_map(CUtensorMap* map, const int8_t* base, uint64_t Kp, uint64_t Rp, int S, uint32_t box_rows) {
@@ -307,8 +506,24 @@ inline bool oz_make_map(CUtensorMap* map, const int8_t* base, uint64_t Kp, uint6
 template <int S> inline cudaError_t oz_set_attr_s() {
   return cudaFuncSetAttribute(oz_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_smem_bytes(S));
 }
+inline bool oz_make_map_k(CUtensorMap* map, const int8_t* base, uint64_t Kp, uint64_t Rp, int planes_total, int box_planes, uint32_t box_rows, int BK) {
+  PFN_encodeTiled fn = tma_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {Kp, Rp, (cuuint64_t)planes_total};
+  cuuint64_t strides[2] = {Kp, Kp * Rp};
+  cuuint32_t box[3] = {(cuuint32_t)BK, box_rows, (cuuint32_t)box_planes};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            BK == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+using OzWinLo = OzWin<8, 128, 32, 6, 9>;
+using OzWinHi = OzWin<8, 128, 64, 2, 5>;
+
 inline cudaError_t oz_set_attr() {
-  cudaError_t e = oz_set_attr_s<8>();
+  cudaError_t e = cudaFuncSetAttribute(oz_gemm_win_kernel<8, 128, 32, 6, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWinLo::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<8, 128, 64, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWinHi::SMEM);
+  if (e == cudaSuccess) e = oz_set_attr_s<8>();
   if (e == cudaSuccess) e = oz_set_attr_s<7>();
   if (e == cudaSuccess) e = oz_set_attr_s<6>();
   if (e == cudaSuccess) e = oz_set_attr_s<2>();
@@ -325,7 +540,9 @@ inline size_t oz_workspace_bytes(int M, int N, int K, int S) {
 // flags: GEMM_UPPER_ONLY (1), GEMM_K_FROM_N (2), GEMM_SKIP_TILE00 (64).  When A and B are the same matrix (the symmetric
 // updates of potrf and the W^T W product of the inverse) its digit planes are formed once and shared.
 inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int S, double alpha, const double* A, long long lda, const double* B,
-                                      long long ldb, double beta, double* C, long long ldc, int flags, void* workspace, int k_off = 0) {
+                                      long long ldb, double beta, double* C, long long ldc, int flags, void* workspace, int k_off = 0,
+                                      const int* col_gtile = nullptr, int row_gtile0 = 0) {
+  if ((flags & 8) && !col_gtile) return cudaErrorInvalidValue;
   if ((S != 8 && S != 7 && S != 6 && S != 2) || (M % OZ_BM) || (N % 128) || (K % 128) || K > 32768) return cudaErrorInvalidValue;
   const size_t Kp = (size_t)K;
   const bool shared = (A == B && lda == ldb);
@@ -342,7 +559,22 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
   if (!shared) oz_slice_kernel<<<(N + 7) / 8, 256, 0, st>>>(B, ldb, K, N, S, pb, (long long)Kp, N, sb, kfrom, k_off);
   CUtensorMap mA, mB;
   if (!oz_make_map(&mA, pa, Kp, (uint64_t)Ra, S, OZ_BM) || !oz_make_map(&mB, pb, Kp, (uint64_t)Rb, S, OZ_BN)) return cudaErrorInvalidValue;
-  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags, k_off};
+  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~512, k_off, col_gtile, row_gtile0};
+  if (S == 8 && (flags & 512)) {
+    // two diagonal windows, 128 x 128 tiles (flag 512; measured 73.5 against 69.1 TFLOP/s at 8192^3 and no gain inside the
+    // factorization -- the tensor pipe runs INT8 at ~4600 MAC per cycle and SM for N = 64 and N = 128 alike -- so the single-pass
+    // 128 x 64 kernel stays the default)
+    CUtensorMap aLo, bLo, aHi, bHi;
+    if (!oz_make_map_k(&aLo, pa, Kp, (uint64_t)Ra, S, OzWinLo::PL, OZ_BM, 32) || !oz_make_map_k(&bLo, pb, Kp, (uint64_t)Rb, S, OzWinLo::PL, 128, 32) ||
+        !oz_make_map_k(&aHi, pa, Kp, (uint64_t)Ra, S, OzWinHi::PL, OZ_BM, 64) || !oz_make_map_k(&bHi, pb, Kp, (uint64_t)Rb, S, OzWinHi::PL, 128, 64))
+      return cudaErrorInvalidValue;
+    dim3 grid2(M / OZ_BM, N / 128);
+    oz_gemm_win_kernel<8, 128, 32, 6, 9><<<grid2, OZ_THREADS, OzWinLo::SMEM, st>>>(p, aLo, bLo);     // low-order diagonals first: C = ... + beta C
+    OzParams p2 = p;
+    p2.beta = 1.0;
+    oz_gemm_win_kernel<8, 128, 64, 2, 5><<<grid2, OZ_THREADS, OzWinHi::SMEM, st>>>(p2, aHi, bHi);    // high-order diagonals accumulate
+    return cudaGetLastError();
+  }
   dim3 grid(M / OZ_BM, N / OZ_BN);
   if (S == 8) oz_gemm_kernel<8><<<grid, OZ_THREADS, oz_smem_bytes(8), st>>>(p, mA, mB);
   else if (S == 7) oz_gemm_kernel<7><<<grid, OZ_THREADS, oz_smem_bytes(7), st>>>(p, mA, mB);

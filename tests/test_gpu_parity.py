@@ -748,6 +748,29 @@ def test_mgpu_rank_count_independence_n8192(gpr):
         assert grad_err(Gd, G1) <= 1e-9, (G, nb, grad_err(Gd, G1))
 
 
+@pytest.mark.parametrize("G", [1, 2, 3])
+def test_mgpu_potrf_on_int8_tensor_cores_vs_oracle(gpr, G):
+    """The rank-nb trailing updates of the block-cyclic potrf (csrc/dist_blocked.hpp) through the INT8-tensor-core product
+    (tile-mapped form of csrc/ozaki_i8.cuh; nb = 1024 so that K = nb reaches the route) against the committed oracle values
+    of config 2 (N = 8192, D = 8, SquaredExp()+WhiteNoise(), set A), forced on and in automatic mode."""
+    from gpr_sm100a import _ffi
+    mg2 = _load_module("mg2", "make_golden_config2.py")
+    x, y, sets = mg2.inputs()
+    g = np.load(os.path.join(HERE, "golden", "config2_n8192.npz"))
+    hp = sets["A"]
+    for forced in (8, -1, 0):
+        mc = _ffi.MultiContext(_devices(G), nb=1024)
+        mc.set_option("ozaki", forced)
+        mm = _ffi.MultiModelHandle(mc, [1, 2], 8, x, y)
+        l0 = mc.launch_count()
+        F, Gd = mm.nlml_grad(hp)
+        nl = mc.launch_count() - l0
+        mm.close(); mc.close()
+        relF, relG = abs(F - float(g["F_A"])) / abs(float(g["F_A"])), grad_err(Gd, g["G_A"])
+        print(f"\nmgpu potrf, G={G}, ozaki={forced}: relF {relF:.2e} relG {relG:.2e} ({nl} launches)")
+        assert relF <= TOL_F and relG <= TOL_G
+
+
 # ------------------------------------------------------------------ (6) SURVEY.md 8f "next" rows on the device
 def test_update_sample_matches_oracle(gpr):
     """update_sample!(md, dy, BFGSQuad(), MarginalLikelihood(), eps_J) (src/update_model.jl:6-48, test/test_update.jl:50-76):
