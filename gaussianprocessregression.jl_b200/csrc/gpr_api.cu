@@ -66,11 +66,14 @@ struct gpr_ctx {
                                 // DMMA otherwise; "ozaki_min": smallest M, N, K routed there
   int oz_active = 0;            // digits in force for the model being worked on (set by the entry points)
   int64_t ozaki_min = 1024;
-  int ozaki_windows = 0;        // option "ozaki_windows": two-diagonal-window 128 x 128 kernel for the INT8 products (csrc/ozaki_i8.cuh)
-  int64_t ozaki_panel = 4096;   // option "ozaki_panel": k-panel of the W^T W product (own digit scales per panel)
-  int oz_mask = 11, oz_cur = 8;   // option "ozaki_phases": bit 0 potrf, 1 trtri, 2 lauum (W^T W), 3 everything else (prediction solves).
-                                  // Default without W^T W: its operand columns span many orders of magnitude and one power-of-two scale per
-                                  // column costs the gradient three digits (1e-7 vs the oracle against 6e-11), profiles/README.md
+  int ozaki_lauum = 9;          // option "ozaki_lauum": digits of the INT8 route for the W^T W product of the inverse (0 = DMMA, 8, 9 = default)
+  int ozaki_windows = 2;        // option "ozaki_windows": bit 0 two-diagonal-window 128 x 128 kernel for the 8-digit products, bit 1 128 x 256
+                                // tiles for the tenth diagonal of the 9-digit product (csrc/ozaki_i8.cuh)
+  int64_t ozaki_panel = 32768;  // option "ozaki_panel": k-panel of the W^T W product (own digit scales per panel)
+  int oz_mask = 11, oz_cur = 8;   // option "ozaki_phases": bit 0 potrf, 1 trtri, 3 everything else (prediction solves); the W^T W product of the
+                                  // inverse (lauum) is governed by "ozaki_lauum": its operand columns span many orders of magnitude under ONE
+                                  // power-of-two scale per column, and with 8 digits the gradient keeps only 7 digits (1.1e-7 vs the oracle);
+                                  // NINE digits restore it (4.0e-11, DMMA: 6.1e-11 at N = 32768; profiles/ozaki_lauum9_r2s.log)
   void* oz_ws = nullptr; size_t oz_ws_bytes = 0;
   int gemm_tma = 1;             // option "gemm_tma": T,N products through the TMA-fed kernel (csrc/dgemm_tma.cuh)
   int kbuild_gram = 1;          // option "kbuild_gram": TMA-fed Gram-form covariance build (csrc/kbuild_tma.cuh); 0 = direct-difference kernel
@@ -108,7 +111,8 @@ struct CudaBE {
   void note(cudaError_t e) { if (e != cudaSuccess && ctx->pending == cudaSuccess) ctx->pending = e; }
   bool ozaki_eligible(char tA, char tB, int64_t M, int64_t N, int64_t K, const double* A, const double* B, const double* C, int flags,
                       int64_t batch) const {
-    if (ctx->oz_active <= 0 || ctx->stream != ctx->main_stream || !(ctx->oz_mask & ctx->oz_cur)) return false;
+    if (ctx->oz_active <= 0 || ctx->stream != ctx->main_stream) return false;
+    if (ctx->oz_cur == 4 ? ctx->ozaki_lauum == 0 : !(ctx->oz_mask & ctx->oz_cur)) return false;
     if (tA != 'T' || tB != 'N') return false;
     if (flags & ~(BLK_UPPER_ONLY | BLK_K_FROM_N | BLK_SKIP_TILE00)) return false;
     if ((const double*)C == A || (const double*)C == B) return false;
@@ -122,7 +126,8 @@ struct CudaBE {
     // grid.z is limited to 65535: split very large batches
     if (ozaki_eligible(tA, tB, M, N, K, A, B, C, flags, batch)) {
       // large T,N product: INT8 tensor cores (csrc/ozaki_i8.cuh), one launch per batch member
-      const size_t need = oz_workspace_bytes((int)std::max(M, N), (int)N, (int)K, ctx->oz_active);
+      const int digits = ctx->oz_cur == 4 ? ctx->ozaki_lauum : ctx->oz_active;
+      const size_t need = oz_workspace_bytes((int)std::max(M, N), (int)N, (int)K, digits);
       if (need > ctx->oz_ws_bytes) {
         cudaStreamSynchronize(ctx->main_stream);
         cudaFree(ctx->oz_ws); ctx->oz_ws = nullptr; ctx->oz_ws_bytes = 0;
@@ -139,16 +144,16 @@ struct CudaBE {
         for (int64_t p1 = K; p1 > 0; p1 -= P) {
           const int64_t p0 = std::max<int64_t>(0, p1 - P);
           const int64_t cols = std::min<int64_t>(N, p1);
-          note(launch_ozaki_dgemm(ctx->stream, (int)cols, (int)cols, (int)(p1 - p0), ctx->oz_active, alpha, A + p0, lda, B + p0, ldb,
-                                  p1 == K ? beta : 1.0, C, ldc, flags, ctx->oz_ws, (int)p0));
+          note(launch_ozaki_dgemm(ctx->stream, (int)cols, (int)cols, (int)(p1 - p0), digits, alpha, A + p0, lda, B + p0, ldb,
+                                  p1 == K ? beta : 1.0, C, ldc, flags | ((ctx->ozaki_windows & 2) ? 1024 : 0), ctx->oz_ws, (int)p0));
           ctx->launches += 2;
         }
         return;
       }
       if (ctx->oz_ws_bytes >= need) {
         for (int64_t z = 0; z < batch; ++z) {
-          note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, ctx->oz_active, alpha, A + z * sA, lda, B + z * sB, ldb, beta, C + z * sC, ldc,
-                                  flags | (ctx->ozaki_windows ? 512 : 0), ctx->oz_ws));
+          note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, digits, alpha, A + z * sA, lda, B + z * sB, ldb, beta, C + z * sC, ldc,
+                                  flags | ((ctx->ozaki_windows & 1) ? 512 : 0) | ((ctx->ozaki_windows & 2) ? 1024 : 0), ctx->oz_ws));
           ctx->launches += 3;
         }
         return;
@@ -649,6 +654,7 @@ int gpr_ctx_create(int device, gpr_ctx** out) {
   }
   if (const char* ev = getenv("GPR_OZAKI_MIN")) ctx->ozaki_min = std::max<int64_t>(128, atoll(ev));
   if (const char* ev = getenv("GPR_OZAKI_PHASES")) ctx->oz_mask = atoi(ev) & 15;
+  if (const char* ev = getenv("GPR_OZAKI_LAUUM")) { const int v = atoi(ev); if (v == 0 || v == 8 || v == 9) ctx->ozaki_lauum = v; }
   e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
@@ -693,7 +699,11 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
       return fail(ctx, GPR_ERR_ARG, "ozaki: number of digits must be -1 (automatic), 0 (off), 6, 7 or 8");
     ctx->ozaki = (int)value; ctx->oz_active = value > 0 ? (int)value : 0; return GPR_OK;
   }
-  if (!strcmp(name, "ozaki_windows")) { ctx->ozaki_windows = value ? 1 : 0; return GPR_OK; }
+  if (!strcmp(name, "ozaki_lauum")) {
+    if (value != 0 && value != 8 && value != 9) return fail(ctx, GPR_ERR_ARG, "ozaki_lauum: 0 (DMMA), 8 or 9 digits");
+    ctx->ozaki_lauum = (int)value; return GPR_OK;
+  }
+  if (!strcmp(name, "ozaki_windows")) { ctx->ozaki_windows = (int)value & 3; return GPR_OK; }
   if (!strcmp(name, "ozaki_panel")) { ctx->ozaki_panel = std::max<int64_t>(128, (value / 128) * 128); return GPR_OK; }
   if (!strcmp(name, "ozaki_phases")) { ctx->oz_mask = (int)value & 15; return GPR_OK; }
   if (!strcmp(name, "ozaki_min")) { ctx->ozaki_min = std::max<int64_t>(128, value); return GPR_OK; }

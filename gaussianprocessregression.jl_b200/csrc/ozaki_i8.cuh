@@ -329,7 +329,7 @@ template <int S, int BN, int BK, int DLO, int DHI> struct OzWin {
   static constexpr int NACC = DHI - DLO + 1;
   static constexpr int PL = (DHI - 1 < S) ? DHI - 1 : S;                  // digit planes needed
   static constexpr size_t STAGE = (size_t)PL * (OZ_BM + BN) * BK;
-  static constexpr int NST = (int)((200 * 1024) / STAGE) > 4 ? 4 : (int)((200 * 1024) / STAGE);
+  static constexpr int NST = (int)(231000 / STAGE) > 4 ? 4 : (int)(231000 / STAGE);      // 227 KB of shared memory per CTA
   static constexpr size_t SMEM = NST * STAGE + 1024 + 256;
   static constexpr unsigned IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(OZ_BM >> 4) << 24);
   static_assert(NACC * BN <= 512, "accumulators exceed TMEM");
@@ -371,8 +371,9 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
     tile_m = first_m + rem % gsize;
     tile_n = rem / gsize;
   }
-  const int blk_n = (tile_n * BN) >> 7;
-  if ((p.flags & 1) && tile_m > blk_n) return;
+  const int blk_n = (tile_n * BN) >> 7;                       // first 128-block of the tile's columns (BN = 256 spans two)
+  if (tile_n * BN >= p.N) return;
+  if ((p.flags & 1) && tile_m > ((tile_n * BN + BN - 1) >> 7)) return;
   if ((p.flags & 64) && tile_m == 0 && blk_n == 0) return;
   int gt = 0;
   if (p.flags & 8) {
@@ -451,11 +452,15 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
     const int q = warp & 3;
     const int row = 32 * q + lane;
     const unsigned lane_addr = tmem_base + ((unsigned)(32 * q) << 16);
-    const bool diag_tile = ((p.flags & 1) && (tile_m == blk_n)) || ((p.flags & 8) && (p.row_gtile0 + tile_m == gt));
+    // rows below the diagonal of a diagonal tile stay untouched: local product (flag 1) by global index, tile-mapped form
+    // (flag 8, BN <= 128 only) by the position inside the 128-block
+    const bool diag_local = (p.flags & 1) && !(p.flags & 8) && (tile_m >= blk_n);
+    const bool diag_map = (p.flags & 8) && (p.row_gtile0 + tile_m == gt);
     const int coff = n0 & 127;
     const double sa = p.scaleA[m0 + row] * p.alpha;
     double* Crow = p.C + (long long)(m0 + row) + (long long)n0 * p.ldc;
     for (int c0 = 0; c0 < BN; c0 += 16) {
+      if (n0 + c0 >= p.N) break;
       double acc[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = 0.0;
@@ -475,7 +480,8 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int col = c0 + j;
-        if (diag_tile && row > col + coff) continue;
+        if (diag_local && m0 + row > n0 + col) continue;
+        if (diag_map && row > col + coff) continue;
         double* cp = Crow + (long long)col * p.ldc;
         const double r = acc[j] * sa * p.scaleB[n0 + col];
         *cp = (p.beta != 0.0) ? fma(p.beta, *cp, r) : r;
@@ -519,10 +525,14 @@ inline bool oz_make_map_k(CUtensorMap* map, const int8_t* base, uint64_t Kp, uin
 }
 using OzWinLo = OzWin<8, 128, 32, 6, 9>;
 using OzWinHi = OzWin<8, 128, 64, 2, 5>;
+using OzWin9X = OzWin<9, 128, 32, 10, 10>;    // ninth digit: the extra diagonal d = 10 (pairs (1,9) .. (9,1))
+using OzWin9Y = OzWin<9, 256, 32, 10, 10>;    // the same with 128 x 256 tiles (one accumulator of 256 columns): 25% fewer operand bytes per product
 
 inline cudaError_t oz_set_attr() {
   cudaError_t e = cudaFuncSetAttribute(oz_gemm_win_kernel<8, 128, 32, 6, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWinLo::SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<8, 128, 64, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWinHi::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<9, 128, 32, 10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWin9X::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<9, 256, 32, 10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWin9Y::SMEM);
   if (e == cudaSuccess) e = oz_set_attr_s<8>();
   if (e == cudaSuccess) e = oz_set_attr_s<7>();
   if (e == cudaSuccess) e = oz_set_attr_s<6>();
@@ -543,7 +553,7 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
                                       long long ldb, double beta, double* C, long long ldc, int flags, void* workspace, int k_off = 0,
                                       const int* col_gtile = nullptr, int row_gtile0 = 0) {
   if ((flags & 8) && !col_gtile) return cudaErrorInvalidValue;
-  if ((S != 8 && S != 7 && S != 6 && S != 2) || (M % OZ_BM) || (N % 128) || (K % 128) || K > 32768) return cudaErrorInvalidValue;
+  if ((S != 9 && S != 8 && S != 7 && S != 6 && S != 2) || (M % OZ_BM) || (N % 128) || (K % 128) || K > 32768) return cudaErrorInvalidValue;
   const size_t Kp = (size_t)K;
   const bool shared = (A == B && lda == ldb);
   const int kfrom = (flags & 2) ? 1 : 0;
@@ -559,7 +569,29 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
   if (!shared) oz_slice_kernel<<<(N + 7) / 8, 256, 0, st>>>(B, ldb, K, N, S, pb, (long long)Kp, N, sb, kfrom, k_off);
   CUtensorMap mA, mB;
   if (!oz_make_map(&mA, pa, Kp, (uint64_t)Ra, S, OZ_BM) || !oz_make_map(&mB, pb, Kp, (uint64_t)Rb, S, OZ_BN)) return cudaErrorInvalidValue;
-  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~512, k_off, col_gtile, row_gtile0};
+  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~(512 | 1024), k_off, col_gtile, row_gtile0};
+  if (S == 9) {
+    // nine digits (products whose operands span several orders of magnitude under one scale per column: the W^T W of the inverse):
+    // three diagonal windows, lowest order first -- d = 10 (9 pairs, all nine planes), d = 6..9 (26 pairs), d = 2..5 (10 pairs)
+    CUtensorMap aX, bX, aLo, bLo, aHi, bHi;
+    if (!oz_make_map_k(&aX, pa, Kp, (uint64_t)Ra, S, OzWin9X::PL, OZ_BM, 32) || !oz_make_map_k(&bX, pb, Kp, (uint64_t)Rb, S, OzWin9X::PL, 128, 32) ||
+        !oz_make_map_k(&aLo, pa, Kp, (uint64_t)Ra, S, OzWinLo::PL, OZ_BM, 32) || !oz_make_map_k(&bLo, pb, Kp, (uint64_t)Rb, S, OzWinLo::PL, 128, 32) ||
+        !oz_make_map_k(&aHi, pa, Kp, (uint64_t)Ra, S, OzWinHi::PL, OZ_BM, 64) || !oz_make_map_k(&bHi, pb, Kp, (uint64_t)Rb, S, OzWinHi::PL, 128, 64))
+      return cudaErrorInvalidValue;
+    dim3 grid2(M / OZ_BM, N / 128);
+    if ((flags & 1024) && !(flags & (8 | 64))) {
+      CUtensorMap bY;
+      if (!oz_make_map_k(&bY, pb, Kp, (uint64_t)Rb, S, OzWin9Y::PL, 256, 32)) return cudaErrorInvalidValue;
+      oz_gemm_win_kernel<9, 256, 32, 10, 10><<<dim3(M / OZ_BM, (N + 255) / 256), OZ_THREADS, OzWin9Y::SMEM, st>>>(p, aX, bY);
+    } else {
+      oz_gemm_win_kernel<9, 128, 32, 10, 10><<<grid2, OZ_THREADS, OzWin9X::SMEM, st>>>(p, aX, bX);
+    }
+    OzParams p2 = p;
+    p2.beta = 1.0;
+    oz_gemm_win_kernel<8, 128, 32, 6, 9><<<grid2, OZ_THREADS, OzWinLo::SMEM, st>>>(p2, aLo, bLo);
+    oz_gemm_win_kernel<8, 128, 64, 2, 5><<<grid2, OZ_THREADS, OzWinHi::SMEM, st>>>(p2, aHi, bHi);
+    return cudaGetLastError();
+  }
   if (S == 8 && (flags & 512)) {
     // two diagonal windows, 128 x 128 tiles (flag 512; measured 73.5 against 69.1 TFLOP/s at 8192^3 and no gain inside the
     // factorization -- the tensor pipe runs INT8 at ~4600 MAC per cycle and SM for N = 64 and N = 128 alike -- so the single-pass

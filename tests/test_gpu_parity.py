@@ -461,10 +461,52 @@ def test_ozaki_int8_gemm_is_an_fp64_product(gpr):
         ctx.close()
 
 
+def test_ozaki_nine_digit_product(gpr):
+    """The W^T W product of the inverse takes NINE digits (csrc/ozaki_i8.cuh: three diagonal windows d = 10 | 6..9 | 2..5, 45
+    integer products): on operands whose entries span many orders of magnitude under one scale per column it must be at least
+    16x closer to the exact product than the 8-digit form, equal the 128 x 256-tile variant of the tenth diagonal to rounding, and
+    honour upper-only / K-from-N (lauum_oop_t's flags) on a size whose last 256-wide tile is half outside."""
+    from gpr_sm100a import _ffi
+    rng = np.random.default_rng(77)
+    ctx = gpr.Context(0)
+    try:
+        K, M = 1024, 640
+        A = np.asfortranarray(rng.standard_normal((K, M)) * np.exp(rng.uniform(-14, 0, (K, M))))
+        ref = (A.astype(np.longdouble).T @ A.astype(np.longdouble))
+        den = np.abs(A).T @ np.abs(A)
+        err = {}
+        for S, fl in ((8, 0), (9, 0), (9, 1024)):
+            Cm, _ = _ffi.dbg_ozaki_dgemm(ctx, 1.0, A, A, 0.0, np.zeros((M, M)), S=S, flags=fl)
+            err[(S, fl)] = float(np.max(np.abs(Cm - ref) / den))
+        print(f"\nW^T W with 6 decades inside a column: err/(|A|^T|A|) 8 digits {err[(8, 0)]:.2e}, 9 digits {err[(9, 0)]:.2e}, 9 digits 128x256 {err[(9, 1024)]:.2e}")
+        assert err[(9, 0)] < 2e-15 and err[(9, 1024)] < 2e-15
+        assert err[(9, 0)] * 16 <= err[(8, 0)] or err[(8, 0)] < 1e-15
+        # lauum_oop_t's form: lower-triangular operand (garbage above the diagonal blocks), upper triangle of C only
+        Kt = 640
+        L = np.tril(rng.standard_normal((Kt, Kt))) + 4 * np.eye(Kt)
+        G = L.copy()
+        for J in range(Kt // 128):
+            G[:128 * J, 128 * J:128 * (J + 1)] = 1e30
+        G = np.asfortranarray(G)
+        reft = L.astype(np.longdouble).T @ L.astype(np.longdouble)
+        dent = np.abs(L).T @ np.abs(L)
+        C0 = np.asfortranarray(rng.standard_normal((Kt, Kt)))
+        for fl in (3, 3 | 1024):
+            Cm, _ = _ffi.dbg_ozaki_dgemm(ctx, 1.0, np.asfortranarray(L), G, 0.0, C0, S=9, flags=fl)      # separate operands: only op(B) is masked
+            up = np.triu(np.ones((Kt, Kt), dtype=bool))
+            e = float(np.max((np.abs(Cm - reft) / dent)[up]))
+            print(f"L^T L, K-from-N + upper-only, flags {fl}: err {e:.2e}")
+            assert e < 2e-15
+            assert np.array_equal(Cm[~up], C0[~up])
+    finally:
+        ctx.close()
+
+
 def test_ozaki_route_keeps_nlml_parity(gpr):
-    """The optional INT8-tensor-core route of the blocked factorization (ctx option "ozaki" = 8 digits; potrf, trtri and
-    the prediction solves, not the W^T W product) against the oracle on a model large enough that its top-level products
-    are routed there (ozaki_min = 512): same tolerances as the DMMA path (src/cost.jl:96-127, src/predict.jl:83-95)."""
+    """The INT8-tensor-core route of the blocked factorization (ctx option "ozaki" = 8 digits for potrf, trtri and the
+    prediction solves; "ozaki_lauum" = 9 digits for the W^T W product of the inverse) against the oracle on a model large
+    enough that its top-level products are routed there (ozaki_min = 512): same tolerances as the DMMA path
+    (src/cost.jl:96-127, src/predict.jl:83-95)."""
     from gpr_sm100a import _ffi
     rng = np.random.default_rng(4242)
     D, N = 8, 4096
@@ -492,8 +534,19 @@ def test_ozaki_route_keeps_nlml_parity(gpr):
               f"INT8 relF {res[8][0]:.1e} relG {res[8][1]:.1e} mean {res[8][2]:.1e} var {res[8][3]:.1e}")
         assert res[8][0] <= TOL_F and res[8][1] <= TOL_G and res[8][2] <= TOL_MU and res[8][3] <= TOL_VAR
         assert res[8][4] != res[0][4]          # the route was actually taken (different launch count)
+        # the inverse's W^T W on DMMA instead: fewer INT8 launches, same parity
+        ctx.set_option("ozaki", 8)
+        ctx.set_option("ozaki_lauum", 0)
+        mh = _ffi.ModelHandle(ctx, [1, 1, 2], D, np.asfortranarray(x), y)
+        l0 = ctx.launch_count()
+        F, G = mh.nlml_grad(hp)
+        mu, var, _ = mh.predict(xp, want_var=True)
+        assert ctx.launch_count() - l0 != res[8][4]
+        assert abs(F - Fo) / abs(Fo) <= TOL_F and grad_err(G, Go) <= TOL_G
+        mh.close()
     finally:
         ctx.set_option("ozaki", 0)
+        ctx.set_option("ozaki_lauum", 9)
         ctx.close()
 
 
