@@ -698,23 +698,31 @@ def run_gpu(args, rank, world, local_rank):
     except Exception:
         pass
     # INT8-tensor-core route, isolated: FP64-equivalent rate of one 8192^3 product incl. the digit extraction
-    oz_tf = None
+    oz_tf, oz9_tf = None, None
     try:
         An = np.asfortranarray(np.random.default_rng(1).standard_normal((8192, 8192)))
         _, oz_ms = _ffi.dbg_ozaki_dgemm(ctx, 1.0, An, An, 0.0, np.zeros((8192, 8192), order="F"), S=8, reps=4)
         oz_tf = 2 * 8192 ** 3 / oz_ms / 1e9
+        _, oz9_ms = _ffi.dbg_ozaki_dgemm(ctx, 1.0, An, An, 0.0, np.zeros((8192, 8192), order="F"), S=9, flags=0, reps=4)
+        oz9_tf = 2 * 8192 ** 3 / oz9_ms / 1e9
         del An
     except Exception:
         pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": fp64_sust, "unit": "TFLOP/s", "frac": achieved / fp64_sust,
                 "note": "achieved = N^3 FP64-equivalent flop / (potrf + trtri + lauum) ms.  peak = the FP64 (DMMA) roof as measured through cuBLAS DGEMM; "
-                        "the large products of potrf and trtri run on the INT8 tensor cores (tcgen05.mma kind::i8, 36 exact integer products per FP64 "
-                        "product, csrc/ozaki_i8.cuh), which is how frac can exceed the FP64 pipe: extra.dmma_only holds the same step on the DMMA pipe alone",
-                "int8_route": {"fp64_equivalent_tflops_8192": oz_tf, "int8_pops": (oz_tf * 36 / 1e3) if oz_tf else None, "int8_peak_pops_nominal": 4.5,
-                               "frac_of_nominal_int8": (oz_tf * 36 / 4500.0) if oz_tf else None,
-                               "note": "MEASURED_PEAKS.json holds no INT8 figure (bf16 1630 TFLOP/s burst measured); 4.5 POPS is NVIDIA's dense INT8 figure for B200"},
+                        "the large products of potrf, trtri (8 digits: 36 exact integer products per FP64 product) and of the inverse's W^T W "
+                        "(9 digits: 45) run on the INT8 tensor cores (tcgen05.mma kind::i8, csrc/ozaki_i8.cuh), which is how frac can exceed the "
+                        "FP64 pipe: extra.dmma_only holds the same step on the DMMA pipe alone",
+                "int8_route": {"fp64_equivalent_tflops_8192": oz_tf, "fp64_equivalent_tflops_8192_nine_digits": oz9_tf,
+                               "int8_pops": (oz_tf * 36 / 1e3) if oz_tf else None, "int8_pops_nine_digits": (oz9_tf * 45 / 1e3) if oz9_tf else None,
+                               "int8_peak_pops_nominal": 4.5, "frac_of_nominal_int8": (oz_tf * 36 / 4500.0) if oz_tf else None,
+                               "int8_peak_pops_from_measured_bf16": (2e-3 * hp_peak["bf16_tflops"]) if hp_peak and hp_peak.get("bf16_tflops") else None,
+                               "frac_of_measured_scaled_int8": (oz_tf * 36 / (2.0 * hp_peak["bf16_tflops"])) if oz_tf and hp_peak and hp_peak.get("bf16_tflops") else None,
+                               "note": "MEASURED_PEAKS.json holds no INT8 figure; 4.5 POPS is NVIDIA's dense INT8 figure for B200, and twice the "
+                                       "measured bf16 burst rate of MEASURED_PEAKS.json is the rate the same tensor pipe can be expected to sustain "
+                                       "on this pool (bf16 measured: 0.72 of its nominal 2.25 PFLOP/s)"},
                 "traffic": traffic, "traffic_unit": "GB of DRAM read+write by all product kernels (DMMA GEMMs, INT8 GEMM, digit extraction) of one step (ncu launch list, profiles/dram_traffic.json)",
-                "kernel": "dgemm128_tma_kernel (DMMA) + oz_gemm_kernel (INT8 tensor cores) inside blocked potrf+trtri+lauum: N^3 FP64-equivalent flop per step / (potrf+trtri+lauum) CUDA-event ms",
+                "kernel": "oz_gemm_kernel / oz_gemm_win_kernel (INT8 tensor cores) + dgemm128_tma_kernel (DMMA, the products below 1024) inside blocked potrf+trtri+lauum: N^3 FP64-equivalent flop per step / (potrf+trtri+lauum) CUDA-event ms",
                 "peak_source": f"cuBLAS DGEMM 8192^3 via torch.matmul, sustained {fp64_sust:.1f} / burst {fp64_burst:.1f} TFLOP/s measured in this run "
                                "(MEASURED_PEAKS.json holds no FP64 figure" + (f"; its HBM copy figure is {hp_peak.get('hbm_gbs')} GB/s)" if hp_peak else ")"),
                 "kernel_isolated_tflops": gemm_tf, "kernel_isolated_frac": gemm_tf / fp64_burst}

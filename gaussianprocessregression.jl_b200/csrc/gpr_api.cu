@@ -67,8 +67,9 @@ struct gpr_ctx {
   int oz_active = 0;            // digits in force for the model being worked on (set by the entry points)
   int64_t ozaki_min = 1024;
   int ozaki_lauum = 9;          // option "ozaki_lauum": digits of the INT8 route for the W^T W product of the inverse (0 = DMMA, 8, 9 = default)
-  int ozaki_windows = 2;        // option "ozaki_windows": bit 0 two-diagonal-window 128 x 128 kernel for the 8-digit products, bit 1 128 x 256
-                                // tiles for the tenth diagonal of the 9-digit product (csrc/ozaki_i8.cuh)
+  int ozaki_windows = 0;        // option "ozaki_windows" (A/B switches of csrc/ozaki_i8.cuh): bit 0 two-diagonal-window 128 x 128 kernel for the
+                                // 8-digit products; bit 2 the THREE-window form of the 9-digit product (d = 10 | 6..9 | 2..5) instead of the
+                                // default two windows (d = 6..10 with 128 x 96 tiles | 2..5), bit 1 with it: 128 x 256 tiles for d = 10
   int64_t ozaki_panel = 32768;  // option "ozaki_panel": k-panel of the W^T W product (own digit scales per panel)
   int oz_mask = 11, oz_cur = 8;   // option "ozaki_phases": bit 0 potrf, 1 trtri, 3 everything else (prediction solves); the W^T W product of the
                                   // inverse (lauum) is governed by "ozaki_lauum": its operand columns span many orders of magnitude under ONE
@@ -145,7 +146,7 @@ struct CudaBE {
           const int64_t p0 = std::max<int64_t>(0, p1 - P);
           const int64_t cols = std::min<int64_t>(N, p1);
           note(launch_ozaki_dgemm(ctx->stream, (int)cols, (int)cols, (int)(p1 - p0), digits, alpha, A + p0, lda, B + p0, ldb,
-                                  p1 == K ? beta : 1.0, C, ldc, flags | ((ctx->ozaki_windows & 2) ? 1024 : 0), ctx->oz_ws, (int)p0));
+                                  p1 == K ? beta : 1.0, C, ldc, flags | ((ctx->ozaki_windows & 2) ? 1024 : 0) | ((ctx->ozaki_windows & 4) ? 4096 : 0), ctx->oz_ws, (int)p0));
           ctx->launches += 2;
         }
         return;
@@ -153,7 +154,7 @@ struct CudaBE {
       if (ctx->oz_ws_bytes >= need) {
         for (int64_t z = 0; z < batch; ++z) {
           note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, digits, alpha, A + z * sA, lda, B + z * sB, ldb, beta, C + z * sC, ldc,
-                                  flags | ((ctx->ozaki_windows & 1) ? 512 : 0) | ((ctx->ozaki_windows & 2) ? 1024 : 0), ctx->oz_ws));
+                                  flags | ((ctx->ozaki_windows & 1) ? 512 : 0) | ((ctx->ozaki_windows & 2) ? 1024 : 0) | ((ctx->ozaki_windows & 4) ? 4096 : 0), ctx->oz_ws));
           ctx->launches += 3;
         }
         return;
@@ -703,7 +704,7 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
     if (value != 0 && value != 8 && value != 9) return fail(ctx, GPR_ERR_ARG, "ozaki_lauum: 0 (DMMA), 8 or 9 digits");
     ctx->ozaki_lauum = (int)value; return GPR_OK;
   }
-  if (!strcmp(name, "ozaki_windows")) { ctx->ozaki_windows = (int)value & 3; return GPR_OK; }
+  if (!strcmp(name, "ozaki_windows")) { ctx->ozaki_windows = (int)value & 7; return GPR_OK; }
   if (!strcmp(name, "ozaki_panel")) { ctx->ozaki_panel = std::max<int64_t>(128, (value / 128) * 128); return GPR_OK; }
   if (!strcmp(name, "ozaki_phases")) { ctx->oz_mask = (int)value & 15; return GPR_OK; }
   if (!strcmp(name, "ozaki_min")) { ctx->ozaki_min = std::max<int64_t>(128, value); return GPR_OK; }

@@ -92,6 +92,9 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
   }
 }
 
+// (A variant with the column spread over up to 1024 threads so that the second pass hits L2 -- the launch list shows 42.9 GB read
+// for 21.5 GB written per evaluation -- measured SLOWER: 16.5 vs 16.1 ms per 8192^3 product, evaluation +7 ms; removed.)
+
 // ---------------------------------------------------------------------------------------------------------------
 // tcgen05 primitives
 // ---------------------------------------------------------------------------------------------------------------
@@ -526,6 +529,7 @@ inline bool oz_make_map_k(CUtensorMap* map, const int8_t* base, uint64_t Kp, uin
 using OzWinLo = OzWin<8, 128, 32, 6, 9>;
 using OzWinHi = OzWin<8, 128, 64, 2, 5>;
 using OzWin9X = OzWin<9, 128, 32, 10, 10>;    // ninth digit: the extra diagonal d = 10 (pairs (1,9) .. (9,1))
+using OzWin9Z = OzWin<9, 96, 32, 6, 10>;      // nine digits in TWO windows: d = 6..10 in five 96-column accumulators (480 TMEM columns, 35 pairs)
 using OzWin9Y = OzWin<9, 256, 32, 10, 10>;    // the same with 128 x 256 tiles (one accumulator of 256 columns): 25% fewer operand bytes per product
 
 inline cudaError_t oz_set_attr() {
@@ -533,6 +537,7 @@ inline cudaError_t oz_set_attr() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<8, 128, 64, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWinHi::SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<9, 128, 32, 10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWin9X::SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<9, 256, 32, 10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWin9Y::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<9, 96, 32, 6, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWin9Z::SMEM);
   if (e == cudaSuccess) e = oz_set_attr_s<8>();
   if (e == cudaSuccess) e = oz_set_attr_s<7>();
   if (e == cudaSuccess) e = oz_set_attr_s<6>();
@@ -569,16 +574,30 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
   if (!shared) oz_slice_kernel<<<(N + 7) / 8, 256, 0, st>>>(B, ldb, K, N, S, pb, (long long)Kp, N, sb, kfrom, k_off);
   CUtensorMap mA, mB;
   if (!oz_make_map(&mA, pa, Kp, (uint64_t)Ra, S, OZ_BM) || !oz_make_map(&mB, pb, Kp, (uint64_t)Rb, S, OZ_BN)) return cudaErrorInvalidValue;
-  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~(512 | 1024), k_off, col_gtile, row_gtile0};
+  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~(512 | 1024 | 4096), k_off, col_gtile, row_gtile0};
   if (S == 9) {
-    // nine digits (products whose operands span several orders of magnitude under one scale per column: the W^T W of the inverse):
-    // three diagonal windows, lowest order first -- d = 10 (9 pairs, all nine planes), d = 6..9 (26 pairs), d = 2..5 (10 pairs)
+    // nine digits (products whose operands span several orders of magnitude under one scale per column: the W^T W of the inverse).
+    // Nine 64-column accumulators do not fit the 512 TMEM columns, so the diagonals are summed in windows, lowest order first, each
+    // launch accumulating into C.  Default: TWO windows -- d = 6..10 in five 96-column accumulators (35 pairs, 128 x 96 tiles), then
+    // d = 2..5 (10 pairs, 128 x 128 tiles): 19.4 ms at 8192^3.  Flag 4096: three windows d = 10 | 6..9 | 2..5 (24.3 ms; ncu, profiles/
+    // ozaki_ncu_full_r2t.md: the d = 10 window moves all nine planes for nine products and sits at 93 % of the L2 -> SM fill rate)
     CUtensorMap aX, bX, aLo, bLo, aHi, bHi;
     if (!oz_make_map_k(&aX, pa, Kp, (uint64_t)Ra, S, OzWin9X::PL, OZ_BM, 32) || !oz_make_map_k(&bX, pb, Kp, (uint64_t)Rb, S, OzWin9X::PL, 128, 32) ||
         !oz_make_map_k(&aLo, pa, Kp, (uint64_t)Ra, S, OzWinLo::PL, OZ_BM, 32) || !oz_make_map_k(&bLo, pb, Kp, (uint64_t)Rb, S, OzWinLo::PL, 128, 32) ||
         !oz_make_map_k(&aHi, pa, Kp, (uint64_t)Ra, S, OzWinHi::PL, OZ_BM, 64) || !oz_make_map_k(&bHi, pb, Kp, (uint64_t)Rb, S, OzWinHi::PL, 128, 64))
       return cudaErrorInvalidValue;
     dim3 grid2(M / OZ_BM, N / 128);
+    if (!(flags & 4096) && !(flags & (8 | 64))) {
+      // two windows: d = 6..10 with 128 x 96 tiles (the last column tile is partial: TMA zero fill, masked epilogue), then d = 2..5
+      CUtensorMap aZ, bZ;
+      if (!oz_make_map_k(&aZ, pa, Kp, (uint64_t)Ra, S, OzWin9Z::PL, OZ_BM, 32) || !oz_make_map_k(&bZ, pb, Kp, (uint64_t)Rb, S, OzWin9Z::PL, 96, 32))
+        return cudaErrorInvalidValue;
+      oz_gemm_win_kernel<9, 96, 32, 6, 10><<<dim3(M / OZ_BM, (N + 95) / 96), OZ_THREADS, OzWin9Z::SMEM, st>>>(p, aZ, bZ);
+      OzParams pz = p;
+      pz.beta = 1.0;
+      oz_gemm_win_kernel<8, 128, 64, 2, 5><<<grid2, OZ_THREADS, OzWinHi::SMEM, st>>>(pz, aHi, bHi);
+      return cudaGetLastError();
+    }
     if ((flags & 1024) && !(flags & (8 | 64))) {
       CUtensorMap bY;
       if (!oz_make_map_k(&bY, pb, Kp, (uint64_t)Rb, S, OzWin9Y::PL, 256, 32)) return cudaErrorInvalidValue;
@@ -594,8 +613,9 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
   }
   if (S == 8 && (flags & 512)) {
     // two diagonal windows, 128 x 128 tiles (flag 512; measured 73.5 against 69.1 TFLOP/s at 8192^3 and no gain inside the
-    // factorization -- the tensor pipe runs INT8 at ~4600 MAC per cycle and SM for N = 64 and N = 128 alike -- so the single-pass
-    // 128 x 64 kernel stays the default)
+    // factorization, so the single-pass 128 x 64 kernel stays the default).  ncu (profiles/ozaki_ncu_full_r2t.md): the single-pass
+    // kernel keeps the tensor-core pipe 94 % busy (sm__pipe_tc_cycles_active; every N = 64 product re-reads its 4 KB A operand from
+    // shared memory), the windows load the planes twice and sit at 81 % of the L2 -> SM fill rate instead)
     CUtensorMap aLo, bLo, aHi, bHi;
     if (!oz_make_map_k(&aLo, pa, Kp, (uint64_t)Ra, S, OzWinLo::PL, OZ_BM, 32) || !oz_make_map_k(&bLo, pb, Kp, (uint64_t)Rb, S, OzWinLo::PL, 128, 32) ||
         !oz_make_map_k(&aHi, pa, Kp, (uint64_t)Ra, S, OzWinHi::PL, OZ_BM, 64) || !oz_make_map_k(&bHi, pb, Kp, (uint64_t)Rb, S, OzWinHi::PL, 128, 64))

@@ -462,10 +462,10 @@ def test_ozaki_int8_gemm_is_an_fp64_product(gpr):
 
 
 def test_ozaki_nine_digit_product(gpr):
-    """The W^T W product of the inverse takes NINE digits (csrc/ozaki_i8.cuh: three diagonal windows d = 10 | 6..9 | 2..5, 45
-    integer products): on operands whose entries span many orders of magnitude under one scale per column it must be at least
-    16x closer to the exact product than the 8-digit form, equal the 128 x 256-tile variant of the tenth diagonal to rounding, and
-    honour upper-only / K-from-N (lauum_oop_t's flags) on a size whose last 256-wide tile is half outside."""
+    """The W^T W product of the inverse takes NINE digits (csrc/ozaki_i8.cuh: 45 integer products in two diagonal windows,
+    d = 6..10 with 128 x 96 tiles | d = 2..5; a three-window form is kept behind a flag): on operands whose entries span many
+    orders of magnitude under one scale per column it must be at least 16x closer to the exact product than the 8-digit form,
+    and honour upper-only / K-from-N (lauum_oop_t's flags) on a size that is no multiple of the 96- and 256-wide tiles."""
     from gpr_sm100a import _ffi
     rng = np.random.default_rng(77)
     ctx = gpr.Context(0)
@@ -475,12 +475,15 @@ def test_ozaki_nine_digit_product(gpr):
         ref = (A.astype(np.longdouble).T @ A.astype(np.longdouble))
         den = np.abs(A).T @ np.abs(A)
         err = {}
-        for S, fl in ((8, 0), (9, 0), (9, 1024)):
-            Cm, _ = _ffi.dbg_ozaki_dgemm(ctx, 1.0, A, A, 0.0, np.zeros((M, M)), S=S, flags=fl)
-            err[(S, fl)] = float(np.max(np.abs(Cm - ref) / den))
-        print(f"\nW^T W with 6 decades inside a column: err/(|A|^T|A|) 8 digits {err[(8, 0)]:.2e}, 9 digits {err[(9, 0)]:.2e}, 9 digits 128x256 {err[(9, 1024)]:.2e}")
-        assert err[(9, 0)] < 2e-15 and err[(9, 1024)] < 2e-15
+        out = {}
+        for S, fl in ((8, 0), (9, 0), (9, 4096), (9, 4096 | 1024)):       # 9 digits: two windows (default) | three | three with 128 x 256 tiles
+            out[(S, fl)], _ = _ffi.dbg_ozaki_dgemm(ctx, 1.0, A, A, 0.0, np.zeros((M, M)), S=S, flags=fl)
+            err[(S, fl)] = float(np.max(np.abs(out[(S, fl)] - ref) / den))
+        print(f"\nW^T W with 6 decades inside a column: err/(|A|^T|A|) 8 digits {err[(8, 0)]:.2e}, 9 digits {err[(9, 0)]:.2e} (two windows), "
+              f"{err[(9, 4096)]:.2e} (three), {err[(9, 4096 | 1024)]:.2e} (three, 128x256)")
+        assert max(err[(9, 0)], err[(9, 4096)], err[(9, 4096 | 1024)]) < 2e-15
         assert err[(9, 0)] * 16 <= err[(8, 0)] or err[(8, 0)] < 1e-15
+        assert np.array_equal(out[(9, 4096)], out[(9, 4096 | 1024)])          # same windows, same order of summation
         # lauum_oop_t's form: lower-triangular operand (garbage above the diagonal blocks), upper triangle of C only
         Kt = 640
         L = np.tril(rng.standard_normal((Kt, Kt))) + 4 * np.eye(Kt)
@@ -491,7 +494,7 @@ def test_ozaki_nine_digit_product(gpr):
         reft = L.astype(np.longdouble).T @ L.astype(np.longdouble)
         dent = np.abs(L).T @ np.abs(L)
         C0 = np.asfortranarray(rng.standard_normal((Kt, Kt)))
-        for fl in (3, 3 | 1024):
+        for fl in (3, 3 | 4096, 3 | 4096 | 1024):
             Cm, _ = _ffi.dbg_ozaki_dgemm(ctx, 1.0, np.asfortranarray(L), G, 0.0, C0, S=9, flags=fl)      # separate operands: only op(B) is masked
             up = np.triu(np.ones((Kt, Kt), dtype=bool))
             e = float(np.max((np.abs(Cm - reft) / dent)[up]))

@@ -1,4 +1,6 @@
-"""The W^T W product of the inverse (lauum) on the INT8 tensor cores with NINE 7-bit digits (three diagonal windows):
+"""[Historical A/B script: it produced profiles/ozaki_lauum9_r2s.log when the nine-digit product ran as three windows and launch flag 1024 /
+option ozaki_windows = 2 selected 128 x 256 tiles for the tenth diagonal; the default is now two windows, see csrc/ozaki_i8.cuh.]
+The W^T W product of the inverse (lauum) on the INT8 tensor cores with NINE 7-bit digits (three diagonal windows):
 accuracy of NLML + gradient vs the committed N = 32768 oracle golden and stage times.   python tools/ozaki_lauum9.py"""
 import os
 import sys
