@@ -96,6 +96,7 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU arm (oracle; checker/baseline only)
 COV_REF = ("SquaredExp", "SquaredExp", "WhiteNoise")
+MGPU_NB = 1024            # block-column width of the block-cyclic multi-GPU drivers (config 5); GPR_MGPU_NB overrides
 CALIBRATION = os.path.join(ROOT, "profiles", "cpu_calibration_r2.json")
 
 
@@ -391,10 +392,13 @@ def config4_split_predict(torch, dist, _ffi, ctx, rank, world, nvar_rows=64):
         if dist is not None:
             dist.barrier()
 
-    mh.split_predict(xe_blk[:, :128], xq, var_range=None, want_var=False)       # warm-up (workspaces)
+    # warm-up at full size into the caller-owned result array (the reference's split predict! writes in place): device workspaces
+    # and the host pages exist before the timed call -- a fresh 134 MB array costs 35-500 ms of first-touch faults under the copy
+    mean = np.zeros((hi - lo, nq), order="F")
+    mh.split_predict(xe_blk, xq, var_range=None, want_var=False, mean_out=mean)
     sync()
     t0 = time.perf_counter()
-    mean, _ = mh.split_predict(xe_blk, xq, var_range=None, want_var=False)
+    mh.split_predict(xe_blk, xq, var_range=None, want_var=False, mean_out=mean)
     sync()
     t_mean = time.perf_counter() - t0
     tm = mh.timings()
@@ -441,7 +445,8 @@ def config5_distributed(torch, dist, _ffi, rank, world, local_rank, n_override=N
     x = np.asfortranarray(rng.random((D, N)))
     y = np.sin(3 * x).sum(0) + 0.1 * rng.standard_normal(N)
     hp = np.concatenate([[1.0], 0.4 * np.ones(D), [0.1]])
-    mc = shard.dist_context(device=local_rank, nb=1024) if world > 1 else _ffi.MultiContext([local_rank], nb=1024)
+    nb = int(os.environ.get("GPR_MGPU_NB", str(MGPU_NB)))
+    mc = shard.dist_context(device=local_rank, nb=nb) if world > 1 else _ffi.MultiContext([local_rank], nb=nb)
     mm = _ffi.MultiModelHandle(mc, [1, 2], D, x, y)
     mm.nlml_grad(hp * 0.99)                                     # warm-up evaluation
     ts, F, G, tm = [], None, None, None
@@ -469,7 +474,7 @@ def config5_distributed(torch, dist, _ffi, rank, world, local_rank, n_override=N
         Kc[cols, np.arange(32)] += 1e-8 + sn * sn
         resid = float(np.abs(Kc.T @ alpha - y[cols]).max() / np.abs(y).max())
         dense_ms = tm["potrf"] + tm["trtri"] + tm["lauum"]
-        out = {"workload": f"one NLML+gradient, SquaredExp()+WhiteNoise() P=18, N={N}, D=16, block-cyclic over {world} rank(s), nb=1024",
+        out = {"workload": f"one NLML+gradient, SquaredExp()+WhiteNoise() P=18, N={N}, D=16, block-cyclic over {world} rank(s), nb={nb}",
                "transport": "NCCL (one process per GPU)" if world > 1 else "single rank",
                "s_per_eval": t, "evals_per_s": 1.0 / t, "phase_ms": {k: round(v, 1) for k, v in tm.items() if v > 0 and not k.startswith("pred")},
                "dense_tflops_aggregate": float(N) ** 3 / (dense_ms * 1e-3) / 1e12, "dense_tflops_per_gpu": float(N) ** 3 / (dense_ms * 1e-3) / 1e12 / world,
@@ -490,7 +495,8 @@ def config5_single_process(_ffi, world, n_override=None):
     x = np.asfortranarray(rng.random((D, N)))
     y = np.sin(3 * x).sum(0) + 0.1 * rng.standard_normal(N)
     hp = np.concatenate([[1.0], 0.4 * np.ones(D), [0.1]])
-    mc = _ffi.MultiContext(list(range(world)), nb=1024)
+    nb = int(os.environ.get("GPR_MGPU_NB", str(MGPU_NB)))
+    mc = _ffi.MultiContext(list(range(world)), nb=nb)
     mm = _ffi.MultiModelHandle(mc, [1, 2], D, x, y)
     mm.nlml_grad(hp * 0.99)
     t0 = time.perf_counter()
@@ -498,7 +504,7 @@ def config5_single_process(_ffi, world, n_override=None):
     t = time.perf_counter() - t0
     tm = mm.timings()
     dense_ms = tm["potrf"] + tm["trtri"] + tm["lauum"]
-    out = {"workload": f"one NLML+gradient, N={N}, D=16, block-cyclic over {world} GPUs driven by one process (peer memory over NVLink)",
+    out = {"workload": f"one NLML+gradient, N={N}, D=16, block-cyclic over {world} GPUs driven by one process (peer memory over NVLink), nb={nb}",
            "s_per_eval": t, "evals_per_s": 1.0 / t, "phase_ms": {k: round(v, 1) for k, v in tm.items() if v > 0 and not k.startswith("pred")},
            "dense_tflops_aggregate": float(N) ** 3 / (dense_ms * 1e-3) / 1e12, "dense_tflops_per_gpu": float(N) ** 3 / (dense_ms * 1e-3) / 1e12 / world,
            "limiter": max(("potrf", "trtri", "lauum"), key=lambda k: tm[k]), "F": F, "G_norm": float(np.linalg.norm(G))}

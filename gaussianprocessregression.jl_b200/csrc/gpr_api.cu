@@ -70,6 +70,7 @@ struct gpr_ctx {
   int ozaki_windows = 0;        // option "ozaki_windows" (A/B switches of csrc/ozaki_i8.cuh): bit 0 two-diagonal-window 128 x 128 kernel for the
                                 // 8-digit products; bit 2 the THREE-window form of the 9-digit product (d = 10 | 6..9 | 2..5) instead of the
                                 // default two windows (d = 6..10 with 128 x 96 tiles | 2..5), bit 1 with it: 128 x 256 tiles for d = 10
+  int64_t ozaki_kchunk = 32768; // option "ozaki_kchunk": k-chunk of the long-K tile-mapped products (tests lower it to exercise the chunk loop)
   int64_t ozaki_panel = 32768;  // option "ozaki_panel": k-panel of the W^T W product (own digit scales per panel)
   int oz_mask = 11, oz_cur = 8;   // option "ozaki_phases": bit 0 potrf, 1 trtri, 3 everything else (prediction solves); the W^T W product of the
                                   // inverse (lauum) is governed by "ozaki_lauum": its operand columns span many orders of magnitude under ONE
@@ -205,6 +206,28 @@ struct CudaBE {
         note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, ctx->oz_active, alpha, A, lda, B, ldb, beta, C, ldc, flags, ctx->oz_ws, 0,
                                 map.col_gtile, map.row_gtile0));
         ctx->launches += 3;
+        return;
+      }
+    }
+    if (flags == BLK_MAP_KUPTO && ctx->oz_active > 0 && ctx->stream == ctx->main_stream && (ctx->oz_mask & ctx->oz_cur) && tA == 'T' &&
+        tB == 'N' && (const double*)C != A && (const double*)C != B && M >= ctx->ozaki_min && N >= ctx->ozaki_min && K >= ctx->ozaki_min &&
+        !(M % 128) && !(N % 128) && !(K % 128) && A != B) {
+      // row-panel recurrence of the block-cyclic trtri (M = nb rows, per-column contraction limit, K up to N) on the INT8 tensor
+      // cores: k-chunks of at most 32768 (the int32 accumulators are exact up to there), each with its own digit scales, accumulated in C
+      const int64_t KC = std::min<int64_t>(ctx->ozaki_kchunk, 32768);
+      const size_t need = oz_workspace_bytes((int)M, (int)N, (int)std::min(K, KC), ctx->oz_active);
+      if (need > ctx->oz_ws_bytes) {
+        cudaStreamSynchronize(ctx->main_stream);
+        cudaFree(ctx->oz_ws); ctx->oz_ws = nullptr; ctx->oz_ws_bytes = 0;
+        if (cudaMalloc(&ctx->oz_ws, need) == cudaSuccess) ctx->oz_ws_bytes = need; else cudaGetLastError();
+      }
+      if (ctx->oz_ws_bytes >= need) {
+        for (int64_t k0 = 0; k0 < K; k0 += KC) {
+          const int64_t kc = std::min(KC, K - k0);
+          note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)kc, ctx->oz_active, alpha, A + k0, lda, B + k0, ldb, k0 == 0 ? beta : 1.0, C, ldc,
+                                  flags, ctx->oz_ws, (int)k0, map.col_gtile, map.row_gtile0, map.k_gtile0));
+          ctx->launches += 3;
+        }
         return;
       }
     }
@@ -705,6 +728,7 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
     ctx->ozaki_lauum = (int)value; return GPR_OK;
   }
   if (!strcmp(name, "ozaki_windows")) { ctx->ozaki_windows = (int)value & 7; return GPR_OK; }
+  if (!strcmp(name, "ozaki_kchunk")) { ctx->ozaki_kchunk = std::min<int64_t>(32768, std::max<int64_t>(128, (value / 128) * 128)); return GPR_OK; }
   if (!strcmp(name, "ozaki_panel")) { ctx->ozaki_panel = std::max<int64_t>(128, (value / 128) * 128); return GPR_OK; }
   if (!strcmp(name, "ozaki_phases")) { ctx->oz_mask = (int)value & 15; return GPR_OK; }
   if (!strcmp(name, "ozaki_min")) { ctx->ozaki_min = std::max<int64_t>(128, value); return GPR_OK; }

@@ -711,7 +711,7 @@ int gpr_mgpu_destroy(gpr_mgpu* mg) {
 
 int gpr_mgpu_set_option(gpr_mgpu* mg, const char* name, int64_t value) {
   if (!mg || !name) return GPR_ERR_ARG;
-  if (!strcmp(name, "ozaki") || !strcmp(name, "ozaki_min") || !strcmp(name, "ozaki_phases")) {   // INT8 route of the trailing updates
+  if (!strcmp(name, "ozaki") || !strcmp(name, "ozaki_min") || !strcmp(name, "ozaki_phases") || !strcmp(name, "ozaki_kchunk")) {   // INT8 route of the tile-mapped products
     for (auto& R : mg->rk)
       if (R.ctx && gpr_ctx_set_option(R.ctx, name, value) != GPR_OK) return mfail(mg, GPR_ERR_ARG, R.ctx->err);
     return GPR_OK;
@@ -914,7 +914,9 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
     // ---- trtri (+ back substitution): W = U^-1 in place, y columns = -alpha
     tick();
     comm.dma_mode = mg->prefetch_trtri;
+    set_phase(2);
     db.trtri();
+    set_phase(8);
     { int rc = tock(GPR_T_TRTRI); if (rc) return rc; }
     tick();
     if (Ry) {

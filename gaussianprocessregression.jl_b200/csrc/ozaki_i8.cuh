@@ -52,8 +52,11 @@ __host__ __device__ inline size_t oz_smem_bytes(int S) { return OZ_STAGES * oz_s
 // ---------------------------------------------------------------------------------------------------------------
 // kfrom != 0: column r only holds data for k >= 128 * (r / 128) (lower-triangular operand of a K-from-N product, whose
 // upper part may be uninitialised): everything above is treated as zero.
+// kfrom == 2 (GEMM_MAP_KUPTO, the row-panel recurrence of the block-cyclic trtri): column r belongs to global 128-tile column
+// gt = col_gtile[r / 128] and only holds data for k + k_off < (gt - k_gtile0 + 1) * 128; everything below is treated as zero.
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ X, long long ldx, int K, int R, int S, int8_t* __restrict__ planes,
-                                                       long long Kp, long long Rp, double* __restrict__ scale, int kfrom, int k_off) {
+                                                       long long Kp, long long Rp, double* __restrict__ scale, int kfrom, int k_off,
+                                                       const int* __restrict__ col_gtile = nullptr, int k_gtile0 = 0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = blockIdx.x * 8 + warp;
   if (r >= Rp) return;
@@ -64,7 +67,8 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     return;
   }
   const double* col = X + (long long)r * ldx;
-  const int kbeg = kfrom ? max(0, 128 * (r / 128) - k_off) : 0;   // k_off: global row of this operand's first k (k-panel of a larger product)
+  const int kbeg = (kfrom == 1) ? max(0, 128 * (r / 128) - k_off) : 0;   // k_off: global row of this operand's first k (k-panel of a larger product)
+  if (kfrom == 2) K = max(0, min(K, (col_gtile[r / 128] - k_gtile0 + 1) * 128 - k_off));
   double amax = 0.0;
   for (int k = kbeg + lane; k < K; k += 32) amax = fmax(amax, fabs(col[k]));
 #pragma unroll
@@ -156,6 +160,7 @@ struct OzParams {
   int flags;                                     // GEMM_UPPER_ONLY, GEMM_K_FROM_N (same meaning as dgemm_sm100.cuh)
   int k_off;                                     // K-from-N: global index of the first contraction row (k-panels of one product)
   const int* col_gtile; int row_gtile0;          // GEMM_MAP_UPPER (flag 8): global 128-tile column of each local 128-tile column (csrc/dist_blocked.hpp)
+  int k_gtile0;                                  // GEMM_MAP_KUPTO (flag 16): the tile column contracts over k + k_off < (gt - k_gtile0 + 1) * 128 only
 };
 
 template <int S>
@@ -193,7 +198,11 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
     if (p.row_gtile0 + tile_m > gt) return;
   }
   const int kt0 = (p.flags & 2) ? max(0, blk_n * 128 - p.k_off) / OZ_BK : 0;   // GEMM_K_FROM_N
-  const int KT = p.K / OZ_BK - kt0;
+  int KT = p.K / OZ_BK - kt0;
+  if (p.flags & 16) {                                                 // GEMM_MAP_KUPTO: per-column contraction limit (k-chunk of a longer product)
+    KT = min(KT, ((p.col_gtile[blk_n] - p.k_gtile0 + 1) * 128 - p.k_off) / OZ_BK);
+    if (KT <= 0) return;                                              // nothing of this column in this chunk (the caller accumulates: beta = 1)
+  }
   const int m0 = tile_m * OZ_BM, n0 = tile_n * OZ_BN;
 
   if (tid == 0) {
@@ -556,8 +565,9 @@ inline size_t oz_workspace_bytes(int M, int N, int K, int S) {
 // updates of potrf and the W^T W product of the inverse) its digit planes are formed once and shared.
 inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int S, double alpha, const double* A, long long lda, const double* B,
                                       long long ldb, double beta, double* C, long long ldc, int flags, void* workspace, int k_off = 0,
-                                      const int* col_gtile = nullptr, int row_gtile0 = 0) {
-  if ((flags & 8) && !col_gtile) return cudaErrorInvalidValue;
+                                      const int* col_gtile = nullptr, int row_gtile0 = 0, int k_gtile0 = 0) {
+  if ((flags & (8 | 16)) && !col_gtile) return cudaErrorInvalidValue;
+  if ((flags & 16) && (S == 9 || (flags & (1 | 2 | 8 | 64 | 512)) || (A == B && lda == ldb))) return cudaErrorInvalidValue;   // KUPTO: plain 8-digit kernel only
   if ((S != 9 && S != 8 && S != 7 && S != 6 && S != 2) || (M % OZ_BM) || (N % 128) || (K % 128) || K > 32768) return cudaErrorInvalidValue;
   const size_t Kp = (size_t)K;
   const bool shared = (A == B && lda == ldb);
@@ -571,10 +581,13 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
   // K-from-N: only op(B)'s columns are triangular (column block J holds data for k >= 128 J).  With shared planes (W^T W, upper
   // only) the rows I <= J of op(A)^T are the same columns, read for k >= 128 J >= 128 I only, so the same masking is exact.
   oz_slice_kernel<<<(Ra + 7) / 8, 256, 0, st>>>(A, lda, K, Ra, S, pa, (long long)Kp, Ra, sa, shared ? kfrom : 0, k_off);
-  if (!shared) oz_slice_kernel<<<(N + 7) / 8, 256, 0, st>>>(B, ldb, K, N, S, pb, (long long)Kp, N, sb, kfrom, k_off);
+  if (!shared) {
+    if (flags & 16) oz_slice_kernel<<<(N + 7) / 8, 256, 0, st>>>(B, ldb, K, N, S, pb, (long long)Kp, N, sb, 2, k_off, col_gtile, k_gtile0);
+    else oz_slice_kernel<<<(N + 7) / 8, 256, 0, st>>>(B, ldb, K, N, S, pb, (long long)Kp, N, sb, kfrom, k_off);
+  }
   CUtensorMap mA, mB;
   if (!oz_make_map(&mA, pa, Kp, (uint64_t)Ra, S, OZ_BM) || !oz_make_map(&mB, pb, Kp, (uint64_t)Rb, S, OZ_BN)) return cudaErrorInvalidValue;
-  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~(512 | 1024 | 4096), k_off, col_gtile, row_gtile0};
+  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~(512 | 1024 | 4096), k_off, col_gtile, row_gtile0, k_gtile0};
   if (S == 9) {
     // nine digits (products whose operands span several orders of magnitude under one scale per column: the W^T W of the inverse).
     // Nine 64-column accumulators do not fit the 512 TMEM columns, so the diagonals are summed in windows, lowest order first, each

@@ -277,11 +277,17 @@ class ModelHandle:
         self.ctx.check(lib().gpr_predict_device(self.handle, _vp(d_xp_ptr), int(M), int(bool(same_x)), _vp(d_mean_ptr),
                                                 _vp(d_var_ptr) if d_var_ptr else None))
 
-    def split_predict(self, xe, xq, var_range=None, want_var=True):
+    def split_predict(self, xe, xq, var_range=None, want_var=True, mean_out=None, var_out=None):
+        """mean_out / var_out: caller-owned result arrays (the reference's predict!(mu, Sigma, ...) writes in place too); a fresh
+        134 MB array per call costs more in first-touch page faults under the device-to-host copy than the whole computation."""
         xe, xq = f64(xe), f64(xq)
         ne, nq = int(xe.shape[1]), int(xq.shape[1])
-        mean = np.empty((ne, nq), order="F")
-        var = np.empty(ne * nq) if want_var else None
+        if mean_out is not None and (mean_out.shape != (ne, nq) or mean_out.dtype != np.float64 or not mean_out.flags.f_contiguous):
+            raise GPRError("mean_out must be a Fortran-ordered float64 array of shape (ne, nq)")
+        if var_out is not None and (var_out.shape != (ne * nq,) or var_out.dtype != np.float64 or not var_out.flags.c_contiguous):
+            raise GPRError("var_out must be a contiguous float64 vector of length ne * nq")
+        mean = mean_out if mean_out is not None else np.empty((ne, nq), order="F")
+        var = (var_out if var_out is not None else np.empty(ne * nq)) if want_var else None
         lo, hi = (1, 0) if var_range is None else (int(var_range[0]), int(var_range[1]))
         self.ctx.check(lib().gpr_split_predict(self.handle, dptr(xe), ne, dptr(xq), nq, lo, hi, dptr(mean), dptr(var)))
         return mean, var

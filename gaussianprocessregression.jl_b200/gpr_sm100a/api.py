@@ -536,11 +536,20 @@ def predict(md, xp, diagonal_var=False, ctx=None):
         pc.close()
 
 
+def _inplace(a, shape, order):
+    """`a` itself if the C ABI can write the result straight into it (float64, right shape, dense in the given order)."""
+    ok = isinstance(a, np.ndarray) and a.dtype == np.float64 and a.shape == tuple(shape) and a.flags.writeable and \
+        (a.flags.f_contiguous if order == "F" else a.flags.c_contiguous)
+    return a if ok else None
+
+
 def predict_mean_(mu, md, xp, pc):
     """predict_mean!(mu, md, xp, pc)  (src/predict.jl:36-40 ; split: src/split_predict.jl:5-19)"""
     if isinstance(xp, Cmap):
-        m, _ = pc.handle.split_predict(xp.xe, xp.xq, var_range=None, want_var=False)
-        mu[...] = m
+        out = _inplace(mu, (xp.xe.shape[1], xp.xq.shape[1]), "F")          # written in place when the layout allows it
+        m, _ = pc.handle.split_predict(xp.xe, xp.xq, var_range=None, want_var=False, mean_out=out)
+        if out is None:
+            mu[...] = m
         return None
     m, _, _ = pc.handle.predict(xp, same_x=xp is md.x)
     mu[...] = m.reshape(mu.shape, order="F")
@@ -552,9 +561,13 @@ def predict_(mu, Sig, md, xp, pc):
     if isinstance(xp, Cmap):
         if not isinstance(Sig, Diagonal):
             raise GPRError("split predict supports Diagonal covariance only")
-        m, v = pc.handle.split_predict(xp.xe, xp.xq, var_range=pc.var_range, want_var=True)
-        mu[...] = m
-        Sig.diag[...] = v
+        ne, nq = xp.xe.shape[1], xp.xq.shape[1]
+        out, vout = _inplace(mu, (ne, nq), "F"), _inplace(Sig.diag, (ne * nq,), "C")
+        m, v = pc.handle.split_predict(xp.xe, xp.xq, var_range=pc.var_range, want_var=True, mean_out=out, var_out=vout)
+        if out is None:
+            mu[...] = m
+        if vout is None:
+            Sig.diag[...] = v
         return None
     same = xp is md.x
     if isinstance(Sig, Diagonal):

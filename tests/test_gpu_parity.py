@@ -806,25 +806,32 @@ def test_mgpu_rank_count_independence_n8192(gpr):
 
 @pytest.mark.parametrize("G", [1, 2, 3])
 def test_mgpu_potrf_on_int8_tensor_cores_vs_oracle(gpr, G):
-    """The rank-nb trailing updates of the block-cyclic potrf (csrc/dist_blocked.hpp) through the INT8-tensor-core product
-    (tile-mapped form of csrc/ozaki_i8.cuh; nb = 1024 so that K = nb reaches the route) against the committed oracle values
-    of config 2 (N = 8192, D = 8, SquaredExp()+WhiteNoise(), set A), forced on and in automatic mode."""
+    """The tile-mapped products of the block-cyclic drivers (csrc/dist_blocked.hpp) through the INT8-tensor-core product
+    (csrc/ozaki_i8.cuh; nb = 1024 so that they reach the route): the rank-nb trailing updates of potrf (GEMM_MAP_UPPER) and the
+    row-panel recurrence of trtri (GEMM_MAP_KUPTO: per-column contraction limit, long K cut into k-chunks with their own digit
+    scales -- ozaki_kchunk = 2048 exercises the chunk loop) against the committed oracle values of config 2 (N = 8192, D = 8,
+    SquaredExp()+WhiteNoise(), set A): forced on, automatic, potrf only, off."""
     from gpr_sm100a import _ffi
     mg2 = _load_module("mg2", "make_golden_config2.py")
     x, y, sets = mg2.inputs()
     g = np.load(os.path.join(HERE, "golden", "config2_n8192.npz"))
     hp = sets["A"]
-    for forced in (8, -1, 0):
+    launches = {}
+    for forced, phases, kchunk in ((8, 11, 2048), (-1, 11, 32768), (8, 1, 32768), (0, 11, 32768)):
         mc = _ffi.MultiContext(_devices(G), nb=1024)
         mc.set_option("ozaki", forced)
+        mc.set_option("ozaki_phases", phases)
+        mc.set_option("ozaki_kchunk", kchunk)
         mm = _ffi.MultiModelHandle(mc, [1, 2], 8, x, y)
         l0 = mc.launch_count()
         F, Gd = mm.nlml_grad(hp)
         nl = mc.launch_count() - l0
+        launches[(forced, phases)] = nl
         mm.close(); mc.close()
         relF, relG = abs(F - float(g["F_A"])) / abs(float(g["F_A"])), grad_err(Gd, g["G_A"])
-        print(f"\nmgpu potrf, G={G}, ozaki={forced}: relF {relF:.2e} relG {relG:.2e} ({nl} launches)")
+        print(f"\nmgpu potrf + trtri, G={G}, ozaki={forced} phases={phases} kchunk={kchunk}: relF {relF:.2e} relG {relG:.2e} ({nl} launches)")
         assert relF <= TOL_F and relG <= TOL_G
+    assert len(set(launches.values())) == 4          # four different routes were actually taken
 
 
 # ------------------------------------------------------------------ (6) SURVEY.md 8f "next" rows on the device
