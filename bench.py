@@ -96,7 +96,7 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU arm (oracle; checker/baseline only)
 COV_REF = ("SquaredExp", "SquaredExp", "WhiteNoise")
-MGPU_NB = 1024            # block-column width of the block-cyclic multi-GPU drivers (config 5); GPR_MGPU_NB overrides
+MGPU_NB = 2048            # block-column width of the block-cyclic multi-GPU drivers (config 5); GPR_MGPU_NB overrides
 CALIBRATION = os.path.join(ROOT, "profiles", "cpu_calibration_r2.json")
 
 

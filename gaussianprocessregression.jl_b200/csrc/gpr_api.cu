@@ -111,6 +111,13 @@ int fail_cuda(gpr_ctx* ctx, cudaError_t e, const char* what, int line) {
 struct CudaBE {
   gpr_ctx* ctx;
   void note(cudaError_t e) { if (e != cudaSuccess && ctx->pending == cudaSuccess) ctx->pending = e; }
+  // digit-plane workspace of the INT8 route: grown on demand (a failed allocation leaves the product on the DMMA pipe)
+  void oz_reserve(size_t need) {
+    if (need <= ctx->oz_ws_bytes) return;
+    cudaStreamSynchronize(ctx->main_stream);
+    cudaFree(ctx->oz_ws); ctx->oz_ws = nullptr; ctx->oz_ws_bytes = 0;
+    if (cudaMalloc(&ctx->oz_ws, need) == cudaSuccess) ctx->oz_ws_bytes = need; else cudaGetLastError();
+  }
   bool ozaki_eligible(char tA, char tB, int64_t M, int64_t N, int64_t K, const double* A, const double* B, const double* C, int flags,
                       int64_t batch) const {
     if (ctx->oz_active <= 0 || ctx->stream != ctx->main_stream) return false;
@@ -130,11 +137,7 @@ struct CudaBE {
       // large T,N product: INT8 tensor cores (csrc/ozaki_i8.cuh), one launch per batch member
       const int digits = ctx->oz_cur == 4 ? ctx->ozaki_lauum : ctx->oz_active;
       const size_t need = oz_workspace_bytes((int)std::max(M, N), (int)N, (int)K, digits);
-      if (need > ctx->oz_ws_bytes) {
-        cudaStreamSynchronize(ctx->main_stream);
-        cudaFree(ctx->oz_ws); ctx->oz_ws = nullptr; ctx->oz_ws_bytes = 0;
-        if (cudaMalloc(&ctx->oz_ws, need) == cudaSuccess) ctx->oz_ws_bytes = need; else cudaGetLastError();
-      }
+      oz_reserve(need);
       if (ctx->oz_ws_bytes >= need && batch == 1 && flags == (BLK_UPPER_ONLY | BLK_K_FROM_N) && A == B && lda == ldb && M == N && N == K &&
           K > ctx->ozaki_panel) {
         // W^T W of the inverse (lauum_oop_t): the columns of the triangular factor span many orders of magnitude (O(1/sigma_n)
@@ -197,11 +200,7 @@ struct CudaBE {
         K <= 32768 && !(M % 128) && !(N % 128) && !(K % 128)) {
       // rank-nb trailing update of the block-cyclic potrf on the INT8 tensor cores (csrc/ozaki_i8.cuh)
       const size_t need = oz_workspace_bytes((int)M, (int)N, (int)K, ctx->oz_active);
-      if (need > ctx->oz_ws_bytes) {
-        cudaStreamSynchronize(ctx->main_stream);
-        cudaFree(ctx->oz_ws); ctx->oz_ws = nullptr; ctx->oz_ws_bytes = 0;
-        if (cudaMalloc(&ctx->oz_ws, need) == cudaSuccess) ctx->oz_ws_bytes = need; else cudaGetLastError();
-      }
+      oz_reserve(need);
       if (ctx->oz_ws_bytes >= need) {
         note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, ctx->oz_active, alpha, A, lda, B, ldb, beta, C, ldc, flags, ctx->oz_ws, 0,
                                 map.col_gtile, map.row_gtile0));
@@ -216,11 +215,7 @@ struct CudaBE {
       // cores: k-chunks of at most 32768 (the int32 accumulators are exact up to there), each with its own digit scales, accumulated in C
       const int64_t KC = std::min<int64_t>(ctx->ozaki_kchunk, 32768);
       const size_t need = oz_workspace_bytes((int)M, (int)N, (int)std::min(K, KC), ctx->oz_active);
-      if (need > ctx->oz_ws_bytes) {
-        cudaStreamSynchronize(ctx->main_stream);
-        cudaFree(ctx->oz_ws); ctx->oz_ws = nullptr; ctx->oz_ws_bytes = 0;
-        if (cudaMalloc(&ctx->oz_ws, need) == cudaSuccess) ctx->oz_ws_bytes = need; else cudaGetLastError();
-      }
+      oz_reserve(need);
       if (ctx->oz_ws_bytes >= need) {
         for (int64_t k0 = 0; k0 < K; k0 += KC) {
           const int64_t kc = std::min(KC, K - k0);

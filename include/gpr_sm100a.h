@@ -92,7 +92,13 @@ int gpr_device_count(void);                        /* usable sm_100-class device
 int gpr_ctx_create(int device, gpr_ctx** ctx);
 int gpr_ctx_destroy(gpr_ctx* ctx);
 const char* gpr_last_error(gpr_ctx* ctx);          /* ctx may be NULL: last error of a failed gpr_ctx_create */
-int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value);   /* "predict_tile" (test points per tile), "inplace_lauum" (0/1) */
+/* Tuning / A-B options (defaults in brackets); none of them changes what is computed, only how:
+ *   "predict_tile" test points per prediction tile; "inplace_lauum" 0/1 [0]; "leaf_lookahead" 0/1 [1]; "alpha_from_inverse" 0/1 [1];
+ *   "gemm_cfg" DMMA tile variant [0 = 128x64x16]; "gemm_tma" TMA-fed T,N products 0/1 [1]; "kbuild_gram" TMA-fed Gram covariance build 0/1 [1];
+ *   "ozaki" FP64 products on the INT8 tensor cores: -1 automatic from a condition-number bound [default], 0 off, 6 / 7 / 8 digits forced;
+ *   "ozaki_lauum" digits of the inverse's W^T W product on that route: 9 [default], 8, 0 = DMMA; "ozaki_min" smallest routed M, N, K [1024];
+ *   "ozaki_phases" bit mask potrf 1 | trtri 2 | other solves 8 [11]; "ozaki_panel", "ozaki_kchunk" k-panels [32768]; "ozaki_windows" kernel variants [0]. */
+int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value);
 int64_t gpr_ctx_launch_count(gpr_ctx* ctx);        /* kernels launched by this context so far */
 
 /* dim_hp(K, dim): src/covariance.jl:27,60; src/compose_covar.jl:26-28 */
@@ -175,7 +181,8 @@ int gpr_dbg_dgemm(gpr_ctx* ctx, char transA, char transB, int M, int N, int K, d
 /* diagnostics / prototype: C = alpha A^T B + beta C (T,N form: A is K x M, B is K x N, both k-contiguous) through the INT8
  * tensor cores (tcgen05.mma kind::i8 with TMEM accumulators): Ozaki-type splitting of every row of A^T and column of B
  * into S signed 7-bit digits, S (S + 1) / 2 exact integer products, FP64 recombination (csrc/ozaki_i8.cuh).
- * M % 128 == 0, N % 128 == 0, K % 128 == 0, K <= 32768, 2 <= S <= 8.  flags: 1 = upper only, 2 = K-from-N. */
+ * M % 128 == 0, N % 128 == 0, K % 128 == 0, K <= 32768, S in {2, 6, 7, 8, 9} (9: two diagonal windows, 45 products).
+ * flags: 1 = upper only, 2 = K-from-N, 512 / 1024 / 4096 = kernel variants (csrc/ozaki_i8.cuh). */
 int gpr_dbg_ozaki_dgemm(gpr_ctx* ctx, int M, int N, int K, int S, double alpha, const double* A, int64_t lda, const double* B,
                         int64_t ldb, double beta, double* C, int64_t ldc, int flags, int reps, double* ms);
 /* factor (and optionally invert) a host SPD matrix in place through the blocked path; A is N x N.
