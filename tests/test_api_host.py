@@ -75,3 +75,39 @@ def test_block_ranges_cover(gpr):
             assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
     assert sorted(sum((replica_indices(10, k, 4) for k in range(4)), [])) == list(range(10))
     assert sharded_split_rows(4096, 0, 8) == (1, 512) and sharded_split_rows(4096, 7, 8) == (3585, 4096)
+
+
+def test_inplace_result_arrays(gpr):
+    """predict!(mu, Sigma, ...) writes in place (src/predict.jl:36-71): the mirror hands the caller's array to the C ABI only when
+    the layout allows it and falls back to a copy otherwise."""
+    from gpr_sm100a import api
+    mu = np.zeros((4, 6), order="F")
+    assert api._inplace(mu, (4, 6), "F") is mu
+    assert api._inplace(mu, (6, 4), "F") is None                               # wrong shape
+    assert api._inplace(np.zeros((4, 6)), (4, 6), "F") is None                 # C order
+    assert api._inplace(np.zeros((4, 6), dtype=np.float32, order="F"), (4, 6), "F") is None
+    assert api._inplace(mu[:, ::2], (4, 3), "F") is None                       # strided view
+    v = np.zeros(24)
+    assert api._inplace(v, (24,), "C") is v
+    ro = np.zeros(24)
+    ro.setflags(write=False)
+    assert api._inplace(ro, (24,), "C") is None
+    assert api._inplace([0.0] * 24, (24,), "C") is None
+
+
+def test_bench_stage_wise_scaling():
+    """bench.py's CPU baseline: one measured evaluation is scaled to N = 32768 stage by stage -- the factorization and the dpotrs on
+    the identity by (32768/N)^3, everything else by (32768/N)^2 (reference stages: src/cost.jl:96-127)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    st = {"kbuild": 4.0, "sum": 0.7, "potrf": 1.2, "potrs_identity": 6.6, "gradient": 10.3}
+    dt = 23.0                                                                  # 0.2 s outside the named stages: counted as N^2
+    t = bench.scale_by_stage(dt, st, 16384)
+    assert abs(t - ((1.2 + 6.6) * 8 + (dt - 7.8) * 4)) < 1e-12
+    assert abs(bench.scale_by_stage(dt, st, 32768) - dt) < 1e-12               # already at full size
+    assert bench.scale_by_stage(5.0, {"potrf": 4.0, "potrs_identity": 4.0}, 16384) == 5.0 * 8      # stages cannot exceed the total
+    a, b = bench.fit_cost_model([2048, 4096, 16384], [0.33, 1.31, 22.9])
+    assert a >= 0 and b >= 0
