@@ -67,6 +67,7 @@ struct gpr_ctx {
   int oz_active = 0;            // digits in force for the model being worked on (set by the entry points)
   int64_t ozaki_min = 1024;
   int ozaki_lauum = 9;          // option "ozaki_lauum": digits of the INT8 route for the W^T W product of the inverse (0 = DMMA, 8, 9 = default)
+  int ozaki_lauum_map = 0;      // option "ozaki_lauum_map": nine-digit INT8 form also for the rank-nb W W^T products of the block-cyclic lauum (slower: off)
   int ozaki_windows = 0;        // option "ozaki_windows" (A/B switches of csrc/ozaki_i8.cuh): bit 0 two-diagonal-window 128 x 128 kernel for the
                                 // 8-digit products; bit 2 the THREE-window form of the 9-digit product (d = 10 | 6..9 | 2..5) instead of the
                                 // default two windows (d = 6..10 with 128 x 96 tiles | 2..5), bit 1 with it: 128 x 256 tiles for d = 10
@@ -205,6 +206,22 @@ struct CudaBE {
         note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, ctx->oz_active, alpha, A, lda, B, ldb, beta, C, ldc, flags, ctx->oz_ws, 0,
                                 map.col_gtile, map.row_gtile0));
         ctx->launches += 3;
+        return;
+      }
+    }
+    if (flags == (BLK_MAP_UPPER | BLK_MAP_BROWS) && ctx->oz_active > 0 && ctx->ozaki_lauum_map && ctx->oz_cur == 4 && ctx->stream == ctx->main_stream &&
+        tA == 'T' && tB == 'N' && A == B && lda == ldb && (const double*)C != A && M >= ctx->ozaki_min && N >= ctx->ozaki_min &&
+        K >= ctx->ozaki_min && K <= 32768 && N <= M && !(M % 128) && !(N % 128) && !(K % 128)) {
+      // W W^T accumulation of the block-cyclic lauum (one column panel of W against itself, rank-nb) with NINE digits: the panel is
+      // cut into digit planes once (shared operand), the tile column reads its op(B) rows by global position.  OFF by default
+      // (option "ozaki_lauum_map"): at K = nb the three diagonal windows are dominated by their epilogues -- one rank, N = 32768:
+      // lauum 386 -> 501 ms at nb = 2048, 374 -> 723 ms at nb = 1024 (profiles/mgpu_int8_lauum_r2aa.log); parity is unchanged
+      const size_t need = oz_workspace_bytes((int)M, (int)N, (int)K, 9);
+      oz_reserve(need);
+      if (ctx->oz_ws_bytes >= need) {
+        note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, 9, alpha, A, lda, B, ldb, beta, C, ldc, flags, ctx->oz_ws, 0,
+                                map.col_gtile, map.row_gtile0));
+        ctx->launches += 4;
         return;
       }
     }
@@ -723,6 +740,7 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
     ctx->ozaki_lauum = (int)value; return GPR_OK;
   }
   if (!strcmp(name, "ozaki_windows")) { ctx->ozaki_windows = (int)value & 7; return GPR_OK; }
+  if (!strcmp(name, "ozaki_lauum_map")) { ctx->ozaki_lauum_map = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "ozaki_kchunk")) { ctx->ozaki_kchunk = std::min<int64_t>(32768, std::max<int64_t>(128, (value / 128) * 128)); return GPR_OK; }
   if (!strcmp(name, "ozaki_panel")) { ctx->ozaki_panel = std::max<int64_t>(128, (value / 128) * 128); return GPR_OK; }
   if (!strcmp(name, "ozaki_phases")) { ctx->oz_mask = (int)value & 15; return GPR_OK; }

@@ -711,7 +711,8 @@ int gpr_mgpu_destroy(gpr_mgpu* mg) {
 
 int gpr_mgpu_set_option(gpr_mgpu* mg, const char* name, int64_t value) {
   if (!mg || !name) return GPR_ERR_ARG;
-  if (!strcmp(name, "ozaki") || !strcmp(name, "ozaki_min") || !strcmp(name, "ozaki_phases") || !strcmp(name, "ozaki_kchunk")) {   // INT8 route of the tile-mapped products
+  if (!strcmp(name, "ozaki") || !strcmp(name, "ozaki_min") || !strcmp(name, "ozaki_phases") || !strcmp(name, "ozaki_kchunk") ||
+      !strcmp(name, "ozaki_lauum") || !strcmp(name, "ozaki_lauum_map")) {   // INT8 route of the tile-mapped products
     for (auto& R : mg->rk)
       if (R.ctx && gpr_ctx_set_option(R.ctx, name, value) != GPR_OK) return mfail(mg, GPR_ERR_ARG, R.ctx->err);
     return GPR_OK;
@@ -943,7 +944,9 @@ int gpr_mgpu_nlml_grad(gpr_mgpu_model* m, const double* hp_in, int P, int log_sc
     // ---- K^-1 = W W^T in place, then the fused all-hyper-parameter reduction over the local columns
     tick();
     comm.dma_mode = mg->prefetch_lauum;
+    set_phase(4);
     db.lauum();
+    set_phase(8);
     { int rc = tock(GPR_T_LAUUM); if (rc) return rc; }
     m->have_inverse = true;
     tick();

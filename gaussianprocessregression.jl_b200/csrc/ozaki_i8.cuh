@@ -395,6 +395,9 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
   const int kt0 = (p.flags & 2) ? max(0, blk_n * 128 - p.k_off) / BK : 0;
   const int KT = p.K / BK - kt0;
   const int m0 = tile_m * OZ_BM, n0 = tile_n * BN;
+  // GEMM_MAP_BROWS (flag 32, BN = 128 with flag 8): the op(B) columns of this tile column are the columns gt * 128 .. of the operand
+  // (the W W^T accumulation of the block-cyclic lauum reads its column panel by GLOBAL position), C stays local
+  const int nB = (p.flags & 32) ? gt * 128 + (n0 & 127) : n0;
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -418,7 +421,7 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
         unsigned char* st = smem + (size_t)s * W::STAGE;
         mbar_expect_tx(&full[s], (unsigned)W::STAGE);
         tma_load_3d(st, &mapA, &full[s], (kt0 + kt) * BK, m0, 0);                               // PL x 128 x BK
-        tma_load_3d(st + (size_t)PL * OZ_BM * BK, &mapB, &full[s], (kt0 + kt) * BK, n0, 0);     // PL x BN  x BK
+        tma_load_3d(st + (size_t)PL * OZ_BM * BK, &mapB, &full[s], (kt0 + kt) * BK, nB, 0);     // PL x BN  x BK
       }
     }
   } else if (warp == 1) {
@@ -495,7 +498,7 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
         if (diag_local && m0 + row > n0 + col) continue;
         if (diag_map && row > col + coff) continue;
         double* cp = Crow + (long long)col * p.ldc;
-        const double r = acc[j] * sa * p.scaleB[n0 + col];
+        const double r = acc[j] * sa * p.scaleB[nB + col];
         *cp = (p.beta != 0.0) ? fma(p.beta, *cp, r) : r;
       }
     }
@@ -567,6 +570,7 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
                                       long long ldb, double beta, double* C, long long ldc, int flags, void* workspace, int k_off = 0,
                                       const int* col_gtile = nullptr, int row_gtile0 = 0, int k_gtile0 = 0) {
   if ((flags & (8 | 16)) && !col_gtile) return cudaErrorInvalidValue;
+  if ((flags & 32) && (S != 9 || !(flags & 8))) return cudaErrorInvalidValue;      // mapped B rows: nine-digit window kernels, tile-mapped form only
   if ((flags & 16) && (S == 9 || (flags & (1 | 2 | 8 | 64 | 512)) || (A == B && lda == ldb))) return cudaErrorInvalidValue;   // KUPTO: plain 8-digit kernel only
   if ((S != 9 && S != 8 && S != 7 && S != 6 && S != 2) || (M % OZ_BM) || (N % 128) || (K % 128) || K > 32768) return cudaErrorInvalidValue;
   const size_t Kp = (size_t)K;

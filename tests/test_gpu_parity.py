@@ -810,28 +810,31 @@ def test_mgpu_potrf_on_int8_tensor_cores_vs_oracle(gpr, G):
     (csrc/ozaki_i8.cuh; nb = 1024 so that they reach the route): the rank-nb trailing updates of potrf (GEMM_MAP_UPPER) and the
     row-panel recurrence of trtri (GEMM_MAP_KUPTO: per-column contraction limit, long K cut into k-chunks with their own digit
     scales -- ozaki_kchunk = 2048 exercises the chunk loop) against the committed oracle values of config 2 (N = 8192, D = 8,
-    SquaredExp()+WhiteNoise(), set A): forced on, automatic, potrf only, off."""
+    SquaredExp()+WhiteNoise(), set A), and the W W^T accumulation of lauum with nine digits (GEMM_MAP_UPPER | GEMM_MAP_BROWS, shared
+    digit planes of the column panel): forced on, automatic, without lauum, potrf only, off."""
     from gpr_sm100a import _ffi
     mg2 = _load_module("mg2", "make_golden_config2.py")
     x, y, sets = mg2.inputs()
     g = np.load(os.path.join(HERE, "golden", "config2_n8192.npz"))
     hp = sets["A"]
     launches = {}
-    for forced, phases, kchunk in ((8, 11, 2048), (-1, 11, 32768), (8, 1, 32768), (0, 11, 32768)):
+    for forced, phases, kchunk, lauum in ((8, 11, 2048, 9), (-1, 11, 32768, 9), (8, 11, 32768, 0), (8, 1, 32768, 0), (0, 11, 32768, 9)):
         mc = _ffi.MultiContext(_devices(G), nb=1024)
         mc.set_option("ozaki", forced)
         mc.set_option("ozaki_phases", phases)
         mc.set_option("ozaki_kchunk", kchunk)
+        mc.set_option("ozaki_lauum_map", 1 if lauum else 0)          # W W^T accumulation of lauum: nine-digit tile-mapped form with mapped
+        #                                                              B rows (off by default: slower at K = nb) / DMMA
         mm = _ffi.MultiModelHandle(mc, [1, 2], 8, x, y)
         l0 = mc.launch_count()
         F, Gd = mm.nlml_grad(hp)
         nl = mc.launch_count() - l0
-        launches[(forced, phases)] = nl
+        launches[(forced, phases, kchunk, lauum)] = nl
         mm.close(); mc.close()
         relF, relG = abs(F - float(g["F_A"])) / abs(float(g["F_A"])), grad_err(Gd, g["G_A"])
-        print(f"\nmgpu potrf + trtri, G={G}, ozaki={forced} phases={phases} kchunk={kchunk}: relF {relF:.2e} relG {relG:.2e} ({nl} launches)")
+        print(f"\nmgpu INT8 routes, G={G}, ozaki={forced} phases={phases} kchunk={kchunk} lauum={lauum}: relF {relF:.2e} relG {relG:.2e} ({nl} launches)")
         assert relF <= TOL_F and relG <= TOL_G
-    assert len(set(launches.values())) == 4          # four different routes were actually taken
+    assert len(set(launches.values())) == 5          # five different routes were actually taken
 
 
 # ------------------------------------------------------------------ (6) SURVEY.md 8f "next" rows on the device
