@@ -466,7 +466,31 @@ int ozaki_digits_for(const gpr_model* m, const double* hp, double eps) {
 }
 
 // K (+ noise, + jitter, identity padding) into m->d_U, then blocked potrf; solves for all y columns.
-int factor_and_solve(gpr_model* m, const double* hp, double eps, int64_t* info, bool defer_alpha) {
+// Reads the factorization status back (the only host <-> device round trip of the factor / inverse sequence) and fixes the cache
+// state accordingly.  LAPACK-style info: first failing pivot, 0 = ok (src/cost.jl:104 throws PosDefException the same way).
+int finish_factor_status(gpr_model* m, int64_t* info, const char* where) {
+  gpr_ctx* ctx = m->ctx;
+  long long h_info = 0;
+  CK(cudaMemcpyAsync(&h_info, ctx->d_info, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int rc = check_pending(ctx, where);
+  if (rc) { m->have_factor = false; m->have_inverse = false; return rc; }
+  m->info_host = h_info;
+  if (info) *info = h_info;
+  m->have_factor = (h_info == 0);
+  if (h_info != 0) {
+    m->have_inverse = false;
+    char buf[128];
+    snprintf(buf, sizeof buf, "matrix is not positive definite; Cholesky failed at pivot %lld", h_info);
+    return fail(ctx, GPR_ERR_NOT_POSDEF, buf);
+  }
+  return GPR_OK;
+}
+
+// defer_status: the caller goes straight on to the inverse and reads the status once at the end (finish_factor_status): a failed
+// pivot makes potrf_leaf stop writing, the kernels behind it then work on stale data (dense index ranges only -- nothing can fault)
+// and the result is discarded.
+int factor_and_solve(gpr_model* m, const double* hp, double eps, int64_t* info, bool defer_alpha, bool defer_status = false) {
   gpr_ctx* ctx = m->ctx;
   const int64_t N = m->N, Np = m->Np;
   m->oz = ozaki_digits_for(m, hp, eps);
@@ -511,23 +535,11 @@ int factor_and_solve(gpr_model* m, const double* hp, double eps, int64_t* info, 
       ctx->launches++;
     }
   }
-  long long h_info = 0;
-  CK(cudaMemcpyAsync(&h_info, ctx->d_info, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  int rc = check_pending(ctx, "factor_and_solve");
-  if (rc) return rc;
-  m->info_host = h_info;
-  if (info) *info = h_info;
-  m->have_factor = (h_info == 0);
   m->have_inverse = false;
   m->factor_destroyed = false;
   m->kinv_symmetric = false;
-  if (h_info != 0) {
-    char buf[128];
-    snprintf(buf, sizeof buf, "matrix is not positive definite; Cholesky failed at pivot %lld", h_info);
-    return fail(ctx, GPR_ERR_NOT_POSDEF, buf);
-  }
-  return GPR_OK;
+  if (defer_status) { m->have_factor = true; return GPR_OK; }     // provisional until finish_factor_status
+  return finish_factor_status(m, info, "factor_and_solve");
 }
 
 int form_inverse(gpr_model* m) {
@@ -926,10 +938,13 @@ int gpr_update_cache(gpr_model* m, const double* hp, int P, double eps, int want
     // (12.5 ms).  Needs the separate K^-1 buffer: with the in-place inverse the factor (whose diagonal the log det
     // reads) is gone by then, so that path keeps the solves.
     const bool defer_alpha = want_inverse && m->ny == 1 && ctx->alpha_from_inverse && inverse_is_out_of_place(m);
-    int rc = factor_and_solve(m, hp, eps, info, defer_alpha);
+    // gradient path: potrf, the inverse and alpha are enqueued back to back; the factorization status is read once at the end
+    const bool defer_status = want_inverse != 0;
+    int rc = factor_and_solve(m, hp, eps, info, defer_alpha, defer_status);
     if (rc) { m->hp_host.clear(); return rc; }
-    if (want_inverse) { rc = form_inverse(m); if (rc) { m->hp_host.clear(); return rc; } }
-    if (defer_alpha) { rc = alpha_from_inverse(m); if (rc) { m->hp_host.clear(); return rc; } }
+    if (want_inverse) { rc = form_inverse(m); if (rc) { m->hp_host.clear(); m->have_factor = false; return rc; } }
+    if (defer_alpha) { rc = alpha_from_inverse(m); if (rc) { m->hp_host.clear(); m->have_factor = false; return rc; } }
+    if (defer_status) { rc = finish_factor_status(m, info, "gpr_update_cache"); if (rc) { m->hp_host.clear(); return rc; } }
   } else if (want_inverse && !m->have_inverse) {
     int rc = form_inverse(m);
     if (rc) return rc;

@@ -27,6 +27,16 @@
 //           of the stage into accumulator (s + t - 2) of the 8 x 64-column TMEM accumulators (all 512 columns), then
 //           tcgen05.commit releases the stage; after the last k-tile a commit signals the epilogue;
 //   warps 2-5  epilogue: tcgen05.ld (32 lanes x 16 columns) per diagonal, int32 -> FP64, weighted sum, scaling, C update.
+// ncu (profiles/ozaki_ncu_full_r2t.md): tensor-core pipe 94 % busy -- every 128 x 64 x 32 product re-reads its 4 KB A operand from
+// shared memory, and eight accumulators cannot be wider than 64 of the 512 TMEM columns: the roof of this instruction shape.
+//
+// Kernel (oz_gemm_win_kernel): the same roles for ONE window of diagonals d = DLO..DHI with BN = 96 / 128 / 256 columns per
+// accumulator.  Used for NINE digits (45 products: the W^T W of the inverse, whose operand columns span many orders of magnitude
+// under one scale): d = 6..10 in five 96-column accumulators, then d = 2..5, each launch accumulating into C.
+//
+// Forms (flags, same meaning as dgemm_sm100.cuh): upper only (1), K-from-N (2: triangular operand, masked in the digit extraction),
+// skip tile (0,0) (64), and the tile-mapped forms of the block-cyclic multi-GPU drivers: MAP_UPPER (8), MAP_KUPTO (16: per-column
+// contraction limit, masked in the digit extraction; long K comes in k-chunks <= 32768 with their own scales), MAP_BROWS (32).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>

@@ -277,6 +277,20 @@ def test_not_positive_definite_raises(gpr):
     with pytest.raises(gpr.PosDefException) as ei:
         gpr.update_cache_(tc, md.params, md, ϵ=0.0)
     assert 1 <= ei.value.info <= 300
+    # gradient cache: the factorization status is read once AFTER the inverse has been enqueued (no host round trip between potrf
+    # and the inverse) -- the failure must surface the same way, and the cache must recover on the next valid evaluation
+    tg = gpr.MllGradCache(md)
+    with pytest.raises(gpr.PosDefException) as eg:
+        gpr.update_cache_(tg, md.params, md, ϵ=0.0)
+    assert eg.value.info == ei.value.info
+    gpr.update_cache_(tg, md.params, md, ϵ=1.0)                  # K = 1 1^T + I: positive definite
+    gpr.update_cache_(tc, md.params, md, ϵ=1.0)
+    ll = gpr.MarginalLikelihood()
+    Fg, Fl = gpr.loss(ll, md, tg), gpr.loss(ll, md, tc)            # loss(cost, md, tc): from the cache as it stands (src/cost.jl:113-117)
+    # closed form: eigenvalues 301 (once) and 1; y = 1: y^T K^-1 y = 300 / 301
+    Fref = 0.5 * (300.0 / 301.0 + np.log(301.0) + 300 * np.log(2 * np.pi))
+    assert Fg == pytest.approx(Fref, rel=1e-12) and Fl == pytest.approx(Fref, rel=1e-12)
+    tg.close()
     tc.close()
 
 
