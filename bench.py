@@ -603,6 +603,7 @@ def run_gpu(args, rank, world, local_rank):
     t_wall = time.perf_counter() - t0
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
+    mh_route = mh.route()                     # product engine of the timed steps (digits of the INT8 route, 0 = DMMA)
     # device time of the K timed steps: event pair around every evaluation on the library stream, summed; max over ranks
     t_loc = stage["eval"] * 1e-3
     t_max = t_loc
@@ -714,24 +715,55 @@ def run_gpu(args, rank, world, local_rank):
         del An
     except Exception:
         pass
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": fp64_sust, "unit": "TFLOP/s", "frac": achieved / fp64_sust,
-                "note": "achieved = N^3 FP64-equivalent flop / (potrf + trtri + lauum) ms.  peak = the FP64 (DMMA) roof as measured through cuBLAS DGEMM; "
-                        "the large products of potrf, trtri (8 digits: 36 exact integer products per FP64 product) and of the inverse's W^T W "
-                        "(9 digits: 45) run on the INT8 tensor cores (tcgen05.mma kind::i8, csrc/ozaki_i8.cuh), which is how frac can exceed the "
-                        "FP64 pipe: extra.dmma_only holds the same step on the DMMA pipe alone",
-                "int8_route": {"fp64_equivalent_tflops_8192": oz_tf, "fp64_equivalent_tflops_8192_nine_digits": oz9_tf,
-                               "int8_pops": (oz_tf * 36 / 1e3) if oz_tf else None, "int8_pops_nine_digits": (oz9_tf * 45 / 1e3) if oz9_tf else None,
-                               "int8_peak_pops_nominal": 4.5, "frac_of_nominal_int8": (oz_tf * 36 / 4500.0) if oz_tf else None,
-                               "int8_peak_pops_from_measured_bf16": (2e-3 * hp_peak["bf16_tflops"]) if hp_peak and hp_peak.get("bf16_tflops") else None,
-                               "frac_of_measured_scaled_int8": (oz_tf * 36 / (2.0 * hp_peak["bf16_tflops"])) if oz_tf and hp_peak and hp_peak.get("bf16_tflops") else None,
-                               "note": "MEASURED_PEAKS.json holds no INT8 figure; 4.5 POPS is NVIDIA's dense INT8 figure for B200, and twice the "
-                                       "measured bf16 burst rate of MEASURED_PEAKS.json is the rate the same tensor pipe can be expected to sustain "
-                                       "on this pool (bf16 measured: 0.72 of its nominal 2.25 PFLOP/s)"},
-                "traffic": traffic, "traffic_unit": "GB of DRAM read+write by all product kernels (DMMA GEMMs, INT8 GEMM, digit extraction) of one step (ncu launch list, profiles/dram_traffic.json)",
-                "kernel": "oz_gemm_kernel / oz_gemm_win_kernel (INT8 tensor cores) + dgemm128_tma_kernel (DMMA, the products below 1024) inside blocked potrf+trtri+lauum: N^3 FP64-equivalent flop per step / (potrf+trtri+lauum) CUDA-event ms",
-                "peak_source": f"cuBLAS DGEMM 8192^3 via torch.matmul, sustained {fp64_sust:.1f} / burst {fp64_burst:.1f} TFLOP/s measured in this run "
-                               "(MEASURED_PEAKS.json holds no FP64 figure" + (f"; its HBM copy figure is {hp_peak.get('hbm_gbs')} GB/s)" if hp_peak else ")"),
-                "kernel_isolated_tflops": gemm_tf, "kernel_isolated_frac": gemm_tf / fp64_burst}
+    # which engine the step ran on (gpr_model_route): 8 / 9 digits = INT8 tensor cores, 0 = FP64 DMMA pipe
+    try:
+        digits, digits_inv = mh_route
+    except Exception:
+        digits, digits_inv = 0, 0
+    bf16_sust = (hp_peak or {}).get("bf16_tflops_sustained") or (hp_peak or {}).get("bf16_tflops")
+    bf16_src = "MEASURED_PEAKS.json bf16_tflops_sustained (the kernels are timed inside a long step)"
+    if not bf16_sust:
+        bf16_sust, bf16_src = 1590.0, "fallback of /opt/skills/guides/B200_PROFILING.md (1.59 PFLOP/s bf16): of fallback"
+    common = {"traffic": traffic,
+              "traffic_unit": "GB of DRAM read+write by all product kernels (INT8 GEMMs, digit extraction, DMMA GEMMs) of one step (ncu launch list, profiles/dram_traffic.json)",
+              "fp64_dgemm_roof_tflops": fp64_sust, "frac_of_fp64_dgemm_roof": achieved / fp64_sust,
+              "fp64_dgemm_roof_source": f"cuBLAS DGEMM 8192^3 via torch.matmul, sustained {fp64_sust:.1f} / burst {fp64_burst:.1f} TFLOP/s measured in this run "
+                                        "(MEASURED_PEAKS.json holds no FP64 figure" + (f"; its HBM copy figure is {hp_peak.get('hbm_gbs')} GB/s)" if hp_peak else ")"),
+              "dmma_kernel_isolated_tflops": gemm_tf, "dmma_kernel_isolated_frac": gemm_tf / fp64_burst}
+    if digits > 0:
+        # dominant kernels: oz_gemm_kernel<8> (potrf, trtri) and oz_gemm_win_kernel (the inverse's W^T W) on the INT8 tensor pipe.  Their
+        # roof in FP64-equivalent TFLOP/s = INT8 rate of the pipe / integer products per FP64 product, with the INT8 rate taken as
+        # twice the bf16 rate the driver measured (kind::i8 has twice the MACs of kind::f16 on this part; MEASURED_PEAKS.json has no INT8 line)
+        prods = (36.0 * 2 + (45.0 if digits_inv == 9 else 36.0 if digits_inv == 8 else 0.0)) / (3.0 if digits_inv else 2.0)
+        peak_eq = 2.0 * bf16_sust / prods
+        if digits_inv:
+            ach = achieved
+            what = "N^3 FP64-equivalent flop / (potrf + trtri + lauum) CUDA-event ms"
+        else:   # lauum on the DMMA pipe: the roofline of the INT8 kernels covers potrf + trtri only
+            ach = 2.0 * float(N) ** 3 / 3.0 / ((ms["potrf"] + ms["trtri"]) * 1e-3) / 1e12
+            what = "2 N^3 / 3 FP64-equivalent flop / (potrf + trtri) CUDA-event ms (lauum ran on the DMMA pipe)"
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peak_eq, "unit": "TFLOP/s", "frac": ach / peak_eq,
+                    "note": f"FP64-equivalent TFLOP/s.  achieved = {what}: every launch of the phases (INT8 products, digit extraction, the products below "
+                            "1024 on the DMMA pipe, leaf kernels), i.e. the in-situ rate.  peak = INT8 tensor-pipe rate / integer products per FP64 product "
+                            f"= 2 x {bf16_sust:.1f} TFLOP/s bf16 ({bf16_src}) / {prods:.1f} (36 for the 8-digit products of potrf and trtri, 45 for the "
+                            "9-digit W^T W of the inverse, weighted by flops).  The FP64 pipe's own roof (cuBLAS DGEMM, measured in this run) and the ratio "
+                            "to it are given beside it: the step runs ABOVE the FP64 roof because it does not use the FP64 pipe for its large products; "
+                            "extra.dmma_only holds the same step on the DMMA pipe alone",
+                    "kernel": "oz_gemm_kernel<8> + oz_gemm_win_kernel (tcgen05.mma kind::i8, TMEM accumulators; csrc/ozaki_i8.cuh) inside blocked potrf + trtri + lauum",
+                    "int8_route": {"digits": digits, "digits_inverse": digits_inv, "integer_products_per_fp64_product": prods,
+                                   "achieved_int8_pops_in_situ": ach * prods / 1e3, "int8_peak_pops_from_measured_bf16": 2e-3 * bf16_sust,
+                                   "int8_peak_pops_nominal": 4.5,
+                                   "kernel_isolated_fp64_equivalent_tflops_8192": oz_tf, "kernel_isolated_fp64_equivalent_tflops_8192_nine_digits": oz9_tf,
+                                   "kernel_isolated_int8_pops": (oz_tf * 36 / 1e3) if oz_tf else None,
+                                   "kernel_isolated_int8_pops_nine_digits": (oz9_tf * 45 / 1e3) if oz9_tf else None,
+                                   "kernel_isolated_frac": (oz_tf * 36 / (2.0 * bf16_sust)) if oz_tf else None,
+                                   "ncu": "profiles/ozaki_ncu_full_r2t.md: tensor-core pipe 94 % busy (sm__pipe_tc_cycles_active) in oz_gemm_kernel<8>; 94.7 % "
+                                          "and 93 % of the L2 -> SM fill rate in the d = 6..10 window of the nine-digit product"}}
+    else:
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": fp64_sust, "unit": "TFLOP/s", "frac": achieved / fp64_sust,
+                    "note": "achieved = N^3 flop / (potrf + trtri + lauum) CUDA-event ms on the FP64 DMMA pipe; peak = cuBLAS DGEMM measured in this run",
+                    "kernel": "dgemm128_tma_kernel (DMMA.8x8x4, TMA-fed) inside blocked potrf + trtri + lauum"}
+    roofline.update(common)
 
     base = None
     if world == 1 and not args.no_cpu:

@@ -1027,6 +1027,13 @@ int gpr_fetch(gpr_model* m, int which, double* out) {
   return GPR_OK;
 }
 
+int gpr_model_route(gpr_model* m, int* digits, int* digits_inverse) {
+  if (!m) return GPR_ERR_ARG;
+  if (digits) *digits = m->oz > 0 ? m->oz : 0;
+  if (digits_inverse) *digits_inverse = (m->oz > 0 && m->d_W && m->Np >= m->ctx->ozaki_min && m->Np <= 32768) ? m->ctx->ozaki_lauum : 0;
+  return GPR_OK;
+}
+
 int gpr_timings(gpr_model* m, double* ms, int n) {
   if (!m || !ms) return GPR_ERR_ARG;
   gpr_ctx* ctx = m->ctx;

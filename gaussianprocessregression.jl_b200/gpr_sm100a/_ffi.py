@@ -57,6 +57,7 @@ _SIGS = {
     "gpr_split_kernel": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _dp, _dp, _i64, _dp, _i64, _dp, _i64, _dp, _dp, _dp]),
     "gpr_split_predict": (C.c_int, [_vp, _dp, _i64, _dp, _i64, _i64, _i64, _dp, _dp]),
     "gpr_timings": (C.c_int, [_vp, _dp, C.c_int]),
+    "gpr_model_route": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gpr_integrate": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
     "gpr_sample_mvn": (C.c_int, [_vp, _ip, C.c_int, C.c_int, _dp, _dp, _i64, C.c_double, _dp, _dp, _dp, C.POINTER(_i64)]),
     "gpr_dbg_dgemm": (C.c_int, [_vp, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _i64, _dp, _i64,
@@ -300,6 +301,12 @@ class ModelHandle:
         var = np.empty(1) if want_var else None
         self.ctx.check(lib().gpr_integrate(self.handle, dptr(a), dptr(b), dptr(Iout), dptr(var)))
         return Iout, var
+
+    def route(self):
+        """(digits, digits_inverse) of the INT8-tensor-core route the last factorization took; 0 = FP64 DMMA pipe."""
+        a, b = C.c_int(0), C.c_int(0)
+        self.ctx.check(lib().gpr_model_route(self.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def timings(self):
         ms = np.zeros(T_COUNT)

@@ -160,6 +160,9 @@ int gpr_split_predict(gpr_model* model, const double* xe, int64_t ne, const doub
                       int64_t e_hi, double* mean, double* var);
 
 int gpr_timings(gpr_model* model, double* ms, int n);
+/* which product engine the last factorization of this model took: *digits = 7-bit digits of the INT8-tensor-core route for potrf /
+ * trtri / the prediction solves (0 = FP64 DMMA pipe), *digits_inverse = the same for the W^T W product of the inverse. */
+int gpr_model_route(gpr_model* model, int* digits, int* digits_inverse);
 
 /* integrate!(Iout, var_Iout, md, hp, a, b, nothing, wc, ac): src/integrate.jl:56-62,103-143 (row f-3 of SURVEY.md 8f,
  * the noise-free path; the per-sample-noise path needs a symmetric eigensolver and is not built).
