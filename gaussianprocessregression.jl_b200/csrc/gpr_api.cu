@@ -67,6 +67,7 @@ struct gpr_ctx {
   int oz_active = 0;            // digits in force for the model being worked on (set by the entry points)
   int64_t ozaki_min = 1024;
   int ozaki_lauum = 9;          // option "ozaki_lauum": digits of the INT8 route for the W^T W product of the inverse (0 = DMMA, 8, 9 = default)
+  int ozaki_split = 9;          // option "ozaki_split": digits of the INT8 route for the split-predict mean products (0 = DMMA, 8, 9)
   int ozaki_lauum_map = 0;      // option "ozaki_lauum_map": nine-digit INT8 form also for the rank-nb W W^T products of the block-cyclic lauum (slower: off)
   int ozaki_windows = 0;        // option "ozaki_windows" (A/B switches of csrc/ozaki_i8.cuh): bit 0 two-diagonal-window 128 x 128 kernel for the
                                 // 8-digit products; bit 2 the THREE-window form of the 9-digit product (d = 10 | 6..9 | 2..5) instead of the
@@ -89,6 +90,8 @@ struct gpr_ctx {
   cudaStream_t main_stream = nullptr, side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};   // split predict: chunk-ready events for the overlapped download
+  cudaEvent_t ev_d2h[4] = {nullptr, nullptr, nullptr, nullptr};     // ... and chunk-downloaded events (pinned staging buffer)
+  double* h_stage = nullptr; size_t h_stage_elems = 0;              // pinned staging buffer of the split-predict mean
 };
 
 namespace {
@@ -182,6 +185,20 @@ struct CudaBE {
   // C = (A^T B) .* E + beta C, T,N form with the Hadamard epilogue (split-predict mean)
   void gemm_hadamard(int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb,
                      const double* E, int64_t lde, double beta, double* C, int64_t ldc) {
+    if (ctx->ozaki_split && ozaki_eligible('T', 'N', M, N, K, A, B, C, 0, 1) && ctx->oz_cur != 4) {
+      // split-predict mean on the INT8 tensor cores; the Hadamard factor and beta ride in the epilogue.  NINE digits by default: the
+      // columns of Diagonal(wt) C carry the weights' dynamic range and the sum over the training points cancels heavily -- with eight
+      // digits the mean agrees with the dense path to 4e-10 instead of 8e-12 (N = 32768, profiles/README.md)
+      const int digits = ctx->ozaki_split;
+      const size_t need = oz_workspace_bytes((int)M, (int)N, (int)K, digits);
+      oz_reserve(need);
+      if (ctx->oz_ws_bytes >= need) {
+        note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, digits, 1.0, A, lda, B, ldb, beta, C, ldc, 0, ctx->oz_ws, 0, nullptr, 0, 0,
+                                E, lde));
+        ctx->launches += 3;
+        return;
+      }
+    }
     if (ctx->gemm_tma && gemm_tma_supported('T', 'N', (int)M, (int)N, (int)K, A, B, C, 0, 1, 0, 0))
       note(launch_dgemm128_tma(ctx->stream, (int)M, (int)N, (int)K, 1.0, A, lda, B, ldb, beta, C, ldc, 0, 1, 0, 0, 0, nullptr, 0, 0, E, lde));
     else
@@ -722,6 +739,8 @@ int gpr_ctx_destroy(gpr_ctx* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (auto& ev : ctx->ev_chunk) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_d2h) if (ev) cudaEventDestroy(ev);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   cudaFree(ctx->oz_ws);
   cudaFree(ctx->d_info);
   cudaStreamDestroy(ctx->stream);
@@ -752,6 +771,10 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
     ctx->ozaki_lauum = (int)value; return GPR_OK;
   }
   if (!strcmp(name, "ozaki_windows")) { ctx->ozaki_windows = (int)value & 7; return GPR_OK; }
+  if (!strcmp(name, "ozaki_split")) {
+    if (value != 0 && value != 8 && value != 9) return fail(ctx, GPR_ERR_ARG, "ozaki_split: 0 (DMMA), 8 or 9 digits");
+    ctx->ozaki_split = (int)value; return GPR_OK;
+  }
   if (!strcmp(name, "ozaki_lauum_map")) { ctx->ozaki_lauum_map = value ? 1 : 0; return GPR_OK; }
   if (!strcmp(name, "ozaki_kchunk")) { ctx->ozaki_kchunk = std::min<int64_t>(32768, std::max<int64_t>(128, (value / 128) * 128)); return GPR_OK; }
   if (!strcmp(name, "ozaki_panel")) { ctx->ozaki_panel = std::max<int64_t>(128, (value / 128) * 128); return GPR_OK; }
@@ -1375,16 +1398,39 @@ int gpr_split_predict(gpr_model* m, const double* xe, int64_t ne, const double* 
   }
   rc = check_pending(ctx, "split mean");
   if (rc) return rc;
+  // Download: the caller's array is pageable (2-4 GB/s through the driver's bounce buffer -- 75 ms for 134 MB, longer than the
+  // products since they moved to the INT8 tensor cores), so the chunks land in a pinned staging buffer of the context at PCIe speed
+  // and the host copies each finished chunk on while the GPU computes the next one.  Falls back to the direct copy if the pinned
+  // allocation fails or would exceed 1 GB.
+  const size_t stage_elems = (size_t)ne * (size_t)nq;
+  if (stage_elems > ctx->h_stage_elems && stage_elems * sizeof(double) <= ((size_t)1 << 30)) {
+    if (ctx->h_stage) { cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_elems = 0; }
+    if (cudaMallocHost(&ctx->h_stage, stage_elems * sizeof(double)) == cudaSuccess) ctx->h_stage_elems = stage_elems;
+    else { cudaGetLastError(); ctx->h_stage = nullptr; }
+  }
+  const bool staged = ctx->h_stage_elems >= stage_elems;
+  if (staged && !ctx->ev_d2h[0])
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+  double* dst = staged ? ctx->h_stage : mean;
+  int nsent = 0;
   {
     Scope s(m->tm, GPR_T_SPLIT_D2H, ctx->side_stream);
     for (int ch = 0; ch < nch; ++ch) {
       const int64_t q0 = ch * cw, qn = std::min<int64_t>(cw, nq - q0);
       if (qn <= 0) break;
       CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_chunk[ch], 0));
-      CK(cudaMemcpy2DAsync(mean + q0 * ne, sizeof(double) * ne, d_mu + q0 * nep, sizeof(double) * nep, sizeof(double) * ne, qn,
+      CK(cudaMemcpy2DAsync(dst + q0 * ne, sizeof(double) * ne, d_mu + q0 * nep, sizeof(double) * nep, sizeof(double) * ne, qn,
                            cudaMemcpyDeviceToHost, ctx->side_stream));
+      if (staged) CK(cudaEventRecord(ctx->ev_d2h[ch], ctx->side_stream));
+      ++nsent;
     }
   }
+  if (staged)
+    for (int ch = 0; ch < nsent; ++ch) {
+      const int64_t q0 = ch * cw, qn = std::min<int64_t>(cw, nq - q0);
+      CK(cudaEventSynchronize(ctx->ev_d2h[ch]));
+      memcpy(mean + q0 * ne, ctx->h_stage + q0 * ne, sizeof(double) * (size_t)ne * (size_t)qn);
+    }
   CK(cudaStreamSynchronize(ctx->side_stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (var) {

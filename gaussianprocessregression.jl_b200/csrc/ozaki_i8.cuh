@@ -171,6 +171,7 @@ struct OzParams {
   int k_off;                                     // K-from-N: global index of the first contraction row (k-panels of one product)
   const int* col_gtile; int row_gtile0;          // GEMM_MAP_UPPER (flag 8): global 128-tile column of each local 128-tile column (csrc/dist_blocked.hpp)
   int k_gtile0;                                  // GEMM_MAP_KUPTO (flag 16): the tile column contracts over k + k_off < (gt - k_gtile0 + 1) * 128 only
+  const double* E; long long lde;                // Hadamard epilogue: C = alpha (A^T B) .* E + beta C  (split-predict mean)
 };
 
 template <int S>
@@ -321,7 +322,8 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
         const int col = c0 + j;
         if (diag_tile && row > col + coff) continue;
         double* cp = Crow + (long long)col * p.ldc;
-        const double r = acc[j] * sa * p.scaleB[n0 + col];
+        double r = acc[j] * sa * p.scaleB[n0 + col];
+        if (p.E) r *= p.E[(long long)(m0 + row) + (long long)(n0 + col) * p.lde];
         *cp = (p.beta != 0.0) ? fma(p.beta, *cp, r) : r;
       }
     }
@@ -508,7 +510,8 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
         if (diag_local && m0 + row > n0 + col) continue;
         if (diag_map && row > col + coff) continue;
         double* cp = Crow + (long long)col * p.ldc;
-        const double r = acc[j] * sa * p.scaleB[nB + col];
+        double r = acc[j] * sa * p.scaleB[nB + col];
+        if (p.E) r *= p.E[(long long)(m0 + row) + (long long)(n0 + col) * p.lde];       // Hadamard epilogue: linear, so every window applies it
         *cp = (p.beta != 0.0) ? fma(p.beta, *cp, r) : r;
       }
     }
@@ -578,7 +581,9 @@ inline size_t oz_workspace_bytes(int M, int N, int K, int S) {
 // updates of potrf and the W^T W product of the inverse) its digit planes are formed once and shared.
 inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int S, double alpha, const double* A, long long lda, const double* B,
                                       long long ldb, double beta, double* C, long long ldc, int flags, void* workspace, int k_off = 0,
-                                      const int* col_gtile = nullptr, int row_gtile0 = 0, int k_gtile0 = 0) {
+                                      const int* col_gtile = nullptr, int row_gtile0 = 0, int k_gtile0 = 0, const double* E = nullptr,
+                                      long long lde = 0) {
+  if (E && (flags & (8 | 16 | 32))) return cudaErrorInvalidValue;                    // Hadamard epilogue: plain forms only
   if ((flags & (8 | 16)) && !col_gtile) return cudaErrorInvalidValue;
   if ((flags & 32) && (S != 9 || !(flags & 8))) return cudaErrorInvalidValue;      // mapped B rows: nine-digit window kernels, tile-mapped form only
   if ((flags & 16) && (S == 9 || (flags & (1 | 2 | 8 | 64 | 512)) || (A == B && lda == ldb))) return cudaErrorInvalidValue;   // KUPTO: plain 8-digit kernel only
@@ -601,7 +606,7 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
   }
   CUtensorMap mA, mB;
   if (!oz_make_map(&mA, pa, Kp, (uint64_t)Ra, S, OZ_BM) || !oz_make_map(&mB, pb, Kp, (uint64_t)Rb, S, OZ_BN)) return cudaErrorInvalidValue;
-  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~(512 | 1024 | 4096), k_off, col_gtile, row_gtile0, k_gtile0};
+  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~(512 | 1024 | 4096), k_off, col_gtile, row_gtile0, k_gtile0, E, lde};
   if (S == 9) {
     // nine digits (products whose operands span several orders of magnitude under one scale per column: the W^T W of the inverse).
     // Nine 64-column accumulators do not fit the 512 TMEM columns, so the diagonals are summed in windows, lowest order first, each

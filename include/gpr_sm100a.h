@@ -96,7 +96,8 @@ const char* gpr_last_error(gpr_ctx* ctx);          /* ctx may be NULL: last erro
  *   "predict_tile" test points per prediction tile; "inplace_lauum" 0/1 [0]; "leaf_lookahead" 0/1 [1]; "alpha_from_inverse" 0/1 [1];
  *   "gemm_cfg" DMMA tile variant [0 = 128x64x16]; "gemm_tma" TMA-fed T,N products 0/1 [1]; "kbuild_gram" TMA-fed Gram covariance build 0/1 [1];
  *   "ozaki" FP64 products on the INT8 tensor cores: -1 automatic from a condition-number bound [default], 0 off, 6 / 7 / 8 digits forced;
- *   "ozaki_lauum" digits of the inverse's W^T W product on that route: 9 [default], 8, 0 = DMMA; "ozaki_min" smallest routed M, N, K [1024];
+ *   "ozaki_lauum" digits of the inverse's W^T W product on that route: 9 [default], 8, 0 = DMMA; "ozaki_split" the same for the
+ *   split-predict mean products; "ozaki_min" smallest routed M, N, K [1024];
  *   "ozaki_phases" bit mask potrf 1 | trtri 2 | other solves 8 [11]; "ozaki_panel", "ozaki_kchunk" k-panels [32768]; "ozaki_windows" kernel variants [0]. */
 int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value);
 int64_t gpr_ctx_launch_count(gpr_ctx* ctx);        /* kernels launched by this context so far */

@@ -534,6 +534,8 @@ def test_ozaki_route_keeps_nlml_parity(gpr):
     mdo = o.GPRModel((o.SE, o.SE, o.NOISE), hp, x, y)
     Fo, Go = o.loss_grad(hp, mdo)
     mu_o, var_o = o.predict(mdo, xp, diagonal_var=True)
+    xe_s, xq_s = np.asfortranarray(0.5 * rng.random((D, 512))), np.asfortranarray(0.5 * rng.random((D, 512)))
+    mu_split_o = {e: o.predict(mdo, xe_s[:, e:e + 1] + xq_s, diagonal_var=True)[0] for e in (0, 255, 511)}     # rows of the sum grid
     ctx = gpr.Context(0)
     try:
         res = {}
@@ -544,12 +546,16 @@ def test_ozaki_route_keeps_nlml_parity(gpr):
             l0 = ctx.launch_count()
             F, G = mh.nlml_grad(hp)
             mu, var, _ = mh.predict(xp, want_var=True)
+            # split-predict mean (src/split_predict.jl:10-19): its T,N products with the Hadamard epilogue take the same route
+            ms_, _ = mh.split_predict(xe_s, xq_s, var_range=None, want_var=False)
+            split_err = max(mean_err(ms_[e, :], mu_split_o[e], y) for e in mu_split_o)
             res[oz] = (abs(F - Fo) / abs(Fo), grad_err(G, Go), mean_err(mu.reshape(-1), mu_o, y), np.abs(var - var_o).max() / o.prior_diag(mdo),
-                       ctx.launch_count() - l0)
+                       ctx.launch_count() - l0, split_err)
             mh.close()
-        print(f"\nN={N}: DMMA relF {res[0][0]:.1e} relG {res[0][1]:.1e} mean {res[0][2]:.1e} var {res[0][3]:.1e} | "
-              f"INT8 relF {res[8][0]:.1e} relG {res[8][1]:.1e} mean {res[8][2]:.1e} var {res[8][3]:.1e}")
+        print(f"\nN={N}: DMMA relF {res[0][0]:.1e} relG {res[0][1]:.1e} mean {res[0][2]:.1e} var {res[0][3]:.1e} split mean {res[0][5]:.1e} | "
+              f"INT8 relF {res[8][0]:.1e} relG {res[8][1]:.1e} mean {res[8][2]:.1e} var {res[8][3]:.1e} split mean {res[8][5]:.1e}")
         assert res[8][0] <= TOL_F and res[8][1] <= TOL_G and res[8][2] <= TOL_MU and res[8][3] <= TOL_VAR
+        assert res[0][5] <= TOL_MU and res[8][5] <= TOL_MU
         assert res[8][4] != res[0][4]          # the route was actually taken (different launch count)
         # the inverse's W^T W on DMMA instead: fewer INT8 launches, same parity
         ctx.set_option("ozaki", 8)
