@@ -775,6 +775,10 @@ def run_gpu(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD if N == N_FULL else WORKLOAD.replace("N=32768", f"N={N}"),
                        "parallelism": "replicas only (one hyper-parameter set per GPU, no data-path collective)" if world > 1 else "1 GPU",
                        "l2": "inputs larger than L2 (K is 8.6 GB per evaluation); no explicit flush needed",
+                       "arithmetic": ("FP64 in, FP64 out; products with M, N, K >= 1024 are formed from exact int8 digit products on the INT8 tensor "
+                                      f"cores ({digits} seven-bit digits per operand, {digits_inv} for the inverse's W^T W; error <= 2^-56 of the operand row "
+                                      "maxima, parity vs the oracle unchanged), everything else on the FP64 DMMA pipe") if digits > 0 else
+                                     "FP64 throughout (DMMA pipe): the condition-number gate kept the INT8 route off for this model",
                        "timing": "CUDA events on the library stream around every evaluation (hp upload .. F, G read back), summed over the K "
                                  "steps, max over ranks; barrier + torch.cuda.synchronize on both sides; wall clock reported beside it"},
             "wall_ms_per_step": t_wall / args.steps * 1e3,
