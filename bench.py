@@ -129,6 +129,13 @@ class RefArm:
         import gpr_oracle_big as ob
         self.ob = ob
         self.ws = {}
+        # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must still use every host core (rank 0 is the only rank
+        # that runs it), so the BLAS pools are sized explicitly
+        try:
+            import threadpoolctl
+            self._blas_limits = threadpoolctl.threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
+        except Exception:
+            self._blas_limits = None
 
     def run(self, N, step):
         x, y, hp0 = make_problem(N, D_FULL)
