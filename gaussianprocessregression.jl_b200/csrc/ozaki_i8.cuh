@@ -552,7 +552,7 @@ inline bool oz_make_map_k(CUtensorMap* map, const int8_t* base, uint64_t Kp, uin
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 using OzWinLo = OzWin<8, 128, 32, 6, 9>;
-using OzWinHi = OzWin<8, 128, 64, 2, 5>;
+using OzWinHi = OzWin<8, 128, 64, 2, 5>;      // (k-tiles of 32 with seven stages instead of 64 with three: measured slower, 20.1 vs 18.7 ms per 8192^3 nine-digit product)
 using OzWin9X = OzWin<9, 128, 32, 10, 10>;    // ninth digit: the extra diagonal d = 10 (pairs (1,9) .. (9,1))
 using OzWin9Z = OzWin<9, 96, 32, 6, 10>;      // nine digits in TWO windows: d = 6..10 in five 96-column accumulators (480 TMEM columns, 35 pairs)
 using OzWin9Y = OzWin<9, 256, 32, 10, 10>;    // the same with 128 x 256 tiles (one accumulator of 256 columns): 25% fewer operand bytes per product
