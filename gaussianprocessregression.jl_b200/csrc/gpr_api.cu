@@ -67,6 +67,9 @@ struct gpr_ctx {
   int oz_active = 0;            // digits in force for the model being worked on (set by the entry points)
   int64_t ozaki_min = 1024;
   int ozaki_lauum = 9;          // option "ozaki_lauum": digits of the INT8 route for the W^T W product of the inverse (0 = DMMA, 8, 9 = default)
+  int64_t ozaki_win_mink = 8192;   // option "ozaki_win_mink": two-diagonal-window form (128 x 128 tiles) of the 8-digit product for products with M, N,
+                                   // K >= this (0 = never): the windows pay for their second pass over the digit planes only on the largest products --
+                                   // N = 32768 evaluation 680 -> 667 ms at 8192, 670 at 4096, 680 at 2048 (profiles/ozaki_win_mink_r2an.log)
   int ozaki_split = 9;          // option "ozaki_split": digits of the INT8 route for the split-predict mean products (0 = DMMA, 8, 9)
   int ozaki_lauum_map = 0;      // option "ozaki_lauum_map": nine-digit INT8 form also for the rank-nb W W^T products of the block-cyclic lauum (slower: off)
   int ozaki_windows = 0;        // option "ozaki_windows" (A/B switches of csrc/ozaki_i8.cuh): bit 0 two-diagonal-window 128 x 128 kernel for the
@@ -162,7 +165,8 @@ struct CudaBE {
       if (ctx->oz_ws_bytes >= need) {
         for (int64_t z = 0; z < batch; ++z) {
           note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, digits, alpha, A + z * sA, lda, B + z * sB, ldb, beta, C + z * sC, ldc,
-                                  flags | ((ctx->ozaki_windows & 1) ? 512 : 0) | ((ctx->ozaki_windows & 2) ? 1024 : 0) | ((ctx->ozaki_windows & 4) ? 4096 : 0), ctx->oz_ws));
+                                  flags | (((ctx->ozaki_windows & 1) || (ctx->ozaki_win_mink > 0 && std::min(K, std::min(M, N)) >= ctx->ozaki_win_mink)) ? 512 : 0) |
+                                      ((ctx->ozaki_windows & 2) ? 1024 : 0) | ((ctx->ozaki_windows & 4) ? 4096 : 0), ctx->oz_ws));
           ctx->launches += 3;
         }
         return;
@@ -771,6 +775,7 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
     ctx->ozaki_lauum = (int)value; return GPR_OK;
   }
   if (!strcmp(name, "ozaki_windows")) { ctx->ozaki_windows = (int)value & 7; return GPR_OK; }
+  if (!strcmp(name, "ozaki_win_mink")) { ctx->ozaki_win_mink = std::max<int64_t>(0, value); return GPR_OK; }
   if (!strcmp(name, "ozaki_split")) {
     if (value != 0 && value != 8 && value != 9) return fail(ctx, GPR_ERR_ARG, "ozaki_split: 0 (DMMA), 8 or 9 digits");
     ctx->ozaki_split = (int)value; return GPR_OK;
