@@ -66,24 +66,45 @@ SM100(md::GPRModel{K,T,P,X}) where {K,T,P,X} = SM100{K,T,P,X,typeof(md)}(md)
 Base.getproperty(s::SM100, f::Symbol) = f === :md ? getfield(s, :md) : getproperty(getfield(s, :md), f)
 Base.propertynames(s::SM100) = (:md, propertynames(getfield(s, :md))...)
 GaussianProcessRegression.get_sample(s::SM100) = get_sample(s.md)      # src/models.jl:39-45 is typed on GPRModel
+# src/models.jl:6-16 prints size(getfield(md, f)) for every field and src/models.jl:47-49 calls typeof(md)(covar, hp, x, y):
+# neither works on a one-field wrapper, so both are forwarded (cv_batch / cv_step build their fold models with `similar`)
+Base.show(io::IO, m::MIME"text/plain", s::SM100) = (println(io, "SM100 wrapper of"); show(io, m, s.md))
+Base.similar(s::SM100, hp, x, y) = SM100(similar(s.md, hp, x, y))
 
 mutable struct Handle
     c::Ctx
     h::Ptr{Cvoid}
+    x::Matrix{Float64}      # what the device holds: the reference reads md.x / md.y afresh at every call, and its callers
+    y::Matrix{Float64}      # mutate them in place between calls (md.y .+= dy, src/update_model.jl:36; mdt.x .= ..., src/crossval.jl:27-30)
 end
+_ymat(y) = y isa AbstractVector ? reshape(y, :, 1) : y
 function Handle(md)
     c = ctx()
     t = comp_types(md.covar)
-    y = md.y isa AbstractVector ? reshape(md.y, :, 1) : md.y
+    x = Matrix{Float64}(md.x)
+    y = Matrix{Float64}(_ymat(md.y))
     r = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:gpr_model_create, LIB), Cint,
         (Ptr{Cvoid}, Ptr{Cint}, Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Ref{Ptr{Cvoid}}),
-        c.h, t, length(t), size(md.x, 1), size(md.x, 2), md.x, y, size(y, 2), md.train_axis, r)
+        c.h, t, length(t), size(x, 1), size(x, 2), x, y, size(y, 2), md.train_axis, r)
     check(c, rc)
-    h = Handle(c, r[])
+    h = Handle(c, r[], x, y)
     # The Handle keeps its Ctx reachable, but at process exit finalizers run in no particular order: the library
     # tolerates that (gpr_ctx_destroy releases the models it still owns; gpr_model_destroy on such a handle is a no-op).
-    finalizer(x -> ccall((:gpr_model_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), h)
+    finalizer(o -> ccall((:gpr_model_destroy, LIB), Cint, (Ptr{Cvoid},), o.h), h)
+end
+"re-upload x / y when the caller changed them since the last call (O(N D) host compare; gpr_model_set_* drop the cached factor)"
+function _sync!(h::Handle, md)
+    if md.x != h.x
+        copyto!(h.x, md.x)
+        check(h.c, ccall((:gpr_model_set_x, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), h.h, h.x))
+    end
+    y = _ymat(md.y)
+    if y != h.y
+        copyto!(h.y, y)
+        check(h.c, ccall((:gpr_model_set_y, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), h.h, h.y))
+    end
+    return nothing
 end
 
 struct SM100LossCache <: AbstractLossCache;    hp::Vector{Float64}; h::Handle; end
@@ -106,9 +127,11 @@ function _update!(h::Handle, hp, want_inverse::Bool; ϵ = 1e-8)
         h.h, hp, length(hp), ϵ, want_inverse, info)
     check(h.c, rc, info[])
 end
-update_cache!(tc::SM100LossCache, hp, md) = (tc.hp .= hp; _update!(tc.h, tc.hp, false))
-update_cache!(tc::SM100GradCache, hp, md) = (tc.hp .= hp; _update!(tc.h, tc.hp, true))
-update_cache!(pc::Union{SM100PredictCache,SM100SplitPredictCache}, md) = _update!(pc.h, md.params, false)
+update_cache!(tc::SM100LossCache, hp, md) = (tc.hp .= hp; _sync!(tc.h, md); _update!(tc.h, tc.hp, false))
+update_cache!(tc::SM100GradCache, hp, md) = (tc.hp .= hp; _sync!(tc.h, md); _update!(tc.h, tc.hp, true))
+# md::AbstractGPRModel, not Any: an untyped md would be ambiguous with update_cache!(::AbstractPredictCache, ::AbstractGPRModel) (src/predict.jl:29)
+update_cache!(pc::Union{SM100PredictCache,SM100SplitPredictCache}, md::AbstractGPRModel) =
+    (_sync!(pc.h, md); _update!(pc.h, Vector{Float64}(md.params), false))
 
 function loss(::MarginalLikelihood, md::SM100, tc::Union{SM100LossCache,SM100GradCache})
     F = Ref{Float64}(0.0)
@@ -120,7 +143,8 @@ function grad!(∇L, ::MarginalLikelihood, md::SM100, tc::SM100GradCache)
     return nothing
 end
 # fused single-call forms of src/cost.jl:50-70 (Optim only_fg! contract: F / G may be `nothing`)
-function _fg!(F, G, v, tc::SM100GradCache, logscale::Bool)
+function _fg!(F, G, v, md, tc::SM100GradCache, logscale::Bool)
+    _sync!(tc.h, md)
     f = Ref{Float64}(0.0); info = Ref{Int64}(0)
     rc = ccall((:gpr_nlml_grad, LIB), Cint,
         (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cdouble, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
@@ -128,8 +152,8 @@ function _fg!(F, G, v, tc::SM100GradCache, logscale::Bool)
     check(tc.h.c, rc, info[])
     F === nothing ? nothing : f[]
 end
-loss_grad!(::MarginalLikelihood, F, G, hp, md::SM100, tc::SM100GradCache) = _fg!(F, G, hp, tc, false)
-log_loss_grad!(::MarginalLikelihood, F, G, log_hp, md::SM100, tc::SM100GradCache) = _fg!(F, G, log_hp, tc, true)
+loss_grad!(::MarginalLikelihood, F, G, hp, md::SM100, tc::SM100GradCache) = _fg!(F, G, hp, md, tc, false)
+log_loss_grad!(::MarginalLikelihood, F, G, log_hp, md::SM100, tc::SM100GradCache) = _fg!(F, G, log_hp, md, tc, true)
 
 "tc.kchol_base / tc.α / tc.K⁻¹ of the reference caches (test/test_loss.jl:46-48)"
 function fetch(h::Handle, which::Cint, dims...)
@@ -169,7 +193,7 @@ end
 # ---------------------------------------------------------------------------------------------------------
 # Multi-GPU gradient cache (BASELINE.json config 5: N = 131072, 137 GB of FP64 K): K / U / K^-1 block-cyclic over
 # `devices`, one Julia process drives all of them (gpr_mgpu_*, include/gpr_sm100a.h).  Drop-in for
-# SM100GradCache in loss_grad! / log_loss_grad!, hence in `train(SM100Multi(md; devices = 0:7), ...)`.
+# SM100GradCache in loss_grad! / log_loss_grad!; `train(SM100Multi(md; devices = 0:7), ...)` builds it (wrapper below).
 # ---------------------------------------------------------------------------------------------------------
 mutable struct MultiHandle
     mg::Ptr{Cvoid}
@@ -178,33 +202,39 @@ end
 struct SM100MultiGradCache <: AbstractGradCache
     hp::Vector{Float64}
     h::MultiHandle
+    x::Matrix{Float64}      # snapshots: the distributed model is immutable, a changed md.x / md.y is an error, not a silent stale result
+    y::Matrix{Float64}
 end
 function mcheck(h::MultiHandle, rc::Cint, info::Int64 = 0)
     rc == 0 && return nothing
     rc == 1 && throw(PosDefException(info))
     error("libgpr_sm100a: ", unsafe_string(ccall((:gpr_mgpu_last_error, LIB), Cstring, (Ptr{Cvoid},), h.mg)))
 end
-function SM100MultiGradCache(md::GPRModel; devices = 0:(ccall((:gpr_device_count, LIB), Cint, ()) - 1), nb::Integer = 1024)
+default_nb(md) = size(md.x, 2) >= 65536 ? 2048 : 1024      # block-column width (DESIGN.md 7: 2048 feeds the INT8 route at large N)
+all_devices() = 0:(ccall((:gpr_device_count, LIB), Cint, ()) - 1)
+function SM100MultiGradCache(md::GPRModel; devices = all_devices(), nb::Integer = default_nb(md))
     devs = Cint.(collect(devices))
     mg = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:gpr_mgpu_create, LIB), Cint, (Cint, Ptr{Cint}, Int64, Ref{Ptr{Cvoid}}), length(devs), devs, nb, mg)
     rc == 0 || error("gpr_mgpu_create: ", unsafe_string(ccall((:gpr_mgpu_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
     t = comp_types(md.covar)
-    y = md.y isa AbstractVector ? reshape(md.y, :, 1) : md.y
+    x = Matrix{Float64}(md.x)
+    y = Matrix{Float64}(_ymat(md.y))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     mh = MultiHandle(mg[], C_NULL)
+    finalizer(mh) do o           # registered before the model exists: a failed model creation still releases the devices
+        o.h == C_NULL || ccall((:gpr_mgpu_model_destroy, LIB), Cint, (Ptr{Cvoid},), o.h)
+        ccall((:gpr_mgpu_destroy, LIB), Cint, (Ptr{Cvoid},), o.mg)
+    end
     rc = ccall((:gpr_mgpu_model_create, LIB), Cint,
         (Ptr{Cvoid}, Ptr{Cint}, Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Cint, Ref{Ptr{Cvoid}}),
-        mg[], t, length(t), size(md.x, 1), size(md.x, 2), md.x, y, size(y, 2), md.train_axis, h)
+        mg[], t, length(t), size(x, 1), size(x, 2), x, y, size(y, 2), md.train_axis, h)
     mcheck(mh, rc)
     mh.h = h[]
-    finalizer(mh) do x
-        ccall((:gpr_mgpu_model_destroy, LIB), Cint, (Ptr{Cvoid},), x.h)
-        ccall((:gpr_mgpu_destroy, LIB), Cint, (Ptr{Cvoid},), x.mg)
-    end
-    SM100MultiGradCache(copy(md.params), mh)
+    SM100MultiGradCache(Vector{Float64}(md.params), mh, x, y)
 end
-function _fg!(F, G, v, tc::SM100MultiGradCache, logscale::Bool)
+function _fg!(F, G, v, md, tc::SM100MultiGradCache, logscale::Bool)
+    (md.x == tc.x && _ymat(md.y) == tc.y) || error("SM100MultiGradCache: x / y changed; build a new cache")
     f = Ref{Float64}(0.0); info = Ref{Int64}(0)
     rc = ccall((:gpr_mgpu_nlml_grad, LIB), Cint,
         (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cdouble, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
@@ -212,8 +242,27 @@ function _fg!(F, G, v, tc::SM100MultiGradCache, logscale::Bool)
     mcheck(tc.h, rc, info[])
     F === nothing ? nothing : f[]
 end
-loss_grad!(::MarginalLikelihood, F, G, hp, md, tc::SM100MultiGradCache) = _fg!(F, G, hp, tc, false)
-log_loss_grad!(::MarginalLikelihood, F, G, log_hp, md, tc::SM100MultiGradCache) = _fg!(F, G, log_hp, tc, true)
+loss_grad!(::MarginalLikelihood, F, G, hp, md, tc::SM100MultiGradCache) = _fg!(F, G, hp, md, tc, false)
+log_loss_grad!(::MarginalLikelihood, F, G, log_hp, md, tc::SM100MultiGradCache) = _fg!(F, G, log_hp, md, tc, true)
+
+"""
+Wrapper that makes `train(SM100Multi(md; devices = 0:7), MarginalLikelihood(); method = LBFGS())` build the multi-GPU gradient
+cache: `loss_grad_cache(cost)(md)` (src/train.jl:38,49) is `MllGradCache(md)`, overloaded below.  Same supertype parameters as
+`SM100`, so `islog` (src/cost.jl:4-8) dispatches on the wrapped kernel.  First-order methods only (the distributed handle has no
+loss-only / predict path; use `SM100` for those).
+"""
+struct SM100Multi{K<:AbstractKernel,T,P<:AbstractArray{T},X<:AbstractArray{T,2},M<:GPRModel{K,T,P,X}} <: AbstractGPRModel{K,T,P,X}
+    md::M
+    devices::Vector{Cint}
+    nb::Int
+end
+SM100Multi(md::GPRModel{K,T,P,X}; devices = all_devices(), nb::Integer = default_nb(md)) where {K,T,P,X} =
+    SM100Multi{K,T,P,X,typeof(md)}(md, Cint.(collect(devices)), Int(nb))
+Base.getproperty(s::SM100Multi, f::Symbol) = f in (:md, :devices, :nb) ? getfield(s, f) : getproperty(getfield(s, :md), f)
+Base.propertynames(s::SM100Multi) = (:md, :devices, :nb, propertynames(getfield(s, :md))...)
+Base.show(io::IO, m::MIME"text/plain", s::SM100Multi) = (println(io, "SM100Multi wrapper (devices ", Int.(s.devices), ") of"); show(io, m, s.md))
+GaussianProcessRegression.get_sample(s::SM100Multi) = get_sample(s.md)
+GaussianProcessRegression.MllGradCache(s::SM100Multi) = SM100MultiGradCache(s.md; devices = s.devices, nb = s.nb)
 
 # ---------------------------------------------------------------------------------------------------------
 # sample(N::NormalDistribution) on the device (src/distributions.jl:30-35): the draws stay on the Julia side (rng),
