@@ -34,6 +34,8 @@
 // accumulator.  Used for NINE digits (45 products: the W^T W of the inverse, whose operand columns span many orders of magnitude
 // under one scale): d = 6..10 in five 96-column accumulators, then d = 2..5, each launch accumulating into C.
 //
+// Launch flags of launch_ozaki_dgemm only: 512 two-window form of the 8-digit product, 1024 / 4096 window layouts of the 9-digit
+// product, 8192 cluster pairs with a multicast op(B) tile for the 128 x 128 window kernels.
 // Forms (flags, same meaning as dgemm_sm100.cuh): upper only (1), K-from-N (2: triangular operand, masked in the digit extraction),
 // skip tile (0,0) (64), and the tile-mapped forms of the block-cyclic multi-GPU drivers: MAP_UPPER (8), MAP_KUPTO (16: per-column
 // contraction limit, masked in the digit extraction; long K comes in k-chunks <= 32768 with their own scales), MAP_BROWS (32).
@@ -148,6 +150,34 @@ __device__ __forceinline__ void tc_mma_i8(unsigned tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
+// ---- thread-block-cluster primitives of the multicast variant of the window kernel (oz_gemm_win_mc_kernel) ----
+__device__ __forceinline__ unsigned oz_cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+// every thread of every CTA of the cluster (release / acquire at cluster scope)
+__device__ __forceinline__ void oz_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// one TMA load delivered to the SAME shared-memory offset of every CTA in `mask`, completing bytes on the mbarrier at the same
+// offset in each of them (L2 is read once for the whole cluster)
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6}], [%2], %3;\n" ::"r"(
+          (unsigned)__cvta_generic_to_shared(smem_dst)),
+      "l"((uint64_t)map), "r"((unsigned)__cvta_generic_to_shared(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// completion of the MMAs issued so far arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, unsigned short mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // K-major operand tile with 64-byte rows, SWIZZLE_64B: 8-row groups are 512 bytes apart
 __device__ __forceinline__ uint64_t oz_smem_desc(const void* p) {
   const unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -371,11 +401,19 @@ template <int BK> __device__ __forceinline__ uint64_t oz_smem_desc_k(const void*
   return d;
 }
 
-template <int S, int BN, int BK, int DLO, int DHI>
-__global__ void __launch_bounds__(OZ_THREADS, 1)
-oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+// MC = 1 (oz_gemm_win_mc_kernel, launched as clusters of two CTAs along x): the pair works on the row tiles (2j, 2j + 1) of ONE
+// column tile, so both need the same op(B) tile.  Each CTA loads its own op(A) tile and HALF of the digit planes of the op(B) tile,
+// multicast into both CTAs' shared memory: 25 % fewer bytes L2 -> SM per product (the windows are bound by that fill, not by the
+// tensor pipe: profiles/ozaki_ncu_full_r2t.md).  Protocol: full[s] of a CTA receives its own A bytes + both halves of B; a stage may
+// only be refilled once BOTH CTAs' MMAs have read it, so empty[s] counts two arrivals and every tcgen05.commit of a stage arrives
+// on both CTAs' barriers; cluster barriers after the mbarrier initialisation and before exit keep either CTA from signalling a
+// peer that is not there.  A CTA whose tile is skipped (below the diagonal of an upper-only product, tile (0,0) of a skip-tile
+// product) while its partner's is not runs as a ghost: same loads, same MMAs, no stores.
+template <int S, int BN, int BK, int DLO, int DHI, int MC>
+__device__ __forceinline__ void oz_gemm_win_body(const OzParams& p, const CUtensorMap* pmapA, const CUtensorMap* pmapB) {
   using W = OzWin<S, BN, BK, DLO, DHI>;
   constexpr int NST = W::NST, PL = W::PL;
+  static_assert(!MC || (PL % 2 == 0), "the multicast variant splits the digit planes of op(B) in two halves");
   extern __shared__ unsigned char oz_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * W::STAGE);
@@ -397,8 +435,22 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
   }
   const int blk_n = (tile_n * BN) >> 7;                       // first 128-block of the tile's columns (BN = 256 spans two)
   if (tile_n * BN >= p.N) return;
-  if ((p.flags & 1) && tile_m > ((tile_n * BN + BN - 1) >> 7)) return;
-  if ((p.flags & 64) && tile_m == 0 && blk_n == 0) return;
+  [[maybe_unused]] bool ghost = false;
+  [[maybe_unused]] unsigned crank = 0;
+  if constexpr (!MC) {
+    if ((p.flags & 1) && tile_m > ((tile_n * BN + BN - 1) >> 7)) return;
+    if ((p.flags & 64) && tile_m == 0 && blk_n == 0) return;
+  } else {
+    // the partner holds row tile tile_m ^ 1 of the same column tile (grid x even, GM even: consecutive CTAs of a pair are
+    // consecutive row tiles); the pair leaves only if BOTH tiles are skipped
+    crank = oz_cluster_ctarank();
+    const int last_blk = (tile_n * BN + BN - 1) >> 7;
+    const bool skip_me = ((p.flags & 1) && tile_m > last_blk) || ((p.flags & 64) && tile_m == 0 && blk_n == 0);
+    const int pm = tile_m ^ 1;
+    const bool skip_peer = ((p.flags & 1) && pm > last_blk) || ((p.flags & 64) && pm == 0 && blk_n == 0);
+    if (skip_me && skip_peer) return;
+    ghost = skip_me;
+  }
   int gt = 0;
   if (p.flags & 8) {
     gt = p.col_gtile[blk_n];
@@ -412,7 +464,7 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
   const int nB = (p.flags & 32) ? gt * 128 + (n0 & 127) : n0;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], MC ? 2 : 1); }
     mbar_init(tfull, 1);
     mbar_fence_init();
   }
@@ -422,6 +474,7 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) oz_cluster_sync();      // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
 
@@ -432,8 +485,14 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
         if (kt >= NST) oz_wait(&empty[s], (unsigned)((kt / NST - 1) & 1));
         unsigned char* st = smem + (size_t)s * W::STAGE;
         mbar_expect_tx(&full[s], (unsigned)W::STAGE);
-        tma_load_3d(st, &mapA, &full[s], (kt0 + kt) * BK, m0, 0);                               // PL x 128 x BK
-        tma_load_3d(st + (size_t)PL * OZ_BM * BK, &mapB, &full[s], (kt0 + kt) * BK, nB, 0);     // PL x BN  x BK
+        tma_load_3d(st, pmapA, &full[s], (kt0 + kt) * BK, m0, 0);                               // PL x 128 x BK
+        if constexpr (!MC) {
+          tma_load_3d(st + (size_t)PL * OZ_BM * BK, pmapB, &full[s], (kt0 + kt) * BK, nB, 0);   // PL x BN  x BK
+        } else {
+          // planes crank * PL/2 .. of the op(B) tile into both CTAs (the map's box holds PL / 2 planes)
+          tma_load_3d_mc(st + (size_t)PL * OZ_BM * BK + (size_t)crank * (PL / 2) * BN * BK, pmapB, &full[s], (kt0 + kt) * BK, nB,
+                         (int)crank * (PL / 2), (unsigned short)0x3);
+        }
       }
     }
   } else if (warp == 1) {
@@ -468,7 +527,7 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
             }
           }
         }
-        tc_commit(&empty[s]);
+        if constexpr (MC) tc_commit_mc(&empty[s], (unsigned short)0x3); else tc_commit(&empty[s]);
       }
       __syncwarp();
     }
@@ -488,6 +547,7 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
     double* Crow = p.C + (long long)(m0 + row) + (long long)n0 * p.ldc;
     for (int c0 = 0; c0 < BN; c0 += 16) {
       if (n0 + c0 >= p.N) break;
+      if constexpr (MC) { if (ghost) break; }
       double acc[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = 0.0;
@@ -518,10 +578,23 @@ oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, c
     tc_fence_before();
   }
   __syncthreads();
+  if constexpr (MC) oz_cluster_sync();      // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
   }
+}
+
+template <int S, int BN, int BK, int DLO, int DHI>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm_win_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+  oz_gemm_win_body<S, BN, BK, DLO, DHI, 0>(p, &mapA, &mapB);
+}
+// cluster pairs with a multicast op(B) tile; mapB's box holds PL / 2 digit planes
+template <int S, int BN, int BK, int DLO, int DHI>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm_win_mc_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+  oz_gemm_win_body<S, BN, BK, DLO, DHI, 1>(p, &mapA, &mapB);
 }
 
 // ---- host side ----
@@ -563,11 +636,31 @@ inline cudaError_t oz_set_attr() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<9, 128, 32, 10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWin9X::SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<9, 256, 32, 10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWin9Y::SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_kernel<9, 96, 32, 6, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWin9Z::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_mc_kernel<8, 128, 32, 6, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWinLo::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_win_mc_kernel<8, 128, 64, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OzWinHi::SMEM);
   if (e == cudaSuccess) e = oz_set_attr_s<8>();
   if (e == cudaSuccess) e = oz_set_attr_s<7>();
   if (e == cudaSuccess) e = oz_set_attr_s<6>();
   if (e == cudaSuccess) e = oz_set_attr_s<2>();
   return e;
+}
+
+// launch of a window kernel as clusters of two CTAs along x (grid.x even)
+template <typename Kern>
+inline cudaError_t oz_launch_pairs(Kern kern, dim3 grid, size_t smem, cudaStream_t st, const OzParams& p, const CUtensorMap& a, const CUtensorMap& b) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(OZ_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p, a, b);
 }
 
 // workspace (bytes) for the digit planes and scales of one product
@@ -606,7 +699,9 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
   }
   CUtensorMap mA, mB;
   if (!oz_make_map(&mA, pa, Kp, (uint64_t)Ra, S, OZ_BM) || !oz_make_map(&mB, pb, Kp, (uint64_t)Rb, S, OZ_BN)) return cudaErrorInvalidValue;
-  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~(512 | 1024 | 4096), k_off, col_gtile, row_gtile0, k_gtile0, E, lde};
+  OzParams p{M, N, K, S, alpha, beta, C, ldc, sa, sb, flags & ~(512 | 1024 | 4096 | 8192), k_off, col_gtile, row_gtile0, k_gtile0, E, lde};
+  // flag 8192: cluster pairs with a multicast op(B) tile for the 128 x 128 window kernels (plain forms with an even number of row tiles)
+  const bool mc = (flags & 8192) && !(flags & (8 | 16 | 32)) && (M % (2 * OZ_BM)) == 0;
   if (S == 9) {
     // nine digits (products whose operands span several orders of magnitude under one scale per column: the W^T W of the inverse).
     // Nine 64-column accumulators do not fit the 512 TMEM columns, so the diagonals are summed in windows, lowest order first, each
@@ -627,6 +722,12 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
       oz_gemm_win_kernel<9, 96, 32, 6, 10><<<dim3(M / OZ_BM, (N + 95) / 96), OZ_THREADS, OzWin9Z::SMEM, st>>>(p, aZ, bZ);
       OzParams pz = p;
       pz.beta = 1.0;
+      if (mc) {
+        CUtensorMap bHiH;
+        if (!oz_make_map_k(&bHiH, pb, Kp, (uint64_t)Rb, S, OzWinHi::PL / 2, 128, 64)) return cudaErrorInvalidValue;
+        cudaError_t e = oz_launch_pairs(oz_gemm_win_mc_kernel<8, 128, 64, 2, 5>, grid2, OzWinHi::SMEM, st, pz, aHi, bHiH);
+        return e != cudaSuccess ? e : cudaGetLastError();
+      }
       oz_gemm_win_kernel<8, 128, 64, 2, 5><<<grid2, OZ_THREADS, OzWinHi::SMEM, st>>>(pz, aHi, bHi);
       return cudaGetLastError();
     }
@@ -653,9 +754,17 @@ inline cudaError_t launch_ozaki_dgemm(cudaStream_t st, int M, int N, int K, int 
         !oz_make_map_k(&aHi, pa, Kp, (uint64_t)Ra, S, OzWinHi::PL, OZ_BM, 64) || !oz_make_map_k(&bHi, pb, Kp, (uint64_t)Rb, S, OzWinHi::PL, 128, 64))
       return cudaErrorInvalidValue;
     dim3 grid2(M / OZ_BM, N / 128);
-    oz_gemm_win_kernel<8, 128, 32, 6, 9><<<grid2, OZ_THREADS, OzWinLo::SMEM, st>>>(p, aLo, bLo);     // low-order diagonals first: C = ... + beta C
     OzParams p2 = p;
     p2.beta = 1.0;
+    if (mc) {
+      CUtensorMap bLoH, bHiH;
+      if (!oz_make_map_k(&bLoH, pb, Kp, (uint64_t)Rb, S, OzWinLo::PL / 2, 128, 32) || !oz_make_map_k(&bHiH, pb, Kp, (uint64_t)Rb, S, OzWinHi::PL / 2, 128, 64))
+        return cudaErrorInvalidValue;
+      cudaError_t e = oz_launch_pairs(oz_gemm_win_mc_kernel<8, 128, 32, 6, 9>, grid2, OzWinLo::SMEM, st, p, aLo, bLoH);
+      if (e == cudaSuccess) e = oz_launch_pairs(oz_gemm_win_mc_kernel<8, 128, 64, 2, 5>, grid2, OzWinHi::SMEM, st, p2, aHi, bHiH);
+      return e != cudaSuccess ? e : cudaGetLastError();
+    }
+    oz_gemm_win_kernel<8, 128, 32, 6, 9><<<grid2, OZ_THREADS, OzWinLo::SMEM, st>>>(p, aLo, bLo);     // low-order diagonals first: C = ... + beta C
     oz_gemm_win_kernel<8, 128, 64, 2, 5><<<grid2, OZ_THREADS, OzWinHi::SMEM, st>>>(p2, aHi, bHi);    // high-order diagonals accumulate
     return cudaGetLastError();
   }

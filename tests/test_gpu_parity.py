@@ -519,6 +519,41 @@ def test_ozaki_nine_digit_product(gpr):
         ctx.close()
 
 
+def test_ozaki_multicast_pairs_are_bit_identical(gpr):
+    """csrc/ozaki_i8.cuh, launch flag 8192 (ctx option "ozaki_mc"): the 128 x 128 window kernels launched as clusters of two CTAs that
+    share one op(B) tile through a multicast TMA load.  Integer products are exact and the epilogue is the same code, so the result
+    must equal the single-CTA windows BIT FOR BIT -- for the 8-digit two-window product (flag 512) and the second window of the
+    9-digit product, in the plain, upper-only (ghost CTAs below the diagonal), K-from-N and skip-tile(0,0) forms, with beta != 0,
+    on row counts that are multiples of 256 (pairs) and on one that is not (falls back to single CTAs)."""
+    from gpr_sm100a import _ffi
+    rng = np.random.default_rng(2024)
+    ctx = gpr.Context(0)
+    try:
+        for (M, N, K, S, base, beta) in ((512, 512, 1024, 8, 512, 0.0), (768, 512, 2048, 8, 512, 0.5), (512, 768, 512, 8, 512 | 1, 1.0),
+                                         (1024, 1024, 1024, 8, 512 | 1 | 2, 0.0), (512, 512, 640, 8, 512 | 64, 1.0), (512, 512, 640, 8, 512 | 1 | 64, 1.0),
+                                         (1024, 1024, 1024, 9, 0, 0.0), (768, 768, 768, 9, 1 | 2, 0.25), (384, 384, 512, 8, 512, 0.0),
+                                         (2304, 2304, 4096, 8, 512 | 1, 1.0)):
+            if base & 2:
+                A = np.tril(rng.standard_normal((K, M)))
+                for J in range(M // 128):
+                    A[:128 * J, 128 * J:128 * (J + 1)] = 1e30          # garbage above the diagonal blocks, masked by the digit extraction
+                B = A
+            elif S == 9:
+                A = rng.standard_normal((K, M)) * np.exp(rng.uniform(-8, 0, (K, M)))
+                B = A
+            else:
+                A, B = rng.standard_normal((K, M)), rng.standard_normal((K, N))
+            A, B = np.asfortranarray(A), np.asfortranarray(B)
+            C0 = np.asfortranarray(rng.standard_normal((M, N)))
+            C1, _ = _ffi.dbg_ozaki_dgemm(ctx, 1.0, A, B, beta, C0, S=S, flags=base)
+            C2, _ = _ffi.dbg_ozaki_dgemm(ctx, 1.0, A, B, beta, C0, S=S, flags=base | 8192)
+            assert np.array_equal(C1, C2), (M, N, K, S, base, float(np.abs(C1 - C2).max()))
+            if base & 64:
+                assert np.array_equal(C2[:128, :128], C0[:128, :128])      # tile (0,0) untouched by the ghost CTA
+    finally:
+        ctx.close()
+
+
 def test_ozaki_route_keeps_nlml_parity(gpr):
     """The INT8-tensor-core route of the blocked factorization (ctx option "ozaki" = 8 digits for potrf, trtri and the
     prediction solves; "ozaki_lauum" = 9 digits for the W^T W product of the inverse) against the oracle on a model large
