@@ -82,7 +82,8 @@ struct gpr_ctx {
                                 // 8-digit products; bit 2 the THREE-window form of the 9-digit product (d = 10 | 6..9 | 2..5) instead of the
                                 // default two windows (d = 6..10 with 128 x 96 tiles | 2..5), bit 1 with it: 128 x 256 tiles for d = 10
   int ozaki_mc = oz_mc_default();   // option "ozaki_mc": the 128 x 128 window kernels of the INT8 route run as clusters of two CTAs that share one
-                                    // op(B) tile through a multicast TMA load (csrc/ozaki_i8.cuh, launch flag 8192); results are bit-identical
+                                    // op(B) tile through a multicast TMA load (csrc/ozaki_i8.cuh, launch flag 8192); results are bit-identical,
+                                    // the whole GPU suite passes with it, and it is measured neutral (668 -> 667 ms per evaluation): off
   int64_t ozaki_kchunk = 32768; // option "ozaki_kchunk": k-chunk of the long-K tile-mapped products (tests lower it to exercise the chunk loop)
   int64_t ozaki_panel = 32768;  // option "ozaki_panel": k-panel of the W^T W product (own digit scales per panel)
   int oz_mask = 11, oz_cur = 8;   // option "ozaki_phases": bit 0 potrf, 1 trtri, 3 everything else (prediction solves); the W^T W product of the

@@ -403,8 +403,11 @@ template <int BK> __device__ __forceinline__ uint64_t oz_smem_desc_k(const void*
 
 // MC = 1 (oz_gemm_win_mc_kernel, launched as clusters of two CTAs along x): the pair works on the row tiles (2j, 2j + 1) of ONE
 // column tile, so both need the same op(B) tile.  Each CTA loads its own op(A) tile and HALF of the digit planes of the op(B) tile,
-// multicast into both CTAs' shared memory: 25 % fewer bytes L2 -> SM per product (the windows are bound by that fill, not by the
-// tensor pipe: profiles/ozaki_ncu_full_r2t.md).  Protocol: full[s] of a CTA receives its own A bytes + both halves of B; a stage may
+// multicast into both CTAs' shared memory: 25 % fewer bytes read from L2 per product.  MEASURED NEUTRAL (profiles/
+// ozaki_multicast_ab_r2ap.log: 8192^3 14.76 -> 14.74 ms with 8 digits, 18.80 -> 18.23 ms with 9; N = 32768 evaluation 668 -> 667 ms,
+// results bit-identical), so it is off by default: what limits the windows is not the L2 read side of the fill but what each SM
+// takes in and reads back from shared memory -- a multicast still delivers every byte of the tile to both SMs; only
+// cta_group::2 (each SM keeps HALF of op(B)) lowers that.  Protocol: full[s] of a CTA receives its own A bytes + both halves of B; a stage may
 // only be refilled once BOTH CTAs' MMAs have read it, so empty[s] counts two arrivals and every tcgen05.commit of a stage arrives
 // on both CTAs' barriers; cluster barriers after the mbarrier initialisation and before exit keep either CTA from signalling a
 // peer that is not there.  A CTA whose tile is skipped (below the diagonal of an upper-only product, tile (0,0) of a skip-tile

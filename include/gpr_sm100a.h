@@ -99,7 +99,9 @@ const char* gpr_last_error(gpr_ctx* ctx);          /* ctx may be NULL: last erro
  *   "ozaki_lauum" digits of the inverse's W^T W product on that route: 9 [default], 8, 0 = DMMA; "ozaki_split" the same for the
  *   split-predict mean products; "ozaki_min" smallest routed M, N, K [1024];
  *   "ozaki_phases" bit mask potrf 1 | trtri 2 | other solves 8 [11]; "ozaki_panel", "ozaki_kchunk" k-panels [32768]; "ozaki_windows" kernel variants [0];
- *   "ozaki_win_mink" smallest M, N, K for the two-window form of the 8-digit product [8192]. */
+ *   "ozaki_win_mink" smallest M, N, K for the two-window form of the 8-digit product [8192];
+ *   "ozaki_mc" 0/1 [0; environment GPR_OZ_MC overrides the default]: the 128 x 128 window kernels of that route as clusters of two CTAs
+ *   sharing one op(B) tile through a multicast TMA load (bit-identical results; measured neutral, profiles/ozaki_multicast_ab_r2ap.log). */
 int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value);
 int64_t gpr_ctx_launch_count(gpr_ctx* ctx);        /* kernels launched by this context so far */
 
