@@ -51,11 +51,6 @@ struct Timer {
 }  // namespace
 
 // default of the "ozaki_mc" context option; GPR_OZ_MC=0 / 1 in the environment overrides it (A/B runs without touching the callers)
-// default of the "ozaki_epi" context option (1 = batched epilogue of the INT8 kernels, 0 = the first, serial form); GPR_OZ_EPI overrides
-static int oz_epi_default() {
-  const char* e = getenv("GPR_OZ_EPI");
-  return (e && *e) ? (atoi(e) != 0) : 0;
-}
 static int oz_mc_default() {
   const char* e = getenv("GPR_OZ_MC");
   return (e && *e) ? (atoi(e) != 0) : 0;
@@ -86,8 +81,6 @@ struct gpr_ctx {
   int ozaki_windows = 0;        // option "ozaki_windows" (A/B switches of csrc/ozaki_i8.cuh): bit 0 two-diagonal-window 128 x 128 kernel for the
                                 // 8-digit products; bit 2 the THREE-window form of the 9-digit product (d = 10 | 6..9 | 2..5) instead of the
                                 // default two windows (d = 6..10 with 128 x 96 tiles | 2..5), bit 1 with it: 128 x 256 tiles for d = 10
-  int ozaki_epi = oz_epi_default(); // option "ozaki_epi": epilogue of the INT8 kernels with the C / E / scale loads of 16 columns issued together and
-                                    // the C tile prefetched to L2 during the main loop (1) or the first, column-serial form (0: launch flag 16384)
   int ozaki_mc = oz_mc_default();   // option "ozaki_mc": the 128 x 128 window kernels of the INT8 route run as clusters of two CTAs that share one
                                     // op(B) tile through a multicast TMA load (csrc/ozaki_i8.cuh, launch flag 8192); results are bit-identical,
                                     // the whole GPU suite passes with it, and it is measured neutral (668 -> 667 ms per evaluation): off
@@ -173,7 +166,7 @@ struct CudaBE {
           const int64_t p0 = std::max<int64_t>(0, p1 - P);
           const int64_t cols = std::min<int64_t>(N, p1);
           note(launch_ozaki_dgemm(ctx->stream, (int)cols, (int)cols, (int)(p1 - p0), digits, alpha, A + p0, lda, B + p0, ldb,
-                                  p1 == K ? beta : 1.0, C, ldc, flags | ((ctx->ozaki_windows & 2) ? 1024 : 0) | ((ctx->ozaki_windows & 4) ? 4096 : 0) | (ctx->ozaki_mc ? 8192 : 0) | (ctx->ozaki_epi ? 0 : 16384), ctx->oz_ws, (int)p0));
+                                  p1 == K ? beta : 1.0, C, ldc, flags | ((ctx->ozaki_windows & 2) ? 1024 : 0) | ((ctx->ozaki_windows & 4) ? 4096 : 0) | (ctx->ozaki_mc ? 8192 : 0), ctx->oz_ws, (int)p0));
           ctx->launches += 2;
         }
         return;
@@ -182,7 +175,7 @@ struct CudaBE {
         for (int64_t z = 0; z < batch; ++z) {
           note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, digits, alpha, A + z * sA, lda, B + z * sB, ldb, beta, C + z * sC, ldc,
                                   flags | (((ctx->ozaki_windows & 1) || (ctx->ozaki_win_mink > 0 && std::min(K, std::min(M, N)) >= ctx->ozaki_win_mink)) ? 512 : 0) |
-                                      ((ctx->ozaki_windows & 2) ? 1024 : 0) | ((ctx->ozaki_windows & 4) ? 4096 : 0) | (ctx->ozaki_mc ? 8192 : 0) | (ctx->ozaki_epi ? 0 : 16384), ctx->oz_ws));
+                                      ((ctx->ozaki_windows & 2) ? 1024 : 0) | ((ctx->ozaki_windows & 4) ? 4096 : 0) | (ctx->ozaki_mc ? 8192 : 0), ctx->oz_ws));
           ctx->launches += 3;
         }
         return;
@@ -213,7 +206,7 @@ struct CudaBE {
       const size_t need = oz_workspace_bytes((int)M, (int)N, (int)K, digits);
       oz_reserve(need);
       if (ctx->oz_ws_bytes >= need) {
-        note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, digits, 1.0, A, lda, B, ldb, beta, C, ldc, (ctx->ozaki_mc ? 8192 : 0) | (ctx->ozaki_epi ? 0 : 16384), ctx->oz_ws, 0,
+        note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, digits, 1.0, A, lda, B, ldb, beta, C, ldc, ctx->ozaki_mc ? 8192 : 0, ctx->oz_ws, 0,
                                 nullptr, 0, 0, E, lde));
         ctx->launches += 3;
         return;
@@ -240,7 +233,7 @@ struct CudaBE {
       const size_t need = oz_workspace_bytes((int)M, (int)N, (int)K, ctx->oz_active);
       oz_reserve(need);
       if (ctx->oz_ws_bytes >= need) {
-        note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, ctx->oz_active, alpha, A, lda, B, ldb, beta, C, ldc, flags | (ctx->ozaki_epi ? 0 : 16384), ctx->oz_ws, 0,
+        note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, ctx->oz_active, alpha, A, lda, B, ldb, beta, C, ldc, flags, ctx->oz_ws, 0,
                                 map.col_gtile, map.row_gtile0));
         ctx->launches += 3;
         return;
@@ -256,7 +249,7 @@ struct CudaBE {
       const size_t need = oz_workspace_bytes((int)M, (int)N, (int)K, 9);
       oz_reserve(need);
       if (ctx->oz_ws_bytes >= need) {
-        note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, 9, alpha, A, lda, B, ldb, beta, C, ldc, flags | (ctx->ozaki_epi ? 0 : 16384), ctx->oz_ws, 0,
+        note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)K, 9, alpha, A, lda, B, ldb, beta, C, ldc, flags, ctx->oz_ws, 0,
                                 map.col_gtile, map.row_gtile0));
         ctx->launches += 4;
         return;
@@ -274,7 +267,7 @@ struct CudaBE {
         for (int64_t k0 = 0; k0 < K; k0 += KC) {
           const int64_t kc = std::min(KC, K - k0);
           note(launch_ozaki_dgemm(ctx->stream, (int)M, (int)N, (int)kc, ctx->oz_active, alpha, A + k0, lda, B + k0, ldb, k0 == 0 ? beta : 1.0, C, ldc,
-                                  flags | (ctx->ozaki_epi ? 0 : 16384), ctx->oz_ws, (int)k0, map.col_gtile, map.row_gtile0, map.k_gtile0));
+                                  flags, ctx->oz_ws, (int)k0, map.col_gtile, map.row_gtile0, map.k_gtile0));
           ctx->launches += 3;
         }
         return;
@@ -792,7 +785,6 @@ int gpr_ctx_set_option(gpr_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "ozaki_windows")) { ctx->ozaki_windows = (int)value & 7; return GPR_OK; }
   if (!strcmp(name, "ozaki_mc")) { ctx->ozaki_mc = value != 0; return GPR_OK; }
-  if (!strcmp(name, "ozaki_epi")) { ctx->ozaki_epi = value != 0; return GPR_OK; }
   if (!strcmp(name, "ozaki_win_mink")) { ctx->ozaki_win_mink = std::max<int64_t>(0, value); return GPR_OK; }
   if (!strcmp(name, "ozaki_split")) {
     if (value != 0 && value != 8 && value != 9) return fail(ctx, GPR_ERR_ARG, "ozaki_split: 0 (DMMA), 8 or 9 digits");

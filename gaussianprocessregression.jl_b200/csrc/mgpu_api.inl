@@ -712,7 +712,7 @@ int gpr_mgpu_destroy(gpr_mgpu* mg) {
 int gpr_mgpu_set_option(gpr_mgpu* mg, const char* name, int64_t value) {
   if (!mg || !name) return GPR_ERR_ARG;
   if (!strcmp(name, "ozaki") || !strcmp(name, "ozaki_min") || !strcmp(name, "ozaki_phases") || !strcmp(name, "ozaki_kchunk") ||
-      !strcmp(name, "ozaki_lauum") || !strcmp(name, "ozaki_lauum_map") || !strcmp(name, "ozaki_epi") || !strcmp(name, "ozaki_mc")) {   // INT8 route of the tile-mapped products
+      !strcmp(name, "ozaki_lauum") || !strcmp(name, "ozaki_lauum_map")) {   // INT8 route of the tile-mapped products
     for (auto& R : mg->rk)
       if (R.ctx && gpr_ctx_set_option(R.ctx, name, value) != GPR_OK) return mfail(mg, GPR_ERR_ARG, R.ctx->err);
     return GPR_OK;

@@ -35,8 +35,7 @@
 // under one scale): d = 6..10 in five 96-column accumulators, then d = 2..5, each launch accumulating into C.
 //
 // Launch flags of launch_ozaki_dgemm only: 512 two-window form of the 8-digit product, 1024 / 4096 window layouts of the 9-digit
-// product, 8192 cluster pairs with a multicast op(B) tile for the 128 x 128 window kernels; 16384 (also seen by the kernels) the
-// serial form of the epilogue instead of the batched one.
+// product, 8192 cluster pairs with a multicast op(B) tile for the 128 x 128 window kernels.
 // Forms (flags, same meaning as dgemm_sm100.cuh): upper only (1), K-from-N (2: triangular operand, masked in the digit extraction),
 // skip tile (0,0) (64), and the tile-mapped forms of the block-cyclic multi-GPU drivers: MAP_UPPER (8), MAP_KUPTO (16: per-column
 // contraction limit, masked in the digit extraction; long K comes in k-chunks <= 32768 with their own scales), MAP_BROWS (32).
@@ -323,45 +322,16 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lanes 32 (warp % 4) .. +31 = rows of the tile =====
-    // Batched form (default; launch flag 16384 = the first, serial form, kept for A/B): a thread owns one row of the tile, and
-    // written naively every column is load C -> fma -> store with the next column's loads queued behind the store -- one full
-    // memory latency per column with nothing else on the SM to hide it (ncu: the d = 2..5 window at 8192^3 keeps the tensor pipe
-    // 57 % busy, at 4096^3 37 %: a fixed ~120 k cycles per 128-column tile).  So the C tile (and E) is pulled towards L2 while the
-    // main loop runs, and the loads of 16 columns (C, E, column scales) are issued together before the accumulators are read.
-    // Same arithmetic in the same order: results are bit-identical to the serial form.
-    const int q = warp & 3;
-    const int row = 32 * q + lane;
-    const bool batched = !(p.flags & 16384);
-    if (batched) {
-      const int t128 = 32 * q + lane;
-      if (p.beta != 0.0) {
-        const double* cbase = p.C + (long long)m0 + (long long)n0 * p.ldc;
-        for (int L = t128; L < OZ_BN * 8; L += 128) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(cbase + (long long)(L >> 3) * p.ldc + (L & 7) * 16));
-      }
-      if (p.E) {
-        const double* ebase = p.E + (long long)m0 + (long long)n0 * p.lde;
-        for (int L = t128; L < OZ_BN * 8; L += 128) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ebase + (long long)(L >> 3) * p.lde + (L & 7) * 16));
-      }
-    }
     oz_wait(tfull, 0);
     tc_fence_after();
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
     const unsigned lane_addr = tmem_base + ((unsigned)(32 * q) << 16);
     const bool diag_tile = ((p.flags & 1) && (tile_m == blk_n)) || ((p.flags & 8) && (p.row_gtile0 + tile_m == gt));
     const int coff = n0 & 127;
     const double sa = p.scaleA[m0 + row] * p.alpha;
     double* Crow = p.C + (long long)(m0 + row) + (long long)n0 * p.ldc;
     for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-      double sb[16], old[16], ev[16];
-      if (batched) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c0 + j;
-          const bool skip = diag_tile && row > col + coff;
-          sb[j] = p.scaleB[n0 + col];
-          old[j] = (p.beta != 0.0 && !skip) ? Crow[(long long)col * p.ldc] : 0.0;
-          ev[j] = (p.E && !skip) ? p.E[(long long)(m0 + row) + (long long)(n0 + col) * p.lde] : 1.0;
-        }
-      }
       double acc[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = 0.0;
@@ -376,17 +346,6 @@ oz_gemm_kernel(const OzParams p, const __grid_constant__ CUtensorMap mapA, const
         const double w = __hiloint2double((1023 - 7 * d) << 20, 0);   // 2^(-7 d)
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = fma((double)(int)v[j], w, acc[j]);
-      }
-      if (batched) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c0 + j;
-          if (diag_tile && row > col + coff) continue;
-          double r = acc[j] * sa * sb[j];
-          if (p.E) r *= ev[j];
-          Crow[(long long)col * p.ldc] = (p.beta != 0.0) ? fma(p.beta, old[j], r) : r;
-        }
-        continue;
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -577,23 +536,10 @@ __device__ __forceinline__ void oz_gemm_win_body(const OzParams& p, const CUtens
     }
     if (elected) tc_commit(tfull);
   } else {
-    const int q = warp & 3;
-    const int row = 32 * q + lane;
-    const bool batched = !(p.flags & 16384);       // see the epilogue of oz_gemm_kernel
-    if (batched && !ghost) {
-      if (p.beta != 0.0) {
-        const double* cbase = p.C + (long long)m0 + (long long)n0 * p.ldc;
-        for (int L = row; L < BN * 8; L += 128)
-          if (n0 + (L >> 3) < p.N) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(cbase + (long long)(L >> 3) * p.ldc + (L & 7) * 16));
-      }
-      if (p.E) {
-        const double* ebase = p.E + (long long)m0 + (long long)n0 * p.lde;
-        for (int L = row; L < BN * 8; L += 128)
-          if (n0 + (L >> 3) < p.N) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ebase + (long long)(L >> 3) * p.lde + (L & 7) * 16));
-      }
-    }
     oz_wait(tfull, 0);
     tc_fence_after();
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
     const unsigned lane_addr = tmem_base + ((unsigned)(32 * q) << 16);
     // rows below the diagonal of a diagonal tile stay untouched: local product (flag 1) by global index, tile-mapped form
     // (flag 8, BN <= 128 only) by the position inside the 128-block
@@ -605,17 +551,6 @@ __device__ __forceinline__ void oz_gemm_win_body(const OzParams& p, const CUtens
     for (int c0 = 0; c0 < BN; c0 += 16) {
       if (n0 + c0 >= p.N) break;
       if constexpr (MC) { if (ghost) break; }
-      double sb[16], old[16], ev[16];
-      if (batched) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c0 + j;
-          const bool skip = (diag_local && m0 + row > n0 + col) || (diag_map && row > col + coff);
-          sb[j] = p.scaleB[nB + col];
-          old[j] = (p.beta != 0.0 && !skip) ? Crow[(long long)col * p.ldc] : 0.0;
-          ev[j] = (p.E && !skip) ? p.E[(long long)(m0 + row) + (long long)(n0 + col) * p.lde] : 1.0;
-        }
-      }
       double acc[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = 0.0;
@@ -631,18 +566,6 @@ __device__ __forceinline__ void oz_gemm_win_body(const OzParams& p, const CUtens
         const double w = __hiloint2double((1023 - 7 * d) << 20, 0);
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = fma((double)(int)v[j], w, acc[j]);
-      }
-      if (batched) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c0 + j;
-          if (diag_local && m0 + row > n0 + col) continue;
-          if (diag_map && row > col + coff) continue;
-          double r = acc[j] * sa * sb[j];
-          if (p.E) r *= ev[j];
-          Crow[(long long)col * p.ldc] = (p.beta != 0.0) ? fma(p.beta, old[j], r) : r;
-        }
-        continue;
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {

@@ -4,7 +4,10 @@
   3. one model (config 2 golden, N = 8192): F, G, predictive mean / variance and the split-predict mean (Hadamard epilogue) identical
      between the two forms, F and G against the committed oracle golden;
   4. the benchmark model (N = 32768): evaluation time with the option off / on, F and G identical, against the oracle golden.
-python tools/oz_epi_check.py"""
+python tools/oz_epi_check.py
+
+NEEDS profiles/ozaki_batched_epilogue_r2ar.patch applied (git apply) and a rebuild: the shipped library has the serial epilogue only and no
+"ozaki_epi" option.  Record of the one run: profiles/ozaki_batched_epilogue_check_r2ar.log; reading in DESIGN.md section 9."""
 import os
 import sys
 import time
