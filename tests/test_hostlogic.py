@@ -102,3 +102,17 @@ def test_dist_not_posdef(hl):
     A = np.asfortranarray(K)
     Y = np.zeros((512, 128), order="F")
     assert hl.hl_dist_factor(dp(A), ctypes.c_int64(512), ctypes.c_int64(128), 2, dp(Y), ctypes.c_int64(128), 0) == 301
+
+
+def test_unshipped_epilogue_patch_still_applies():
+    """profiles/ozaki_batched_epilogue_r2ar.patch (the batched epilogue of the INT8 kernels: measured, not shipped -- DESIGN.md section 9)
+    must keep applying to the kernel sources, or the record stops being something a maintainer can act on."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    patch = os.path.join(root, "profiles", "ozaki_batched_epilogue_r2ar.patch")
+    assert os.path.exists(patch)
+    if shutil.which("git") is None:
+        pytest.skip("git not available")
+    r = subprocess.run(["git", "apply", "--check", patch], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
